@@ -1,0 +1,185 @@
+"""Generate golden vectors by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the authoring container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/decode_golden.npz and tests/golden/cider_golden.npz. Inputs and weights
+are NOT stored: they are regenerated bit-identically from insenticap_model_b200.synthetic
+(seeded CPU generators); a checksum of each is stored to catch RNG drift.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from insenticap_model_b200 import synthetic as syn  # noqa: E402
+from models.captioner import Captioner as RefCaptioner  # noqa: E402
+from self_critical.utils import get_ciderd_scorer, get_self_critical_reward  # noqa: E402
+from self_critical.cider.pyciderevalcap.ciderD.ciderD_scorer import precook  # noqa: E402
+
+T = 16
+
+
+def build_ref(V, seed, eos_heavy=False):
+    m = RefCaptioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS))
+    m.load_state_dict(syn.synthetic_state_dict(V, seed, eos_heavy=eos_heavy))
+    return m.eval()
+
+
+def words_to_ids(caption, T):
+    ids = [int(w[1:]) + 4 for w in caption.split()] if caption else []
+    if len(ids) < T:
+        ids.append(2)
+    return ids
+
+
+def ref_beam(m, fc, att, sentis, labels, K, constraint, xe_mode=False):
+    B = fc.shape[0]
+    toks = np.zeros((B, K, T), dtype=np.int64)
+    lens = np.zeros((B, K), dtype=np.int32)
+    scores = np.zeros((B, K), dtype=np.float64)
+    with torch.no_grad():
+        for i in range(B):
+            if xe_mode:
+                caps, sc = m.sample(fc[i], att[i], beam_size=K, decoding_constraint=constraint, max_seq_len=T)
+            else:
+                caps, sc = m.sample(fc[i], att[i], sentis[i], labels[i:i + 1], beam_size=K,
+                                    decoding_constraint=constraint, max_seq_len=T)
+            for k in range(K):
+                ids = words_to_ids(caps[k], T)
+                toks[i, k, :len(ids)] = ids
+                lens[i, k] = len(ids)
+                scores[i, k] = sc[k]
+    return toks, lens, scores
+
+
+def checksum(t):
+    return float(t.double().sum())
+
+
+def decode_goldens():
+    out = {}
+    # ---- cfg1: V=10000, B=8 -------------------------------------------------------------
+    V, B = 10000, 8
+    m = build_ref(V, 0)
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=1)
+    out["cfg1_checksum_inputs"] = np.array([checksum(fc), checksum(att), checksum(cpts), checksum(sentis)])
+    out["cfg1_checksum_weights"] = np.array([checksum(v) for v in m.state_dict().values()])
+    with torch.no_grad():
+        seq, lp, mask = m(fc, att, cpts, sentis, labels, T, 1, mode="rl")
+        out["cfg1_greedy_seq"], out["cfg1_greedy_lp"], out["cfg1_greedy_mask"] = seq.numpy(), lp.numpy(), mask.numpy()
+        out["cfg1_fc_embedded"] = m.fc_feats.numpy()
+        out["cfg1_cpt_feats"] = m.cpt_feats.numpy()
+        out["cfg1_cont_weights_sum"] = m.cont_weights.double().sum(0).numpy()  # [T*196]
+        out["cfg1_senti_weights"] = m.senti_weights.numpy()  # [B, T*11]
+        out["cfg1_gate_weights"] = m.cont_senti_weights.numpy()  # [B, T]
+    tk, ln, sc = ref_beam(m, fc, att, sentis, labels, 3, 1)
+    out["cfg1_beam3_tokens"], out["cfg1_beam3_lens"], out["cfg1_beam3_scores"] = tk, ln, sc
+    tk, ln, sc = ref_beam(m, fc[:2], att[:2], None, None, 3, 1, xe_mode=True)
+    out["cfg1_beam3xe_tokens"], out["cfg1_beam3xe_lens"], out["cfg1_beam3xe_scores"] = tk, ln, sc
+    # teacher-forced xe / seq2seq log-probs at the target ids
+    caps = syn.synthetic_captions(B, V, T + 1, seed=2)
+    with torch.no_grad():
+        lpx = m(fc, att, cpts, caps, labels, mode="xe")  # [B,T,V]
+        out["cfg1_xe_lp_target"] = lpx.gather(2, caps[:, 1:].unsqueeze(2)).squeeze(2).numpy()
+        out["cfg1_xe_lp_max"] = lpx.max(2).values.numpy()
+        out["cfg1_xe_argmax"] = lpx.argmax(2).numpy()
+        lps = m(caps, cpts, sentis, labels, mode="seq2seq")
+        out["cfg1_s2s_lp_target"] = lps.gather(2, caps[:, 1:].unsqueeze(2)).squeeze(2).numpy()
+        out["cfg1_s2s_argmax"] = lps.argmax(2).numpy()
+    # one forward_step from a non-zero state (rl mode), top-8 per row
+    g = torch.Generator().manual_seed(7)
+    h0 = torch.randn(2, B, 512, generator=g) * 0.3
+    c0 = torch.randn(2, B, 512, generator=g) * 0.3
+    it = torch.randint(0, V, (B,), generator=g)
+    with torch.no_grad():
+        fcE = m.fc_embed(fc)
+        a = m.att_embed(att.view(B, -1, 2048))
+        pa = m.att2att(a)
+        sw = m.word_embed(torch.cat([sentis.new_zeros(B, 1), sentis], 1))
+        psw = m.senti2att(sw)
+        sl = m.senti_label_embed(labels)
+        lp1, (h1, c1) = m.forward_step(it, (h0, c0), fcE, a, pa, sw, psw, sl)
+        m.attention._reset_weights()
+    top = lp1.topk(8, dim=1)
+    out["step_top_vals"], out["step_top_idx"] = top.values.numpy(), top.indices.numpy()
+    out["step_h"], out["step_c"] = h1.numpy(), c1.numpy()
+
+    # ---- EOS-heavy: V=64, B=64 ----------------------------------------------------------
+    V2, B2 = 64, 64
+    m2 = build_ref(V2, 5, eos_heavy=True)
+    fc2, att2, cpts2, sentis2, labels2 = syn.synthetic_inputs(B2, V2, seed=11)
+    with torch.no_grad():
+        seq, lp, mask = m2(fc2, att2, cpts2, sentis2, labels2, T, 1, mode="rl")
+    out["eos_greedy_seq"], out["eos_greedy_lp"], out["eos_greedy_mask"] = seq.numpy(), lp.numpy(), mask.numpy()
+    for K, cons in ((3, 1), (5, 1), (3, 0)):
+        tk, ln, sc = ref_beam(m2, fc2[:24], att2[:24], sentis2, labels2, K, cons)
+        out[f"eos_beam{K}c{cons}_tokens"], out[f"eos_beam{K}c{cons}_lens"], out[f"eos_beam{K}c{cons}_scores"] = tk, ln, sc
+    print("eos greedy lengths:", sorted(set(mask.sum(1).int().tolist())))
+    print("eos beam3 top-1 lengths:", sorted(set(out["eos_beam3c1_lens"][:, 0].tolist())))
+    np.savez_compressed(os.path.join(HERE, "decode_golden.npz"), **out)
+    print("cfg1 greedy row0:", out["cfg1_greedy_seq"][0], out["cfg1_greedy_lp"][0, :3])
+    print("cfg1 beam3 img0 scores:", out["cfg1_beam3_scores"][0])
+
+
+def cider_goldens():
+    V, N = 1000, 96
+    refs = syn.synthetic_references(N, V, 5, seed=3)
+    fns = ["img%d" % i for i in range(N)]
+    split = {"train": {fn: refs[i] for i, fn in enumerate(fns[:64])},
+             "val": {fn: refs[64 + i] for i, fn in enumerate(fns[64:])}}
+    scorer = get_ciderd_scorer(split, 1, 2)
+    g = torch.Generator().manual_seed(9)
+    B = 64
+    sample = torch.zeros(B, T, dtype=torch.long)
+    greedy = torch.zeros(B, T, dtype=torch.long)
+    for i in range(B):
+        for dst, j in ((sample, 0), (greedy, 1)):
+            r = refs[i][(i + j) % 5][1:-1]  # a reference, perturbed
+            ids = list(r)
+            for q in range(len(ids)):
+                if float(torch.rand(1, generator=g)) < 0.3:
+                    ids[q] = int(torch.randint(0, 60, (1,), generator=g))
+            ids = ids[: int(torch.randint(0, len(ids) + 1, (1,), generator=g))] if i % 7 == 0 else ids
+            ids = (ids + [2])[:T]
+            dst[i, :len(ids)] = torch.tensor(ids)
+    sample[5] = 0
+    sample[5, 0] = 2  # EOS-only hypothesis
+    greedy[6] = torch.randint(4, V, (T,), generator=g)  # no EOS at all, 16 words
+    gt = {fn: refs[i] for i, fn in enumerate(fns[:B])}
+    rewards = get_self_critical_reward(sample, greedy, fns[:B], gt, 1, 2, scorer)
+    # raw scores for sample and greedy separately
+    from self_critical.utils import _array_to_str
+    res = [{"image_id": fns[i], "caption": [_array_to_str(sample[i].numpy(), 1, 2)]} for i in range(B)]
+    res += [{"image_id": fns[i], "caption": [_array_to_str(greedy[i].numpy(), 1, 2)]} for i in range(B)]
+    gts = {fns[i]: [_array_to_str(c, 1, 2) for c in refs[i]] for i in range(B)}
+    _, scores = scorer.compute_score(gts, res)
+    # n-gram count dump for the first 8 sample strings: sorted (ngram tuple as ints, count)
+    dump = []
+    for i in range(8):
+        cnt = precook(_array_to_str(sample[i].numpy(), 1, 2))
+        rows = sorted((tuple(int(w) for w in k), v) for k, v in cnt.items())
+        flat = []
+        for k, v in rows:
+            flat.append(list(k) + [-1] * (4 - len(k)) + [v])
+        dump.append(np.array(flat, dtype=np.int64))
+    df_items = sorted((tuple(int(w) for w in k), v) for k, v in scorer.cider_scorer.document_frequency.items()
+                      if v > 0)
+    df_arr = np.array([list(k) + [-1] * (4 - len(k)) + [int(v)] for k, v in df_items], dtype=np.int64)
+    out = {"sample": sample.numpy(), "greedy": greedy.numpy(), "rewards": rewards, "scores": scores,
+           "ref_len": np.array(float(scorer.cider_scorer.ref_len)), "df": df_arr}
+    for i, d in enumerate(dump):
+        out[f"ngrams_{i}"] = d
+    np.savez_compressed(os.path.join(HERE, "cider_golden.npz"), **out)
+    print("cider scores head:", scores[:6], "EOS-only:", scores[5], "n df entries:", len(df_arr))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    decode_goldens()
+    cider_goldens()
