@@ -1,0 +1,234 @@
+/*
+ * isc.h — C ABI of libisc_b200.so: the B200 (sm_100a) caption-decode hot path of InSentiCap.
+ *
+ * The reference (ezeli/InSentiCap_model) is pure Python/PyTorch and has NO FFI, plugin or
+ * operator interface; its boundary for this path is the Python
+ * surface of `Captioner` and two reward helpers. Each entry point below names the reference
+ * function it replaces (paths relative to the reference root); the Python binding a
+ * maintainer would add is a ctypes stub, shown in INTEGRATION.md and implemented in
+ * insenticap_model_b200/_lib.py.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - every function returns int: 0 = ok, < 0 = invalid argument (message via
+ *     isc_last_error(), thread-local), > 0 = cudaError_t of a failed launch/API call.
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`.
+ *   - the caller owns every buffer, including the workspace whose size the
+ *     `*_workspace_bytes` queries return; the library never allocates device memory,
+ *     never synchronises, and enqueues all work on the given stream (CUDA-graph capturable).
+ *   - there is no CPU fallback: on a device that is not sm_100 every compute entry point
+ *     returns ISC_ERR_DEVICE.
+ */
+#ifndef ISC_H_
+#define ISC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#pragma GCC visibility push(default)
+
+typedef void* isc_stream_t; /* cudaStream_t */
+
+#define ISC_OK 0
+#define ISC_ERR_ARG (-1)
+#define ISC_ERR_WORKSPACE (-2)
+#define ISC_ERR_DEVICE (-3)
+#define ISC_ERR_UNSUPPORTED (-4)
+
+/* arithmetic of the dense contractions (SURVEY.md section 0 / 7 "hard parts" #1) */
+#define ISC_PREC_FP32 0   /* fp32 FMA GEMMs on CUDA cores, fp32 features: debugging / strictest parity */
+#define ISC_PREC_BF16X3 1 /* tcgen05, split-bf16 hi*hi + lo*hi + hi*lo, fp32 accumulate, fp32 features */
+#define ISC_PREC_BF16 2   /* tcgen05, single bf16 pass, fp32 accumulate, bf16 projected features */
+
+/* Model geometry. hidden covers word_emb = feat_emb = rnn_hid = att_hid (opts.py:80-95). */
+typedef struct isc_dims {
+  int32_t vocab;      /* V */
+  int32_t hidden;     /* 512 (only value compiled in) */
+  int32_t feat_dim;   /* 2048: fc_feat_dim == att_feat_dim */
+  int32_t n_regions;  /* 196 */
+  int32_t n_senti;    /* 11 = 10 sentiment words + the prepended PAD (captioner.py:307-309) */
+  int32_t n_labels;   /* 3 sentiment categories */
+  int32_t pad_id, sos_id, eos_id, unk_id; /* captioner.py:125-128 */
+} isc_dims_t;
+
+/* fp32 parameters, one pointer per tensor of Captioner.state_dict() (captioner.py:121-161). */
+typedef struct isc_weights {
+  const float* word_embed;        /* [V,H]  word_embed.0.weight */
+  const float* senti_label_embed; /* [n_labels,H] */
+  const float* fc_embed_w;  const float* fc_embed_b;   /* [H,D],[H] */
+  const float* cpt2fc_w;    const float* cpt2fc_b;     /* [H,H],[H] */
+  const float* att_embed_w; const float* att_embed_b;  /* [H,D],[H] */
+  const float* att_lstm_w_ih; const float* att_lstm_w_hh; /* [4H,3H] (in: h_lang|fc|xt), [4H,H] */
+  const float* att_lstm_b_ih; const float* att_lstm_b_hh; /* [4H] */
+  const float* att2att_w;   const float* att2att_b;    /* [H,H],[H] */
+  const float* senti2att_w; const float* senti2att_b;  /* captioner-level senti2att.0 */
+  const float* ca_h2att_w;  const float* ca_h2att_b;   /* attention.cont_att.h2att */
+  const float* ca_alpha_w;  const float* ca_alpha_b;   /* attention.cont_att.att_alpha [1,H],[1] */
+  const float* sa_h2word_w; const float* sa_h2word_b;  /* attention.senti_att.h2word */
+  const float* sa_label2word_w; const float* sa_label2word_b;
+  const float* sa_alpha_w;  const float* sa_alpha_b;   /* attention.senti_att.word_alpha */
+  const float* g_h2att_w;   const float* g_h2att_b;    /* attention.h2att */
+  const float* g_cont2att_w; const float* g_cont2att_b;
+  const float* g_senti2att_w; const float* g_senti2att_b;
+  const float* g_alpha_w;   const float* g_alpha_b;    /* attention.att_alpha */
+  const float* lang_lstm_w_ih; const float* lang_lstm_w_hh; /* [4H,2H] (in: att|h_att), [4H,H] */
+  const float* lang_lstm_b_ih; const float* lang_lstm_b_hh;
+  const float* classifier_w; const float* classifier_b; /* [V,H],[V] */
+} isc_weights_t;
+
+/* Step-invariant per-image features (output of isc_prologue, input of the decode calls).
+ * NULL members select the reference's mode switches (captioner.py:98-103, :171-172):
+ * att == NULL -> seq2seq (sentiment attention only); sw == NULL -> xe (content only). */
+typedef struct isc_feats {
+  float* fc;        /* [B,H]   ReLU(fc_embed(fc_feats)); in seq2seq mode = cpt_feats */
+  void*  att;       /* [B,L,H] ReLU(att_embed(att_feats)); fp32, or bf16 when ISC_PREC_BF16 */
+  void*  p_att;     /* [B,L,H] ReLU(att2att(att)); same dtype as att */
+  float* sw;        /* [B,S,H] ReLU(word_embed([PAD|senti_words])) */
+  float* p_sw;      /* [B,S,H] ReLU(senti2att(sw)) */
+  float* sl;        /* [B,H]   ReLU(senti_label_embed(labels)) */
+  float* pre_gates; /* [B,4H]  W_ih[:,H:2H]·fc + W_ih[:,2H:3H]·sl + b_ih + b_hh (hoisted) */
+  float* pre_word;  /* [B,H]   label2word(sl) (hoisted out of SentiAttention.forward) */
+  float* cpt_feats; /* [B,H]   ReLU(cpt2fc(mean ReLU(word_embed(cpt_words)))) or NULL */
+} isc_feats_t;
+
+const char* isc_version(void);
+const char* isc_last_error(void);
+
+/* 0 if the current CUDA device is sm_100 (B200), ISC_ERR_DEVICE otherwise. */
+int isc_check_device(void);
+
+/* ---- weights ---------------------------------------------------------------------------
+ * Fuse / concatenate / split the fp32 parameters into the layouts the kernels read
+ * (K-concatenated LSTM and projection matrices, summed biases, bf16 hi/lo planes).
+ * Re-run after every optimiser step. Replaces nothing in the reference (it uses the
+ * nn.Module tensors directly); it is the price of the fused step. */
+size_t isc_packed_weights_bytes(const isc_dims_t* dims, int precision);
+int isc_pack_weights(const isc_dims_t* dims, const isc_weights_t* w, int precision,
+                     void* packed, size_t packed_bytes, isc_stream_t stream);
+
+/* ---- prologue: Captioner.forward_rl :294-315, forward_xe :198-214, sample :357-376,
+ *      forward_seq2seq :247-261 (eval-mode: dropout is the identity) -----------------------
+ * fc_feats [B,D], att_feats [B,L,D] fp32 (both NULL with seq2seq != 0);
+ * cpt_words int64 [B,n_cpt] or NULL; senti_words int64 [B,S-1] or NULL; senti_labels int64 [B]
+ * or NULL. Writes every non-NULL member of *out. */
+size_t isc_prologue_workspace_bytes(const isc_dims_t* dims, int precision, int B);
+int isc_prologue(const isc_dims_t* dims, const void* packed, int precision,
+                 const float* fc_feats, const float* att_feats,
+                 const int64_t* cpt_words, int n_cpt,
+                 const int64_t* senti_words, const int64_t* senti_labels,
+                 int B, int seq2seq, const isc_feats_t* out,
+                 void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* Recompute only the hoisted terms (pre_gates, pre_word) from feats->fc / feats->sl:
+ * used when the caller supplies already-embedded features (Captioner.forward_step API). */
+int isc_hoist(const isc_dims_t* dims, const void* packed, int precision, int B,
+              const isc_feats_t* feats, void* workspace, size_t workspace_bytes,
+              isc_stream_t stream);
+
+/* ---- one decode step: Captioner.forward_step, captioner.py:168-186 -------------------------
+ * M rows; row m uses image m / rows_per_image. it int64 [M]; h_in/c_in/h_out/c_out fp32
+ * [2,M,H] (index 0 attention LSTM, 1 language LSTM). logprobs fp32 [M, ld_logprobs >= V]
+ * receives log_softmax(classifier(h_lang)). Optional attention weights (NULL to skip):
+ * cont_w [M,L], senti_w [M,S], gate_w [M] (Attention._get_weights, captioner.py:83-94). */
+size_t isc_decode_workspace_bytes(const isc_dims_t* dims, int precision, int M);
+int isc_decode_step(const isc_dims_t* dims, const void* packed, int precision,
+                    const isc_feats_t* feats, int rows_per_image, int M,
+                    const int64_t* it, const float* h_in, const float* c_in,
+                    float* h_out, float* c_out, float* logprobs, int64_t ld_logprobs,
+                    float* cont_w, float* senti_w, float* gate_w,
+                    void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- batched greedy / sampled decode: Captioner.forward_rl loop, captioner.py:317-349 ------
+ * sample_mode 0: argmax (sample_max=1). 1: Gumbel-max with caller noise fp32 [T,B,V]
+ * (argmax(logprobs + noise), the reproducible stand-in for torch.multinomial).
+ * 2: Gumbel-max with a counter-based generator keyed by (seed, t, row, word).
+ * Outputs seq int64 [B,T], seq_logprobs fp32 [B,T], seq_masks fp32 [B,T]; semantics incl. the
+ * whole-batch early stop (columns after it stay zero) follow :337-344.
+ * Optional weights: cont_w [B,T,L], senti_w [B,T,S], gate_w [B,T] (zero after the stop). */
+int isc_decode_greedy(const isc_dims_t* dims, const void* packed, int precision,
+                      const isc_feats_t* feats, int B, int T, int sample_mode,
+                      const float* noise, uint64_t seed,
+                      int64_t* seq, float* seq_logprobs, float* seq_masks,
+                      float* cont_w, float* senti_w, float* gate_w,
+                      void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- batched beam search: Captioner.sample, captioner.py:378-420, for B images at once -----
+ * K = beam_size <= 8. tokens int64 [B,K,T] (EOS included, zero padded), scores fp64 [B,K]
+ * (running fp64 sums of fp32 log-probs, :404-407), lengths int32 [B,K]. Beams sorted by score,
+ * ties in pool order (parent, then rank) like the reference's stable sort (:409). */
+int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision,
+                    const isc_feats_t* feats, int B, int K, int T, int decoding_constraint,
+                    int64_t* tokens, double* scores, int32_t* lengths,
+                    void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- teacher forcing: forward_xe :216-240 / forward_seq2seq :263-288 with ss_prob = 0 -------
+ * inputs int64 [B, ld_inputs]; feeds inputs[:, i] for i < n_steps; logprobs fp32
+ * [B, n_steps, V] (the tensor the reference returns). Forward only. */
+int isc_teacher_forced(const isc_dims_t* dims, const void* packed, int precision,
+                       const isc_feats_t* feats, int B, int n_steps,
+                       const int64_t* inputs, int64_t ld_inputs, float* logprobs,
+                       void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- dense contraction on its own (validation / profiling of the tensor-core kernel) -------
+ * C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]), fp32 in/out; act 0 none, 1 ReLU, 2 tanh.
+ * With ISC_PREC_BF16X3 / ISC_PREC_BF16 the operands are split to bf16 planes in the
+ * workspace and multiplied by the tcgen05 kernel. */
+size_t isc_gemm_workspace_bytes(int precision, int M, int N, int K);
+int isc_gemm_tn(int precision, const float* A, int64_t lda, const float* W, int64_t ldw,
+                const float* bias, float* C, int64_t ldc, int M, int N, int K, int act,
+                void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- CIDEr-D reward: self_critical/utils.py:56-83 + ciderD_scorer.py:13-192 ------------------
+ * Captions are id arrays. A reference set is ref_tokens int32 [R, ref_ld] with ref_lens [R]
+ * (words AFTER utils._array_to_str: SOS stripped, cut at EOS, EOS appended) and
+ * img_offsets int32 [N+1] (image i owns refs img_offsets[i] .. img_offsets[i+1]-1).
+ * The document-frequency table is an open-addressing hash of EXACT packed n-gram keys
+ * (16 bit per token, so vocab <= 65534): table_slots a power of two >= 2 x distinct n-grams. */
+size_t isc_cider_table_bytes(int64_t table_slots);
+int isc_cider_build_df(const int32_t* ref_tokens, const int32_t* ref_lens, int32_t ref_ld,
+                       const int32_t* img_offsets, int32_t n_images,
+                       void* table, int64_t table_slots, int32_t* overflow_flag,
+                       isc_stream_t stream);
+/* hyps int64 [n_hyp, T] raw decoder output (leading SOS stripped, cut at first EOS, EOS
+ * appended — utils._array_to_str); hyp_img int32 [n_hyp] indexes img_offsets. log_n_docs =
+ * log(number of images the table was built from). scores fp64 [n_hyp] = CIDEr-D x 10. */
+int isc_cider_score(const void* table, int64_t table_slots, double log_n_docs,
+                    const int64_t* hyps, int32_t T, const int32_t* hyp_img, int32_t n_hyp,
+                    const int32_t* ref_tokens, const int32_t* ref_lens, int32_t ref_ld,
+                    const int32_t* img_offsets, int32_t sos_id, int32_t eos_id,
+                    double* scores, isc_stream_t stream);
+/* rewards fp64 [B,T] = (scores[b] - scores[B + b]) repeated over T (utils.py:81-82). */
+int isc_self_critical_reward(const double* scores, int32_t B, int32_t T, double* rewards,
+                             isc_stream_t stream);
+/* n-gram term frequencies of one hypothesis, for parity tests: keys uint64 [<=64],
+ * counts int32 [<=64], n_out int32 [1]. */
+int isc_cider_ngram_counts(const int64_t* hyp, int32_t T, int32_t sos_id, int32_t eos_id,
+                           uint64_t* keys, int32_t* counts, int32_t* n_out, isc_stream_t stream);
+
+/* ---- measurement hooks (bench.py) -----------------------------------------------------------
+ * isc_launch_count: kernels this library has launched in this process (monotonic).
+ * Profiling: when enabled, every launch is bracketed by CUDA events on its own stream and its
+ * algorithmic work is booked per kernel class; isc_profile_read synchronises the recorded events
+ * and returns the class totals since the last isc_profile_reset. Do not enable inside a CUDA-graph
+ * capture. work = flops (GEMM classes: 2*M*N*K*passes) or HBM bytes (all other classes). */
+#define ISC_K_GEMM_TC 0
+#define ISC_K_GEMM_SIMT 1
+#define ISC_K_ATTENTION 2
+#define ISC_K_LSTM 3
+#define ISC_K_POINTWISE 4 /* embed/pack, gate mix, prologue gathers, plane split, fills */
+#define ISC_K_SELECT 5    /* log_softmax, greedy pick, beam expansion + merge */
+#define ISC_K_CIDER 6
+#define ISC_K_NUM 7
+uint64_t isc_launch_count(void);
+int isc_profile_enable(int on);
+int isc_profile_reset(void);
+int isc_profile_read(int kernel_class, double* total_ms, double* total_work, int64_t* launches);
+
+#pragma GCC visibility pop
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISC_H_ */

@@ -1,0 +1,408 @@
+"""Drop-in ``Captioner`` whose decode path runs on libisc_b200.so (hand-written sm_100a CUDA).
+
+Mirrors the Python surface of /root/reference/models/captioner.py:121-424 — constructor,
+parameter names (``state_dict`` keys load verbatim), ``init_hidden``, ``forward_step``,
+``forward(mode=...)``, ``forward_xe`` / ``forward_seq2seq`` / ``forward_rl``, ``sample``,
+``get_optim_criterion`` and the post-call attributes — plus a batched ``beam_search``.
+
+PyTorch is plumbing here (parameters, device memory, streams); every FLOP of the path is in the
+C-ABI library. There is no CPU and no eager-PyTorch fallback: calling a compute method with the
+library missing, on CPU tensors, or on a non-sm_100 device raises.
+
+Scope of this build: inference-mode semantics (dropout = identity, ss_prob = 0). Calling
+forward_xe / forward_seq2seq / forward_rl with ``self.training`` set raises — the autograd
+(backward) path of the fused step is not built yet (DESIGN.md "out of scope this round").
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class _ContentAttentionParams(nn.Module):
+    """Parameter holder for attention.cont_att.* (reference ContentAttention, captioner.py:12-16)."""
+
+    def __init__(self, s):
+        super().__init__()
+        self.h2att = nn.Linear(s["rnn_hid_dim"], s["att_hid_dim"])
+        self.att_alpha = nn.Linear(s["att_hid_dim"], 1)
+
+
+class _SentiAttentionParams(nn.Module):
+    """Parameter holder for attention.senti_att.* (reference SentiAttention, captioner.py:38-43)."""
+
+    def __init__(self, s):
+        super().__init__()
+        self.h2word = nn.Linear(s["rnn_hid_dim"], s["att_hid_dim"])
+        self.label2word = nn.Linear(s["word_emb_dim"], s["att_hid_dim"])
+        self.word_alpha = nn.Linear(s["att_hid_dim"], 1)
+
+
+class _AttentionParams(nn.Module):
+    """Parameter holder for attention.* (reference Attention, captioner.py:65-74)."""
+
+    def __init__(self, s):
+        super().__init__()
+        self.cont_att = _ContentAttentionParams(s)
+        self.senti_att = _SentiAttentionParams(s)
+        self.h2att = nn.Linear(s["rnn_hid_dim"], s["att_hid_dim"])
+        self.cont2att = nn.Linear(s["feat_emb_dim"], s["att_hid_dim"])
+        self.senti2att = nn.Linear(s["feat_emb_dim"], s["att_hid_dim"])
+        self.att_alpha = nn.Linear(s["att_hid_dim"], 1)
+
+
+class XECriterion(nn.Module):
+    """Masked NLL (reference XECriterion, captioner.py:427-440)."""
+
+    def forward(self, pred, target, lengths):
+        max_len = max(lengths)
+        lens = torch.as_tensor(list(lengths), device=pred.device).unsqueeze(1)
+        mask = (torch.arange(max_len, device=pred.device).unsqueeze(0) < lens).to(pred.dtype)
+        nll = -pred.gather(2, target.unsqueeze(2)).squeeze(2) * mask
+        return nll.sum() / mask.sum()
+
+
+class Captioner(nn.Module):
+    def __init__(self, idx2word, sentiment_categories, settings, precision: str = "bf16x3"):
+        super().__init__()
+        s = settings
+        dims = {s["word_emb_dim"], s["feat_emb_dim"], s["rnn_hid_dim"], s["att_hid_dim"]}
+        if dims != {512}:
+            raise ValueError("libisc_b200 is compiled for word/feat/rnn/att dims of 512, got %s" % sorted(dims))
+        if s["fc_feat_dim"] != s["att_feat_dim"]:
+            raise ValueError("fc_feat_dim must equal att_feat_dim")
+        self.idx2word = idx2word
+        self.pad_id = idx2word.index("<PAD>")
+        self.unk_id = idx2word.index("<UNK>")
+        has_sos = "<SOS>" in idx2word
+        self.sos_id = idx2word.index("<SOS>") if has_sos else self.pad_id
+        self.eos_id = idx2word.index("<EOS>") if has_sos else self.pad_id
+        self.neu_idx = sentiment_categories.index("neutral")
+        self.vocab_size = len(idx2word)
+        self.settings = dict(s)
+
+        E, F, Hd, A = s["word_emb_dim"], s["feat_emb_dim"], s["rnn_hid_dim"], s["att_hid_dim"]
+        self.drop = nn.Dropout(s["dropout_p"])
+        self.word_embed = nn.Sequential(nn.Embedding(self.vocab_size, E, padding_idx=self.pad_id), nn.ReLU())
+        self.senti_label_embed = nn.Sequential(nn.Embedding(len(sentiment_categories), E), nn.ReLU())
+        self.fc_embed = nn.Sequential(nn.Linear(s["fc_feat_dim"], F), nn.ReLU())
+        self.cpt2fc = nn.Sequential(nn.Linear(E, F), nn.ReLU())
+        self.att_embed = nn.Sequential(nn.Linear(s["att_feat_dim"], F), nn.ReLU())
+        self.att_lstm = nn.LSTMCell(Hd + F + E, Hd)
+        self.att2att = nn.Sequential(nn.Linear(F, A), nn.ReLU())
+        self.senti2att = nn.Sequential(nn.Linear(E, A), nn.ReLU())
+        self.attention = _AttentionParams(s)
+        self.lang_lstm = nn.LSTMCell(Hd + F, Hd)
+        self.classifier = nn.Linear(Hd, self.vocab_size)
+
+        self.n_labels = len(sentiment_categories)
+        self.n_regions = 196
+        self.num_senti_words = 10
+        self.collect_attention_weights = True
+        self.set_precision(precision)
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+        self.cont_weights = self.senti_weights = self.cont_senti_weights = []
+        self.fc_feats = self.cpt_feats = None
+
+    # ------------------------------------------------------------------ plumbing
+    def set_precision(self, precision: str):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(_lib.PRECISIONS))
+        self.precision = precision
+        self._prec = _lib.PRECISIONS[precision]
+        self._packed_key = None
+
+    def _device(self):
+        dev = self.classifier.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("Captioner parameters are on %s: the decode path only exists as sm_100a CUDA "
+                               "kernels, move the module to a B200 (`.cuda()`); there is no CPU fallback" % dev)
+        return dev
+
+    def _dims(self, n_regions=None, n_senti=None):
+        return _lib.Dims(self.vocab_size, 512, self.settings["att_feat_dim"],
+                         n_regions or self.n_regions, n_senti or (self.num_senti_words + 1), self.n_labels,
+                         self.pad_id, self.sos_id, self.eos_id, self.unk_id)
+
+    def _workspace(self, kind, nbytes, dev):
+        key = (kind, dev.index)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+            self._ws[key] = buf
+        return buf
+
+    def pack_weights(self, force=False):
+        """Fuse/split the fp32 parameters into the kernel layouts (isc_pack_weights). Re-packs when any
+        parameter was modified in place or replaced (optimizer step, load_state_dict)."""
+        dev = self._device()
+        lib = _lib.load()
+        sd = {k: v for k, v in self.named_parameters()}
+        key = (self._prec, dev.index) + tuple((p.data_ptr(), p._version) for p in sd.values())
+        if not force and self._packed is not None and key == self._packed_key:
+            return self._packed
+        w = _lib.Weights()
+        keep = []
+        for field, name in _lib.WEIGHT_FIELDS:
+            t = sd[name].detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            setattr(w, field, t.data_ptr())
+        d = self._dims()
+        nbytes = lib.isc_packed_weights_bytes(C.byref(d), self._prec)
+        if nbytes == 0:
+            _lib.check(-1, "isc_packed_weights_bytes")
+        if self._packed is None or self._packed.numel() < nbytes or self._packed.device != dev:
+            self._packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_pack_weights(C.byref(d), C.byref(w), self._prec, _lib.ptr(self._packed), nbytes,
+                                            _lib.stream_ptr(dev)), "isc_pack_weights")
+        self._packed_key = key
+        return self._packed
+
+    def _feat_dtype(self):
+        return torch.bfloat16 if self._prec == _lib.PREC_BF16 else torch.float32
+
+    def _make_feats(self, tensors):
+        f = _lib.Feats()
+        for name in _lib.FEAT_FIELDS:
+            t = tensors.get(name)
+            setattr(f, name, t.data_ptr() if t is not None else None)
+        return f
+
+    def _check_inference(self, what):
+        if self.training:
+            raise NotImplementedError(
+                "%s in training mode (dropout / scheduled sampling / autograd) is not built yet; "
+                "call .eval() — the B200 path currently covers inference-mode decoding only" % what)
+
+    def prologue(self, fc_feats=None, att_feats=None, cpt_words=None, senti_words=None, senti_labels=None,
+                 seq2seq=False):
+        """Step-invariant features (isc_prologue). Returns (dict of tensors, B)."""
+        dev = self._device()
+        lib = _lib.load()
+        packed = self.pack_weights()
+        ref = fc_feats if fc_feats is not None else cpt_words
+        B = ref.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = {}
+        n_regions, S = self.n_regions, self.num_senti_words + 1
+        if not seq2seq:
+            fc_feats = fc_feats.reshape(B, -1).float().contiguous()
+            att_feats = att_feats.reshape(B, -1, att_feats.shape[-1]).float().contiguous()
+            n_regions = att_feats.shape[1]
+            t["att"] = torch.empty(B, n_regions, 512, dtype=self._feat_dtype(), device=dev)
+            t["p_att"] = torch.empty_like(t["att"])
+        t["fc"] = torch.empty(B, 512, **f32)
+        t["pre_gates"] = torch.empty(B, 2048, **f32)
+        if cpt_words is not None:
+            cpt_words = cpt_words.long().contiguous()
+            t["cpt_feats"] = torch.empty(B, 512, **f32)
+        if senti_words is not None:
+            senti_words = senti_words.reshape(B, -1).long().contiguous()
+            S = senti_words.shape[1] + 1
+            t["sw"] = torch.empty(B, S, 512, **f32)
+            t["p_sw"] = torch.empty(B, S, 512, **f32)
+        if senti_labels is not None:
+            senti_labels = senti_labels.reshape(B).long().contiguous()
+            t["sl"] = torch.empty(B, 512, **f32)
+            t["pre_word"] = torch.empty(B, 512, **f32)
+        d = self._dims(n_regions, S)
+        feats = self._make_feats(t)
+        nbytes = lib.isc_prologue_workspace_bytes(C.byref(d), self._prec, B)
+        ws = self._workspace("prologue", nbytes, dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_prologue(
+                C.byref(d), _lib.ptr(packed), self._prec,
+                _lib.ptr(fc_feats) if not seq2seq else None, _lib.ptr(att_feats) if not seq2seq else None,
+                _lib.ptr(cpt_words), cpt_words.shape[1] if cpt_words is not None else 0,
+                _lib.ptr(senti_words), _lib.ptr(senti_labels), B, 1 if seq2seq else 0, C.byref(feats),
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_prologue")
+        t["_dims"] = d
+        return t, B
+
+    def _decode_ws(self, d, M, dev):
+        lib = _lib.load()
+        nbytes = lib.isc_decode_workspace_bytes(C.byref(d), self._prec, M)
+        return self._workspace("decode", nbytes, dev)
+
+    # ------------------------------------------------------------------ reference API
+    def init_hidden(self, bsz):
+        w = self.classifier.weight
+        return (w.new_zeros([2, bsz, 512]), w.new_zeros([2, bsz, 512]))
+
+    def forward_step(self, it, state, fc_feats, att_feats=None, p_att_feats=None,
+                     senti_word_feats=None, p_senti_word_feats=None, senti_labels=None):
+        """One decode step on ALREADY-EMBEDDED features (captioner.py:168-186).
+        Returns (logprobs [bs, V], (h [2,bs,512], c [2,bs,512]))."""
+        dev = self._device()
+        lib = _lib.load()
+        packed = self.pack_weights()
+        M = it.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        t = {"fc": fc_feats.float().contiguous(), "pre_gates": torch.empty(M, 2048, **f32)}
+        n_regions, S = self.n_regions, self.num_senti_words + 1
+        if att_feats is not None:
+            n_regions = att_feats.shape[1]
+            t["att"] = att_feats.to(self._feat_dtype()).contiguous()
+            t["p_att"] = p_att_feats.to(self._feat_dtype()).contiguous()
+        if senti_word_feats is not None:
+            S = senti_word_feats.shape[1]
+            t["sw"] = senti_word_feats.float().contiguous()
+            t["p_sw"] = p_senti_word_feats.float().contiguous()
+        if senti_labels is not None:
+            t["sl"] = senti_labels.float().contiguous()
+            t["pre_word"] = torch.empty(M, 512, **f32)
+        d = self._dims(n_regions, S)
+        feats = self._make_feats(t)
+        ws = self._decode_ws(d, M, dev)
+        h_in, c_in = state[0].float().contiguous(), state[1].float().contiguous()
+        h_out, c_out = torch.empty_like(h_in), torch.empty_like(c_in)
+        logprobs = torch.empty(M, self.vocab_size, **f32)
+        cw = torch.empty(M, n_regions, **f32) if att_feats is not None else None
+        sw = torch.empty(M, S, **f32) if senti_word_feats is not None else None
+        gw = torch.empty(M, 1, **f32) if (cw is not None and sw is not None) else None
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(lib.isc_hoist(C.byref(d), _lib.ptr(packed), self._prec, M, C.byref(feats), _lib.ptr(ws),
+                                     ws.numel(), st), "isc_hoist")
+            _lib.check(lib.isc_decode_step(
+                C.byref(d), _lib.ptr(packed), self._prec, C.byref(feats), 1, M, _lib.ptr(it.long().contiguous()),
+                _lib.ptr(h_in), _lib.ptr(c_in), _lib.ptr(h_out), _lib.ptr(c_out), _lib.ptr(logprobs),
+                self.vocab_size, _lib.ptr(cw), _lib.ptr(sw), _lib.ptr(gw), _lib.ptr(ws), ws.numel(), st),
+                "isc_decode_step")
+        self._step_weights = (cw, sw, gw)
+        return logprobs, (h_out, c_out)
+
+    def forward(self, *args, **kwargs):
+        mode = kwargs.pop("mode", "xe")
+        return getattr(self, "forward_" + mode)(*args, **kwargs)
+
+    def _teacher_forced(self, t, B, inputs):
+        dev = self._device()
+        lib = _lib.load()
+        d = t["_dims"]
+        n_steps = inputs.shape[1] - 1
+        inputs = inputs.long().contiguous()
+        out = torch.empty(B, n_steps, self.vocab_size, dtype=torch.float32, device=dev)
+        ws = self._decode_ws(d, B, dev)
+        feats = self._make_feats(t)
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_teacher_forced(
+                C.byref(d), _lib.ptr(self._packed), self._prec, C.byref(feats), B, n_steps, _lib.ptr(inputs),
+                inputs.shape[1], _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                "isc_teacher_forced")
+        self.cont_weights = self.senti_weights = self.cont_senti_weights = []
+        return out
+
+    def forward_xe(self, fc_feats, att_feats, cpt_words, captions, senti_labels, ss_prob=0.0):
+        """Teacher-forced log-probs [bs, T-1, V] (captioner.py:194-240), inference semantics."""
+        self._check_inference("forward_xe")
+        t, B = self.prologue(fc_feats, att_feats, cpt_words, None, senti_labels)
+        self.fc_feats, self.cpt_feats = t["fc"], t.get("cpt_feats")
+        return self._teacher_forced(t, B, captions)
+
+    def forward_seq2seq(self, senti_captions, cpt_words, senti_words, senti_labels, ss_prob=0.0):
+        """Sentiment-corpus teacher forcing (captioner.py:242-288), inference semantics."""
+        self._check_inference("forward_seq2seq")
+        t, B = self.prologue(None, None, cpt_words, senti_words, senti_labels, seq2seq=True)
+        return self._teacher_forced(t, B, senti_captions)
+
+    def forward_rl(self, fc_feats, att_feats, cpt_words, senti_words, senti_labels, max_seq_len, sample_max,
+                   noise=None, seed=None):
+        """Batched greedy (sample_max=1) or sampled (sample_max=0) decode (captioner.py:290-349).
+
+        Sampling is Gumbel-max: argmax(logprobs + g). ``noise`` [T,B,V] supplies g explicitly (parity
+        tests); otherwise g comes from a counter-based generator keyed by ``seed`` (drawn from torch's
+        global generator when None, so torch.manual_seed makes it reproducible)."""
+        self._check_inference("forward_rl")
+        dev = self._device()
+        lib = _lib.load()
+        t, B = self.prologue(fc_feats, att_feats, cpt_words, senti_words, senti_labels)
+        self.fc_feats, self.cpt_feats = t["fc"], t.get("cpt_feats")
+        d = t["_dims"]
+        T = int(max_seq_len)
+        f32 = dict(dtype=torch.float32, device=dev)
+        seq = torch.empty(B, T, dtype=torch.long, device=dev)
+        lps = torch.empty(B, T, **f32)
+        masks = torch.empty(B, T, **f32)
+        L, S = d.n_regions, d.n_senti
+        cw = sw = gw = None
+        if self.collect_attention_weights:
+            cw = torch.zeros(B, T, L, **f32)
+            sw = torch.zeros(B, T, S, **f32)
+            gw = torch.zeros(B, T, **f32)
+        if sample_max:
+            mode = 0
+        elif noise is not None:
+            mode = 1
+            noise = noise.to(dev).float().contiguous()
+            assert noise.shape == (T, B, self.vocab_size)
+        else:
+            mode = 2
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        ws = self._decode_ws(d, B, dev)
+        feats = self._make_feats(t)
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_decode_greedy(
+                C.byref(d), _lib.ptr(self._packed), self._prec, C.byref(feats), B, T, mode, _lib.ptr(noise),
+                int(seed or 0), _lib.ptr(seq), _lib.ptr(lps), _lib.ptr(masks), _lib.ptr(cw), _lib.ptr(sw),
+                _lib.ptr(gw), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_decode_greedy")
+        if self.collect_attention_weights:
+            # the reference's lists hold one entry per EXECUTED step (it breaks when every row is done)
+            steps = int(masks.sum(0).gt(0).sum().item())
+            self.cont_weights = cw[:, :steps].reshape(B, steps * L)
+            self.senti_weights = sw[:, :steps].reshape(B, steps * S)
+            self.cont_senti_weights = gw[:, :steps]
+        else:
+            self.cont_weights = self.senti_weights = self.cont_senti_weights = []
+        return seq, lps, masks
+
+    def beam_search(self, fc_feats, att_feats, senti_words=None, senti_labels=None, beam_size=3,
+                    decoding_constraint=1, max_seq_len=16):
+        """Batched beam search: Captioner.sample (captioner.py:351-420) for B images at once.
+        Returns tokens int64 [B,K,T] (EOS included, 0 padded), scores float64 [B,K], lengths int32 [B,K]."""
+        dev = self._device()
+        lib = _lib.load()
+        t, B = self.prologue(fc_feats, att_feats, None, senti_words, senti_labels)
+        d = t["_dims"]
+        K, T = int(beam_size), int(max_seq_len)
+        tokens = torch.empty(B, K, T, dtype=torch.long, device=dev)
+        scores = torch.empty(B, K, dtype=torch.float64, device=dev)
+        lengths = torch.empty(B, K, dtype=torch.int32, device=dev)
+        ws = self._decode_ws(d, B * K, dev)
+        feats = self._make_feats(t)
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_decode_beam(
+                C.byref(d), _lib.ptr(self._packed), self._prec, C.byref(feats), B, K, T,
+                1 if decoding_constraint else 0, _lib.ptr(tokens), _lib.ptr(scores), _lib.ptr(lengths),
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_decode_beam")
+        return tokens, scores, lengths
+
+    def sample(self, fc_feat, att_feat, senti_words=None, senti_label=None, beam_size=3,
+               decoding_constraint=1, max_seq_len=16):
+        """Single-image beam search with the reference's signature and return types
+        (captioner.py:351-420): (list[str] of K captions, list[float] of K scores)."""
+        self.eval()
+        fc = fc_feat.reshape(1, -1)
+        att = att_feat.reshape(1, -1, att_feat.shape[-1])
+        sw = senti_words.reshape(1, -1) if senti_words is not None else None
+        sl = senti_label.reshape(1) if senti_words is not None else None
+        tokens, scores, lengths = self.beam_search(fc, att, sw, sl, beam_size, decoding_constraint, max_seq_len)
+        tokens, scores, lengths = tokens[0].tolist(), scores[0].tolist(), lengths[0].tolist()
+        captions = [" ".join(self.idx2word[w] for w in tokens[k][:lengths[k]] if w != self.eos_id)
+                    for k in range(len(tokens))]
+        self.cont_weights = self.senti_weights = self.cont_senti_weights = []
+        return captions, scores
+
+    def get_optim_criterion(self, lr, weight_decay=0):
+        return (torch.optim.Adam(self.parameters(), lr=lr, weight_decay=weight_decay),
+                XECriterion(), nn.MSELoss())

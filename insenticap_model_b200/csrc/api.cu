@@ -1,0 +1,1002 @@
+// C-ABI entry points (include/isc.h) and the host-side launch sequences of the decode path.
+// No device allocation, no synchronisation: everything is enqueued on the caller's stream into
+// caller-owned buffers, so a whole decode call can be captured in a CUDA graph.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace isc {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ------------------------------------------------------------------ profiler
+namespace prof {
+struct Rec {
+  int kclass;
+  double work;
+  cudaEvent_t e0, e1;
+};
+static std::mutex mu;
+static std::atomic<unsigned long long> launches{0};
+static std::atomic<int> enabled{0};
+static std::vector<Rec> recs;             // records of the current measurement window
+static std::vector<cudaEvent_t> pool;     // recycled events
+static cudaEvent_t get_event() {
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace prof
+
+ProfScope::ProfScope(int kclass, double work, cudaStream_t stream) : slot_(-1), stream_(stream) {
+  prof::launches.fetch_add(1, std::memory_order_relaxed);
+  if (!prof::enabled.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(prof::mu);
+  prof::Rec r;
+  r.kclass = kclass;
+  r.work = work;
+  r.e0 = prof::get_event();
+  r.e1 = prof::get_event();
+  cudaEventRecord(r.e0, stream);
+  prof::recs.push_back(r);
+  slot_ = (int)prof::recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(prof::mu);
+  if (slot_ < (int)prof::recs.size()) cudaEventRecord(prof::recs[slot_].e1, stream_);
+}
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int T_MAX = 64;  // longest caption the beam/greedy bookkeeping buffers are sized for
+
+int check_device() {
+  int dev = 0, major = 0, minor = 0;
+  ISC_CUDA(cudaGetDevice(&dev));
+  ISC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  ISC_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    set_error("device %d is sm_%d%d; libisc_b200 only contains sm_100a code and has no fallback", dev, major, minor);
+    return ISC_ERR_DEVICE;
+  }
+  return 0;
+}
+
+int check_dims(const isc_dims_t* d) {
+  ISC_REQUIRE(d != nullptr, "dims is NULL");
+  ISC_REQUIRE(d->hidden == H, "hidden=%d: only %d is compiled in", d->hidden, H);
+  ISC_REQUIRE(d->vocab >= 8 && d->vocab <= 65534, "vocab=%d out of range [8, 65534]", d->vocab);
+  ISC_REQUIRE(d->feat_dim > 0 && d->feat_dim % 8 == 0, "feat_dim=%d must be a positive multiple of 8", d->feat_dim);
+  ISC_REQUIRE(d->n_regions > 0 && d->n_senti > 0 && d->n_labels > 0, "n_regions/n_senti/n_labels must be positive");
+  return 0;
+}
+int check_precision(int p) {
+  ISC_REQUIRE(p == ISC_PREC_FP32 || p == ISC_PREC_BF16X3 || p == ISC_PREC_BF16, "unknown precision %d", p);
+  return 0;
+}
+
+// ------------------------------------------------------------------ bump allocator
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+// ------------------------------------------------------------------ packed weights
+struct Mat {
+  float* f32 = nullptr;
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  int rows = 0, cols = 0;
+  Operand op() const {
+    Operand o;
+    o.f32 = f32;
+    o.ld = cols;
+    o.hi = hi;
+    o.lo = lo;
+    o.ldp = cols;
+    return o;
+  }
+};
+
+struct Packed {
+  Mat W1, Wpre, W2, W3, W4, W5, Wfc, Watt, Wa2a, Ws2a, Wcpt, Wl2w;
+  float *b1, *b2, *b3, *b4, *b5, *bfc, *batt, *ba2a, *bs2a, *bcpt, *bl2w;
+  float *emb, *lab_emb, *alpha_c, *alpha_s, *alpha_g, *alpha_g_b;
+  size_t total = 0;
+};
+
+Packed carve_packed(const isc_dims_t& d, int precision, void* base) {
+  Bump b(base);
+  Packed p;
+  const int V = d.vocab, D = d.feat_dim;
+  auto mat = [&](Mat& m, int rows, int cols) {
+    m.rows = rows;
+    m.cols = cols;
+    m.f32 = b.take<float>((size_t)rows * cols);
+    if (precision != ISC_PREC_FP32) {
+      m.hi = b.take<bf16>((size_t)rows * cols);
+      if (precision == ISC_PREC_BF16X3) m.lo = b.take<bf16>((size_t)rows * cols);
+    }
+  };
+  mat(p.W1, G4, 3 * H);
+  mat(p.Wpre, G4, 2 * H);
+  mat(p.W2, 3 * H, H);
+  mat(p.W3, H, 2 * H);
+  mat(p.W4, G4, 3 * H);
+  mat(p.W5, V, H);
+  mat(p.Wfc, H, D);
+  mat(p.Watt, H, D);
+  mat(p.Wa2a, H, H);
+  mat(p.Ws2a, H, H);
+  mat(p.Wcpt, H, H);
+  mat(p.Wl2w, H, H);
+  p.b1 = b.take<float>(G4);
+  p.b2 = b.take<float>(3 * H);
+  p.b3 = b.take<float>(H);
+  p.b4 = b.take<float>(G4);
+  p.b5 = b.take<float>(V);
+  p.bfc = b.take<float>(H);
+  p.batt = b.take<float>(H);
+  p.ba2a = b.take<float>(H);
+  p.bs2a = b.take<float>(H);
+  p.bcpt = b.take<float>(H);
+  p.bl2w = b.take<float>(H);
+  p.emb = b.take<float>((size_t)V * H);
+  p.lab_emb = b.take<float>((size_t)d.n_labels * H);
+  p.alpha_c = b.take<float>(H);
+  p.alpha_s = b.take<float>(H);
+  p.alpha_g = b.take<float>(H);
+  p.alpha_g_b = b.take<float>(4);
+  p.total = (b.off + 255) & ~size_t(255);
+  return p;
+}
+
+__global__ void add_vec_kernel(float* dst, const float* a, const float* b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+int copy_block(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int rows, int cols, cudaStream_t s) {
+  ISC_CUDA(cudaMemcpy2DAsync(dst, ld_dst * sizeof(float), src, ld_src * sizeof(float), (size_t)cols * sizeof(float), rows,
+                             cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+int add_vec(float* dst, const float* a, const float* b, int n, cudaStream_t s) {
+  ProfScope ps(ISC_K_POINTWISE, 3.0 * n * sizeof(float), s);
+  add_vec_kernel<<<(n + 255) / 256, 256, 0, s>>>(dst, a, b, n);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int finish_mat(const Mat& m, int precision, cudaStream_t s) {
+  if (precision == ISC_PREC_FP32) return 0;
+  return split_planes(m.f32, m.cols, m.hi, m.lo, m.cols, m.rows, m.cols, s);
+}
+
+// ------------------------------------------------------------------ decode workspace
+struct Planes {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+};
+struct DecodeWs {
+  float *X1, *X2, *gates, *hproj, *cs, *g3, *logits;
+  Planes pX1, pX2, pcs, phL;
+  float* state_h[2];
+  float* state_c[2];
+  long long* it;
+  int* parent;
+  int* unfinished;
+  int* alive_count;
+  int* tok[2];
+  int* len[2];
+  double* score[2];
+  int* alive[2];
+  float* fcsl;
+  Planes pfcsl;
+  long long ld_logits;
+  size_t total;
+};
+
+DecodeWs carve_decode(const isc_dims_t& d, int precision, int M, void* base) {
+  Bump b(base);
+  DecodeWs w;
+  const bool tc = precision != ISC_PREC_FP32;
+  const bool x3 = precision == ISC_PREC_BF16X3;
+  const size_t m = (size_t)M;
+  auto planes = [&](Planes& p, size_t n) {
+    if (tc) {
+      p.hi = b.take<bf16>(n);
+      if (x3) p.lo = b.take<bf16>(n);
+    }
+  };
+  w.X1 = tc ? nullptr : b.take<float>(m * 3 * H);
+  w.X2 = tc ? nullptr : b.take<float>(m * 3 * H);
+  planes(w.pX1, m * 3 * H);
+  planes(w.pX2, m * 3 * H);
+  w.gates = b.take<float>(m * G4);
+  w.hproj = b.take<float>(m * 3 * H);
+  w.cs = b.take<float>(m * 2 * H);
+  planes(w.pcs, m * 2 * H);
+  w.g3 = b.take<float>(m * H);
+  planes(w.phL, m * H);
+  w.ld_logits = (d.vocab + 3) & ~3;
+  w.logits = b.take<float>(m * w.ld_logits);
+  for (int i = 0; i < 2; ++i) {
+    w.state_h[i] = b.take<float>(2 * m * H);
+    w.state_c[i] = b.take<float>(2 * m * H);
+  }
+  w.it = b.take<long long>(m);
+  w.parent = b.take<int>(m);
+  w.unfinished = b.take<int>(m);
+  w.alive_count = b.take<int>(T_MAX);
+  for (int i = 0; i < 2; ++i) {
+    w.tok[i] = b.take<int>(m * T_MAX);
+    w.len[i] = b.take<int>(m);
+    w.score[i] = b.take<double>(m);
+    w.alive[i] = b.take<int>(m);
+  }
+  w.fcsl = b.take<float>(m * 2 * H);
+  planes(w.pfcsl, m * 2 * H);
+  w.total = (b.off + 255) & ~size_t(255);
+  return w;
+}
+
+RowDest rowdest(float* f32, long long ld, const Planes& p, long long ldp) {
+  RowDest r;
+  r.f32 = f32;
+  r.ld = ld;
+  r.hi = p.hi;
+  r.lo = p.lo;
+  r.ldp = ldp;
+  return r;
+}
+Operand operand(const float* f32, long long ld, const Planes& p, long long ldp, long long col = 0) {
+  Operand o;
+  o.f32 = f32 ? f32 + col : nullptr;
+  o.ld = ld;
+  o.hi = p.hi ? p.hi + col : nullptr;
+  o.lo = p.lo ? p.lo + col : nullptr;
+  o.ldp = ldp;
+  return o;
+}
+
+struct Ctx {
+  isc_dims_t d;
+  Packed pk;
+  int precision;
+  const isc_feats_t* f;
+  cudaStream_t s;
+};
+
+// hoisted step-invariant terms: pre_gates = [fc | sl] · Wpre^T + (b_ih + b_hh), pre_word = label2word(sl)
+int run_hoist(const Ctx& c, int B, float* fcsl, const Planes& pfcsl) {
+  const isc_feats_t& f = *c.f;
+  ISC_REQUIRE(f.fc && f.pre_gates, "feats.fc and feats.pre_gates are required");
+  const bool tc = c.precision != ISC_PREC_FP32;
+  const int K = f.sl ? 2 * H : H;
+  ISC_TRY(copy_block(fcsl, 2 * H, f.fc, H, B, H, c.s));
+  if (f.sl) ISC_TRY(copy_block(fcsl + H, 2 * H, f.sl, H, B, H, c.s));
+  if (tc) ISC_TRY(split_planes(fcsl, 2 * H, pfcsl.hi, pfcsl.lo, 2 * H, B, K, c.s));
+  Epilogue ep;
+  ep.bias = c.pk.b1;
+  Dest dst;
+  dst.f32 = f.pre_gates;
+  dst.ld = G4;
+  ISC_TRY(gemm(c.precision, operand(fcsl, 2 * H, pfcsl, 2 * H), c.pk.Wpre.op(), dst, B, G4, K, ep, c.s));
+  if (f.sl && f.pre_word) {
+    Epilogue e2;
+    e2.bias = c.pk.bl2w;
+    Dest d2;
+    d2.f32 = f.pre_word;
+    d2.ld = H;
+    ISC_TRY(gemm(c.precision, operand(fcsl, 2 * H, pfcsl, 2 * H, H), c.pk.Wl2w.op(), d2, B, H, H, e2, c.s));
+  }
+  return 0;
+}
+
+struct StepIO {
+  const long long* it;
+  const int* parent;
+  const float* h_in;
+  const float* c_in;
+  float* h_out;
+  float* c_out;
+  float* logits;
+  long long ld_logits;
+  float* cont_w = nullptr;
+  long long ld_cont_w = 0;
+  float* senti_w = nullptr;
+  long long ld_senti_w = 0;
+  float* gate_w = nullptr;
+  long long ld_gate_w = 0;
+};
+
+// One decode step over M rows (captioner.py:168-186), raw classifier logits out.
+int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
+  const isc_feats_t& f = *c.f;
+  const Packed& pk = c.pk;
+  const int B = M / R;
+  const bool has_att = f.att != nullptr, has_sw = f.sw != nullptr;
+  ISC_REQUIRE(has_att || has_sw, "feats: att and sw are both NULL");
+  ISC_REQUIRE(!has_att || f.p_att, "feats.p_att missing");
+  ISC_REQUIRE(!has_sw || (f.p_sw && f.sl && f.pre_word), "feats.p_sw / sl / pre_word missing");
+  const bool rl = has_att && has_sw;
+  const long long m = M;
+
+  RowDest x1 = rowdest(w.X1, 3 * H, w.pX1, 3 * H);
+  RowDest x2 = rowdest(w.X2, 3 * H, w.pX2, 3 * H);
+  ISC_TRY(launch_embed_pack(io.it, io.parent, io.h_in, M, c.d.vocab, pk.emb, x1, x2, c.s));
+
+  // attention LSTM
+  {
+    Epilogue ep;
+    ep.rowadd = f.pre_gates;
+    ep.ld_rowadd = G4;
+    ep.rows_per_group = R;
+    Dest dst;
+    dst.f32 = w.gates;
+    dst.ld = G4;
+    ISC_TRY(gemm(c.precision, operand(w.X1, 3 * H, w.pX1, 3 * H), pk.W1.op(), dst, M, G4, 3 * H, ep, c.s));
+    ISC_TRY(launch_lstm_pointwise(w.gates, io.parent, io.c_in, io.h_out, io.c_out, x2, H, M, c.s));
+  }
+  // h projections: [cont h2att | senti h2word | gate h2att]
+  {
+    Epilogue ep;
+    ep.bias = pk.b2;
+    Dest dst;
+    dst.f32 = w.hproj;
+    dst.ld = 3 * H;
+    Operand a = c.precision == ISC_PREC_FP32 ? operand(io.h_out, H, Planes(), H) : operand(nullptr, 0, w.pX2, 3 * H, H);
+    ISC_TRY(gemm(c.precision, a, pk.W2.op(), dst, M, 3 * H, H, ep, c.s));
+  }
+  // attention
+  {
+    AttnParams ap;
+    ap.R = R;
+    ap.L = c.d.n_regions;
+    ap.S = c.d.n_senti;
+    ap.hproj = w.hproj;
+    ap.ld_hproj = 3 * H;
+    ap.att = f.att;
+    ap.p_att = f.p_att;
+    ap.sw = f.sw;
+    ap.p_sw = f.p_sw;
+    ap.pre_word = f.pre_word;
+    ap.alpha_c = pk.alpha_c;
+    ap.alpha_s = pk.alpha_s;
+    RowDest cs = rowdest(w.cs, 2 * H, w.pcs, 2 * H);
+    if (rl) {
+      ap.cont_dst = cs;
+      ap.cont_col = 0;
+      ap.senti_dst = cs;
+      ap.senti_col = H;
+    } else {  // xe: content only; seq2seq: sentiment only -> straight into the language-LSTM input
+      ap.cont_dst = x2;
+      ap.cont_col = 0;
+      ap.senti_dst = x2;
+      ap.senti_col = 0;
+    }
+    ap.cont_w = io.cont_w;
+    ap.ld_cont_w = io.ld_cont_w;
+    ap.senti_w = io.senti_w;
+    ap.ld_senti_w = io.ld_senti_w;
+    ISC_TRY(launch_attention(ap, B, c.precision == ISC_PREC_BF16, c.precision == ISC_PREC_BF16, c.s));
+  }
+  if (rl) {
+    Epilogue ep;
+    ep.bias = pk.b3;
+    ep.addmat = w.hproj + 2 * H;
+    ep.ld_addmat = 3 * H;
+    ep.act = ACT_TANH;
+    Dest dst;
+    dst.f32 = w.g3;
+    dst.ld = H;
+    ISC_TRY(gemm(c.precision, operand(w.cs, 2 * H, w.pcs, 2 * H), pk.W3.op(), dst, M, H, 2 * H, ep, c.s));
+    ISC_TRY(launch_gate_mix(w.g3, w.cs, pk.alpha_g, pk.alpha_g_b, x2, io.gate_w, io.ld_gate_w, M, c.s));
+  }
+  // language LSTM
+  {
+    Epilogue ep;
+    ep.bias = pk.b4;
+    Dest dst;
+    dst.f32 = w.gates;
+    dst.ld = G4;
+    ISC_TRY(gemm(c.precision, operand(w.X2, 3 * H, w.pX2, 3 * H), pk.W4.op(), dst, M, G4, 3 * H, ep, c.s));
+    RowDest hl = rowdest(nullptr, 0, w.phL, H);
+    ISC_TRY(launch_lstm_pointwise(w.gates, io.parent, io.c_in + m * H, io.h_out + m * H, io.c_out + m * H, hl, 0, M, c.s));
+  }
+  // classifier logits
+  {
+    Epilogue ep;
+    ep.bias = pk.b5;
+    Dest dst;
+    dst.f32 = io.logits;
+    dst.ld = io.ld_logits;
+    Operand a = operand(io.h_out + m * H, H, w.phL, H);
+    ISC_TRY(gemm(c.precision, a, pk.W5.op(), dst, M, c.d.vocab, H, ep, c.s));
+  }
+  return 0;
+}
+
+int make_ctx(Ctx& c, const isc_dims_t* dims, const void* packed, int precision, const isc_feats_t* feats,
+             isc_stream_t stream) {
+  ISC_TRY(check_device());
+  ISC_TRY(check_dims(dims));
+  ISC_TRY(check_precision(precision));
+  ISC_REQUIRE(packed != nullptr, "packed weights pointer is NULL");
+  c.d = *dims;
+  c.pk = carve_packed(*dims, precision, const_cast<void*>(packed));
+  c.precision = precision;
+  c.f = feats;
+  c.s = static_cast<cudaStream_t>(stream);
+  return 0;
+}
+
+// prologue workspace
+struct ProWs {
+  bf16 *raw_hi, *raw_lo;  // [chunk*L, D] raw region features as planes
+  bf16 *att_hi, *att_lo;  // [chunk*L, H]
+  bf16 *fc_hi, *fc_lo;    // [B, D]
+  float* tmp;             // [B*S, H] scratch rows (cpt mean / sw)
+  bf16 *tmp_hi, *tmp_lo;
+  float* fcsl;
+  Planes pfcsl;
+  int chunk;
+  size_t total;
+};
+ProWs carve_prologue(const isc_dims_t& d, int precision, int B, void* base) {
+  Bump b(base);
+  ProWs w;
+  memset(&w, 0, sizeof(w));
+  const bool tc = precision != ISC_PREC_FP32, x3 = precision == ISC_PREC_BF16X3;
+  w.chunk = B < 64 ? B : 64;
+  const size_t rows = (size_t)w.chunk * d.n_regions;
+  if (tc) {
+    w.raw_hi = b.take<bf16>(rows * d.feat_dim);
+    if (x3) w.raw_lo = b.take<bf16>(rows * d.feat_dim);
+    if (x3) {  // in ISC_PREC_BF16 the bf16 feature tensor itself is the next GEMM's operand
+      w.att_hi = b.take<bf16>(rows * H);
+      w.att_lo = b.take<bf16>(rows * H);
+    }
+    w.fc_hi = b.take<bf16>((size_t)B * d.feat_dim);
+    if (x3) w.fc_lo = b.take<bf16>((size_t)B * d.feat_dim);
+  }
+  const size_t trow = (size_t)B * (d.n_senti > 1 ? d.n_senti : 1);
+  w.tmp = b.take<float>(trow * H);
+  if (tc) {
+    w.tmp_hi = b.take<bf16>(trow * H);
+    if (x3) w.tmp_lo = b.take<bf16>(trow * H);
+  }
+  w.fcsl = b.take<float>((size_t)B * 2 * H);
+  if (tc) {
+    w.pfcsl.hi = b.take<bf16>((size_t)B * 2 * H);
+    if (x3) w.pfcsl.lo = b.take<bf16>((size_t)B * 2 * H);
+  }
+  w.total = (b.off + 255) & ~size_t(255);
+  return w;
+}
+
+}  // namespace
+}  // namespace isc
+
+using namespace isc;
+
+extern "C" {
+
+const char* isc_version(void) { return "insenticap-b200 0.1 (sm_100a)"; }
+
+uint64_t isc_launch_count(void) { return prof::launches.load(); }
+int isc_profile_enable(int on) {
+  prof::enabled.store(on ? 1 : 0);
+  return 0;
+}
+int isc_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(prof::mu);
+  for (auto& r : prof::recs) {
+    cudaEventSynchronize(r.e1);
+    prof::pool.push_back(r.e0);
+    prof::pool.push_back(r.e1);
+  }
+  prof::recs.clear();
+  return 0;
+}
+int isc_profile_read(int kernel_class, double* total_ms, double* total_work, int64_t* launches) {
+  ISC_REQUIRE(kernel_class >= 0 && kernel_class < ISC_K_NUM && total_ms && total_work && launches, "bad profile_read args");
+  std::lock_guard<std::mutex> lk(prof::mu);
+  double ms = 0.0, work = 0.0;
+  long long n = 0;
+  for (auto& r : prof::recs) {
+    if (r.kclass != kernel_class) continue;
+    ISC_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    ISC_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms += t;
+    work += r.work;
+    ++n;
+  }
+  *total_ms = ms;
+  *total_work = work;
+  *launches = n;
+  return 0;
+}
+const char* isc_last_error(void) { return g_err; }
+int isc_check_device(void) { return check_device(); }
+
+size_t isc_packed_weights_bytes(const isc_dims_t* dims, int precision) {
+  if (check_dims(dims) != 0 || check_precision(precision) != 0) return 0;
+  return carve_packed(*dims, precision, nullptr).total;
+}
+
+int isc_pack_weights(const isc_dims_t* dims, const isc_weights_t* w, int precision, void* packed, size_t packed_bytes,
+                     isc_stream_t stream) {
+  ISC_TRY(check_device());
+  ISC_TRY(check_dims(dims));
+  ISC_TRY(check_precision(precision));
+  ISC_REQUIRE(w && packed, "weights / packed pointer is NULL");
+  Packed p = carve_packed(*dims, precision, packed);
+  if (packed_bytes < p.total) {
+    set_error("packed buffer too small: %zu < %zu", packed_bytes, p.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int V = dims->vocab, D = dims->feat_dim;
+  // attention LSTM: reference input order is [h_lang | fc | xt] (captioner.py:174); the fc slice is
+  // step-invariant and moves to Wpre together with the xt slice applied to the sentiment label.
+  ISC_TRY(copy_block(p.W1.f32, 3 * H, w->att_lstm_w_ih, 3 * H, G4, H, s));                  // h_lang_prev
+  ISC_TRY(copy_block(p.W1.f32 + H, 3 * H, w->att_lstm_w_ih + 2 * H, 3 * H, G4, H, s));      // xt
+  ISC_TRY(copy_block(p.W1.f32 + 2 * H, 3 * H, w->att_lstm_w_hh, H, G4, H, s));              // h_att_prev
+  ISC_TRY(copy_block(p.Wpre.f32, 2 * H, w->att_lstm_w_ih + H, 3 * H, G4, H, s));            // fc
+  ISC_TRY(copy_block(p.Wpre.f32 + H, 2 * H, w->att_lstm_w_ih + 2 * H, 3 * H, G4, H, s));    // sl (added to xt)
+  ISC_TRY(add_vec(p.b1, w->att_lstm_b_ih, w->att_lstm_b_hh, G4, s));
+  // the three projections of h_att
+  ISC_TRY(copy_block(p.W2.f32, H, w->ca_h2att_w, H, H, H, s));
+  ISC_TRY(copy_block(p.W2.f32 + (size_t)H * H, H, w->sa_h2word_w, H, H, H, s));
+  ISC_TRY(copy_block(p.W2.f32 + (size_t)2 * H * H, H, w->g_h2att_w, H, H, H, s));
+  ISC_TRY(add_vec(p.b2, w->ca_h2att_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.b2 + H, w->sa_h2word_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.b2 + 2 * H, w->g_h2att_b, nullptr, H, s));
+  // gate: cont2att(c) + senti2att(s)
+  ISC_TRY(copy_block(p.W3.f32, 2 * H, w->g_cont2att_w, H, H, H, s));
+  ISC_TRY(copy_block(p.W3.f32 + H, 2 * H, w->g_senti2att_w, H, H, H, s));
+  ISC_TRY(add_vec(p.b3, w->g_cont2att_b, w->g_senti2att_b, H, s));
+  // language LSTM: [att | h_att] then h_lang_prev
+  ISC_TRY(copy_block(p.W4.f32, 3 * H, w->lang_lstm_w_ih, 2 * H, G4, 2 * H, s));
+  ISC_TRY(copy_block(p.W4.f32 + 2 * H, 3 * H, w->lang_lstm_w_hh, H, G4, H, s));
+  ISC_TRY(add_vec(p.b4, w->lang_lstm_b_ih, w->lang_lstm_b_hh, G4, s));
+  ISC_TRY(copy_block(p.W5.f32, H, w->classifier_w, H, V, H, s));
+  ISC_TRY(add_vec(p.b5, w->classifier_b, nullptr, V, s));
+  ISC_TRY(copy_block(p.Wfc.f32, D, w->fc_embed_w, D, H, D, s));
+  ISC_TRY(copy_block(p.Watt.f32, D, w->att_embed_w, D, H, D, s));
+  ISC_TRY(copy_block(p.Wa2a.f32, H, w->att2att_w, H, H, H, s));
+  ISC_TRY(copy_block(p.Ws2a.f32, H, w->senti2att_w, H, H, H, s));
+  ISC_TRY(copy_block(p.Wcpt.f32, H, w->cpt2fc_w, H, H, H, s));
+  ISC_TRY(copy_block(p.Wl2w.f32, H, w->sa_label2word_w, H, H, H, s));
+  ISC_TRY(add_vec(p.bfc, w->fc_embed_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.batt, w->att_embed_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.ba2a, w->att2att_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.bs2a, w->senti2att_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.bcpt, w->cpt2fc_b, nullptr, H, s));
+  ISC_TRY(add_vec(p.bl2w, w->sa_label2word_b, nullptr, H, s));
+  ISC_TRY(copy_block(p.emb, H, w->word_embed, H, V, H, s));
+  ISC_TRY(copy_block(p.lab_emb, H, w->senti_label_embed, H, dims->n_labels, H, s));
+  ISC_TRY(add_vec(p.alpha_c, w->ca_alpha_w, nullptr, H, s));
+  ISC_TRY(add_vec(p.alpha_s, w->sa_alpha_w, nullptr, H, s));
+  ISC_TRY(add_vec(p.alpha_g, w->g_alpha_w, nullptr, H, s));
+  ISC_TRY(add_vec(p.alpha_g_b, w->g_alpha_b, nullptr, 1, s));
+  const Mat* mats[] = {&p.W1, &p.Wpre, &p.W2, &p.W3, &p.W4, &p.W5, &p.Wfc, &p.Watt, &p.Wa2a, &p.Ws2a, &p.Wcpt, &p.Wl2w};
+  for (const Mat* m : mats) ISC_TRY(finish_mat(*m, precision, s));
+  return 0;
+}
+
+size_t isc_prologue_workspace_bytes(const isc_dims_t* dims, int precision, int B) {
+  if (check_dims(dims) != 0 || check_precision(precision) != 0 || B <= 0) return 0;
+  return carve_prologue(*dims, precision, B, nullptr).total;
+}
+
+int isc_prologue(const isc_dims_t* dims, const void* packed, int precision, const float* fc_feats,
+                 const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
+                 const int64_t* senti_labels, int B, int seq2seq, const isc_feats_t* out, void* workspace,
+                 size_t workspace_bytes, isc_stream_t stream) {
+  Ctx c;
+  ISC_TRY(make_ctx(c, dims, packed, precision, out, stream));
+  ISC_REQUIRE(out != nullptr && B > 0, "out is NULL or B <= 0");
+  ProWs w = carve_prologue(*dims, precision, B, workspace);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("prologue workspace too small: %zu < %zu", workspace_bytes, w.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  const Packed& pk = c.pk;
+  const int D = dims->feat_dim, L = dims->n_regions, S = dims->n_senti, V = dims->vocab;
+  const bool tc = precision != ISC_PREC_FP32;
+  Planes ptmp;
+  ptmp.hi = w.tmp_hi;
+  ptmp.lo = w.tmp_lo;
+  // concept branch (captioner.py:297-300): mean of ReLU(word_embed) -> cpt2fc -> ReLU
+  float* cpt_dst = seq2seq ? out->fc : out->cpt_feats;
+  if (cpt_words && cpt_dst) {
+    ISC_TRY(launch_embed_mean(reinterpret_cast<const long long*>(cpt_words), B, n_cpt, V, pk.emb,
+                              rowdest(w.tmp, H, ptmp, H), c.s));
+    Epilogue ep;
+    ep.bias = pk.bcpt;
+    ep.act = ACT_RELU;
+    Dest dst;
+    dst.f32 = cpt_dst;
+    dst.ld = H;
+    ISC_TRY(gemm(precision, operand(w.tmp, H, ptmp, H), pk.Wcpt.op(), dst, B, H, H, ep, c.s));
+    if (seq2seq && out->cpt_feats && out->cpt_feats != out->fc)
+      ISC_TRY(copy_block(out->cpt_feats, H, out->fc, H, B, H, c.s));
+  } else {
+    ISC_REQUIRE(!seq2seq, "seq2seq prologue needs cpt_words and out->fc");
+  }
+  if (!seq2seq) {
+    ISC_REQUIRE(fc_feats && att_feats && out->fc && out->att && out->p_att, "fc/att inputs or outputs missing");
+    // fc_embed (captioner.py:294)
+    {
+      Planes pfc;
+      pfc.hi = w.fc_hi;
+      pfc.lo = w.fc_lo;
+      if (tc) ISC_TRY(split_planes(fc_feats, D, w.fc_hi, w.fc_lo, D, B, D, c.s));
+      Epilogue ep;
+      ep.bias = pk.bfc;
+      ep.act = ACT_RELU;
+      Dest dst;
+      dst.f32 = out->fc;
+      dst.ld = H;
+      ISC_TRY(gemm(precision, operand(fc_feats, D, pfc, D), pk.Wfc.op(), dst, B, H, D, ep, c.s));
+    }
+    // att_embed + att2att (captioner.py:302-305), chunked over images so the operand planes stay small
+    for (int b0 = 0; b0 < B; b0 += w.chunk) {
+      const int nb = (B - b0 < w.chunk) ? (B - b0) : w.chunk;
+      const long long rows = (long long)nb * L;
+      const float* raw = att_feats + (long long)b0 * L * D;
+      Planes praw;
+      praw.hi = w.raw_hi;
+      praw.lo = w.raw_lo;
+      if (tc) ISC_TRY(split_planes(raw, D, w.raw_hi, w.raw_lo, D, rows, D, c.s));
+      Epilogue ep;
+      ep.bias = pk.batt;
+      ep.act = ACT_RELU;
+      Dest dst;
+      Planes patt;
+      if (precision == ISC_PREC_BF16) {
+        dst.hi = reinterpret_cast<bf16*>(out->att) + (long long)b0 * L * H;
+        dst.ldp = H;
+        patt.hi = dst.hi;
+      } else {
+        dst.f32 = reinterpret_cast<float*>(out->att) + (long long)b0 * L * H;
+        dst.ld = H;
+        if (tc) {
+          dst.hi = w.att_hi;
+          dst.lo = w.att_lo;
+          dst.ldp = H;
+          patt.hi = w.att_hi;
+          patt.lo = w.att_lo;
+        }
+      }
+      ISC_TRY(gemm(precision, operand(raw, D, praw, D), pk.Watt.op(), dst, (int)rows, H, D, ep, c.s));
+      Epilogue ep2;
+      ep2.bias = pk.ba2a;
+      ep2.act = ACT_RELU;
+      Dest d2;
+      if (precision == ISC_PREC_BF16) {
+        d2.hi = reinterpret_cast<bf16*>(out->p_att) + (long long)b0 * L * H;
+        d2.ldp = H;
+      } else {
+        d2.f32 = reinterpret_cast<float*>(out->p_att) + (long long)b0 * L * H;
+        d2.ld = H;
+      }
+      ISC_TRY(gemm(precision, operand(dst.f32, H, patt, H), pk.Wa2a.op(), d2, (int)rows, H, H, ep2, c.s));
+    }
+  }
+  // sentiment words with the PAD prepended (captioner.py:307-312)
+  if (senti_words) {
+    ISC_REQUIRE(out->sw && out->p_sw, "out->sw / out->p_sw missing");
+    ISC_TRY(launch_embed_rows(reinterpret_cast<const long long*>(senti_words), B, S - 1, 1, dims->pad_id, V, pk.emb,
+                              rowdest(out->sw, H, ptmp, H), c.s));
+    Epilogue ep;
+    ep.bias = pk.bs2a;
+    ep.act = ACT_RELU;
+    Dest dst;
+    dst.f32 = out->p_sw;
+    dst.ld = H;
+    ISC_TRY(gemm(precision, operand(out->sw, H, ptmp, H), pk.Ws2a.op(), dst, B * S, H, H, ep, c.s));
+  }
+  if (senti_labels) {
+    ISC_REQUIRE(out->sl, "out->sl missing");
+    ISC_TRY(launch_embed_rows(reinterpret_cast<const long long*>(senti_labels), B, 1, 0, 0, dims->n_labels, pk.lab_emb,
+                              rowdest(out->sl, H, Planes(), H), c.s));
+  }
+  // hoisted terms
+  isc_feats_t f = *out;
+  if (!senti_labels) f.sl = nullptr;
+  Ctx c2 = c;
+  c2.f = &f;
+  ISC_TRY(run_hoist(c2, B, w.fcsl, w.pfcsl));
+  return 0;
+}
+
+size_t isc_decode_workspace_bytes(const isc_dims_t* dims, int precision, int M) {
+  if (check_dims(dims) != 0 || check_precision(precision) != 0 || M <= 0) return 0;
+  return carve_decode(*dims, precision, M, nullptr).total;
+}
+
+int isc_hoist(const isc_dims_t* dims, const void* packed, int precision, int B, const isc_feats_t* feats,
+              void* workspace, size_t workspace_bytes, isc_stream_t stream) {
+  Ctx c;
+  ISC_TRY(make_ctx(c, dims, packed, precision, feats, stream));
+  ISC_REQUIRE(feats && B > 0, "feats is NULL or B <= 0");
+  DecodeWs w = carve_decode(*dims, precision, B, workspace);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("decode workspace too small: %zu < %zu", workspace_bytes, w.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  return run_hoist(c, B, w.fcsl, w.pfcsl);
+}
+
+int isc_decode_step(const isc_dims_t* dims, const void* packed, int precision, const isc_feats_t* feats,
+                    int rows_per_image, int M, const int64_t* it, const float* h_in, const float* c_in, float* h_out,
+                    float* c_out, float* logprobs, int64_t ld_logprobs, float* cont_w, float* senti_w, float* gate_w,
+                    void* workspace, size_t workspace_bytes, isc_stream_t stream) {
+  Ctx c;
+  ISC_TRY(make_ctx(c, dims, packed, precision, feats, stream));
+  ISC_REQUIRE(feats && M > 0 && rows_per_image >= 1 && M % rows_per_image == 0, "bad M / rows_per_image");
+  ISC_REQUIRE(it && h_in && c_in && h_out && c_out && logprobs, "NULL step buffer");
+  ISC_REQUIRE(h_in != h_out && c_in != c_out, "step state must not alias");
+  ISC_REQUIRE(ld_logprobs >= dims->vocab, "ld_logprobs < vocab");
+  DecodeWs w = carve_decode(*dims, precision, M, workspace);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("decode workspace too small: %zu < %zu", workspace_bytes, w.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  StepIO io;
+  io.it = reinterpret_cast<const long long*>(it);
+  io.parent = nullptr;
+  io.h_in = h_in;
+  io.c_in = c_in;
+  io.h_out = h_out;
+  io.c_out = c_out;
+  io.logits = logprobs;
+  io.ld_logits = ld_logprobs;
+  io.cont_w = cont_w;
+  io.ld_cont_w = dims->n_regions;
+  io.senti_w = senti_w;
+  io.ld_senti_w = dims->n_senti;
+  io.gate_w = gate_w;
+  io.ld_gate_w = 1;
+  ISC_TRY(run_step(c, w, M, rows_per_image, io));
+  return launch_log_softmax(logprobs, ld_logprobs, M, dims->vocab, c.s);
+}
+
+int isc_decode_greedy(const isc_dims_t* dims, const void* packed, int precision, const isc_feats_t* feats, int B, int T,
+                      int sample_mode, const float* noise, uint64_t seed, int64_t* seq, float* seq_logprobs,
+                      float* seq_masks, float* cont_w, float* senti_w, float* gate_w, void* workspace,
+                      size_t workspace_bytes, isc_stream_t stream) {
+  Ctx c;
+  ISC_TRY(make_ctx(c, dims, packed, precision, feats, stream));
+  ISC_REQUIRE(feats && B > 0 && T > 0 && T <= T_MAX, "bad B or T (T <= %d)", T_MAX);
+  ISC_REQUIRE(seq && seq_logprobs && seq_masks, "NULL output");
+  ISC_REQUIRE(sample_mode >= 0 && sample_mode <= 2 && (sample_mode != 1 || noise), "bad sample_mode / noise");
+  DecodeWs w = carve_decode(*dims, precision, B, workspace);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("decode workspace too small: %zu < %zu", workspace_bytes, w.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  const size_t st = (size_t)2 * B * H * sizeof(float);
+  ISC_CUDA(cudaMemsetAsync(w.state_h[0], 0, st, c.s));
+  ISC_CUDA(cudaMemsetAsync(w.state_c[0], 0, st, c.s));
+  ISC_CUDA(cudaMemsetAsync(seq, 0, (size_t)B * T * sizeof(int64_t), c.s));
+  ISC_CUDA(cudaMemsetAsync(seq_logprobs, 0, (size_t)B * T * sizeof(float), c.s));
+  ISC_CUDA(cudaMemsetAsync(seq_masks, 0, (size_t)B * T * sizeof(float), c.s));
+  ISC_CUDA(cudaMemsetAsync(w.alive_count, 0, T_MAX * sizeof(int), c.s));
+  ISC_TRY(launch_greedy_init(w.it, w.unfinished, B, dims->sos_id, c.s));
+  const int L = dims->n_regions, S = dims->n_senti, V = dims->vocab;
+  for (int t = 0; t < T; ++t) {
+    StepIO io;
+    io.it = w.it;
+    io.parent = nullptr;
+    io.h_in = w.state_h[t & 1];
+    io.c_in = w.state_c[t & 1];
+    io.h_out = w.state_h[(t + 1) & 1];
+    io.c_out = w.state_c[(t + 1) & 1];
+    io.logits = w.logits;
+    io.ld_logits = w.ld_logits;
+    if (cont_w) {
+      io.cont_w = cont_w + (long long)t * L;
+      io.ld_cont_w = (long long)T * L;
+    }
+    if (senti_w) {
+      io.senti_w = senti_w + (long long)t * S;
+      io.ld_senti_w = (long long)T * S;
+    }
+    if (gate_w) {
+      io.gate_w = gate_w + t;
+      io.ld_gate_w = T;
+    }
+    ISC_TRY(run_step(c, w, B, 1, io));
+    GreedyParams g;
+    g.logits = w.logits;
+    g.ld = w.ld_logits;
+    g.B = B;
+    g.V = V;
+    g.T = T;
+    g.t = t;
+    g.sample_mode = sample_mode;
+    g.noise = noise ? noise + (long long)t * B * V : nullptr;
+    g.seed = seed;
+    g.eos_id = dims->eos_id;
+    g.it = w.it;
+    g.unfinished = w.unfinished;
+    g.alive_count = w.alive_count;
+    g.seq = reinterpret_cast<long long*>(seq);
+    g.seq_logprobs = seq_logprobs;
+    g.seq_masks = seq_masks;
+    ISC_TRY(launch_greedy_select(g, c.s));
+  }
+  return 0;
+}
+
+int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, const isc_feats_t* feats, int B, int K,
+                    int T, int decoding_constraint, int64_t* tokens, double* scores, int32_t* lengths, void* workspace,
+                    size_t workspace_bytes, isc_stream_t stream) {
+  Ctx c;
+  ISC_TRY(make_ctx(c, dims, packed, precision, feats, stream));
+  ISC_REQUIRE(feats && B > 0 && T > 0 && T <= T_MAX && K >= 1 && K <= 8, "bad B / K (1..8) / T (<= %d)", T_MAX);
+  ISC_REQUIRE(tokens && scores && lengths, "NULL output");
+  ISC_REQUIRE(dims->vocab > K + 4, "vocab too small for beam size");
+  const int M = B * K;
+  DecodeWs w = carve_decode(*dims, precision, M, workspace);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("decode workspace too small: %zu < %zu", workspace_bytes, w.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  const size_t st = (size_t)2 * M * H * sizeof(float);
+  ISC_CUDA(cudaMemsetAsync(w.state_h[0], 0, st, c.s));
+  ISC_CUDA(cudaMemsetAsync(w.state_c[0], 0, st, c.s));
+  ISC_CUDA(cudaMemsetAsync(w.tok[0], 0, (size_t)M * T * sizeof(int), c.s));
+  ISC_TRY(launch_beam_init(w.it, w.alive[0], w.len[0], w.score[0], w.parent, B, K, dims->sos_id, c.s));
+  for (int t = 0; t < T; ++t) {
+    StepIO io;
+    io.it = w.it;
+    io.parent = t > 0 ? w.parent : nullptr;
+    io.h_in = w.state_h[t & 1];
+    io.c_in = w.state_c[t & 1];
+    io.h_out = w.state_h[(t + 1) & 1];
+    io.c_out = w.state_c[(t + 1) & 1];
+    io.logits = w.logits;
+    io.ld_logits = w.ld_logits;
+    ISC_TRY(run_step(c, w, M, K, io));
+    BeamParams bp;
+    bp.logits = w.logits;
+    bp.ld = w.ld_logits;
+    bp.B = B;
+    bp.K = K;
+    bp.V = dims->vocab;
+    bp.T = T;
+    bp.t = t;
+    bp.constraint = decoding_constraint;
+    bp.pad_id = dims->pad_id;
+    bp.sos_id = dims->sos_id;
+    bp.eos_id = dims->eos_id;
+    bp.unk_id = dims->unk_id;
+    bp.tok_in = w.tok[t & 1];
+    bp.tok_out = w.tok[(t + 1) & 1];
+    bp.len_in = w.len[t & 1];
+    bp.len_out = w.len[(t + 1) & 1];
+    bp.score_in = w.score[t & 1];
+    bp.score_out = w.score[(t + 1) & 1];
+    bp.alive_in = w.alive[t & 1];
+    bp.alive_out = w.alive[(t + 1) & 1];
+    bp.it = w.it;
+    bp.parent = w.parent;
+    ISC_TRY(launch_beam_select(bp, c.s));
+  }
+  return launch_beam_finalize(w.tok[T & 1], w.len[T & 1], w.score[T & 1], reinterpret_cast<long long*>(tokens), scores,
+                              lengths, B, K, T, c.s);
+}
+
+int isc_teacher_forced(const isc_dims_t* dims, const void* packed, int precision, const isc_feats_t* feats, int B,
+                       int n_steps, const int64_t* inputs, int64_t ld_inputs, float* logprobs, void* workspace,
+                       size_t workspace_bytes, isc_stream_t stream) {
+  Ctx c;
+  ISC_TRY(make_ctx(c, dims, packed, precision, feats, stream));
+  ISC_REQUIRE(feats && B > 0 && n_steps > 0 && inputs && logprobs && ld_inputs >= n_steps, "bad teacher-forcing args");
+  DecodeWs w = carve_decode(*dims, precision, B, workspace);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("decode workspace too small: %zu < %zu", workspace_bytes, w.total);
+    return ISC_ERR_WORKSPACE;
+  }
+  const size_t st = (size_t)2 * B * H * sizeof(float);
+  ISC_CUDA(cudaMemsetAsync(w.state_h[0], 0, st, c.s));
+  ISC_CUDA(cudaMemsetAsync(w.state_c[0], 0, st, c.s));
+  const long long V = dims->vocab;
+  for (int t = 0; t < n_steps; ++t) {
+    ISC_CUDA(cudaMemcpy2DAsync(w.it, sizeof(long long), inputs + t, ld_inputs * sizeof(long long), sizeof(long long), B,
+                               cudaMemcpyDeviceToDevice, c.s));
+    StepIO io;
+    io.it = w.it;
+    io.parent = nullptr;
+    io.h_in = w.state_h[t & 1];
+    io.c_in = w.state_c[t & 1];
+    io.h_out = w.state_h[(t + 1) & 1];
+    io.c_out = w.state_c[(t + 1) & 1];
+    io.logits = logprobs + (long long)t * V;
+    io.ld_logits = (long long)n_steps * V;
+    ISC_TRY(run_step(c, w, B, 1, io));
+    ISC_TRY(launch_log_softmax(io.logits, io.ld_logits, B, (int)V, c.s));
+  }
+  return 0;
+}
+
+size_t isc_gemm_workspace_bytes(int precision, int M, int N, int K) {
+  if (precision == ISC_PREC_FP32) return 256;
+  size_t planes = precision == ISC_PREC_BF16X3 ? 2 : 1;
+  return planes * ((size_t)M * K + (size_t)N * K) * sizeof(bf16) + 4 * 256;
+}
+
+int isc_gemm_tn(int precision, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C,
+                int64_t ldc, int M, int N, int K, int act, void* workspace, size_t workspace_bytes,
+                isc_stream_t stream) {
+  ISC_TRY(check_device());
+  ISC_TRY(check_precision(precision));
+  ISC_REQUIRE(A && W && C && M > 0 && N > 0 && K > 0, "bad gemm arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Operand a, b;
+  a.f32 = A;
+  a.ld = lda;
+  b.f32 = W;
+  b.ld = ldw;
+  if (precision != ISC_PREC_FP32) {
+    if (!workspace || workspace_bytes < isc_gemm_workspace_bytes(precision, M, N, K)) {
+      set_error("gemm workspace too small");
+      return ISC_ERR_WORKSPACE;
+    }
+    Bump bump(workspace);
+    const bool x3 = precision == ISC_PREC_BF16X3;
+    bf16* ahi = bump.take<bf16>((size_t)M * K);
+    bf16* alo = x3 ? bump.take<bf16>((size_t)M * K) : nullptr;
+    bf16* bhi = bump.take<bf16>((size_t)N * K);
+    bf16* blo = x3 ? bump.take<bf16>((size_t)N * K) : nullptr;
+    ISC_TRY(split_planes(A, lda, ahi, alo, K, M, K, s));
+    ISC_TRY(split_planes(W, ldw, bhi, blo, K, N, K, s));
+    a.hi = ahi;
+    a.lo = alo;
+    a.ldp = K;
+    b.hi = bhi;
+    b.lo = blo;
+    b.ldp = K;
+  }
+  Epilogue ep;
+  ep.bias = bias;
+  ep.act = act;
+  Dest d;
+  d.f32 = C;
+  d.ld = ldc;
+  return gemm(precision, a, b, d, M, N, K, ep, s);
+}
+
+}  // extern "C"

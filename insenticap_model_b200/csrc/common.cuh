@@ -1,0 +1,145 @@
+// Shared internal declarations for libisc_b200.so (not part of the public ABI).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/isc.h"
+
+namespace isc {
+
+constexpr int H = 512;    // word_emb = feat_emb = rnn_hid = att_hid (opts.py:80-95)
+constexpr int G4 = 4 * H; // LSTM gate width
+
+void set_error(const char* fmt, ...);
+
+#define ISC_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) {                                                  \
+      isc::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return (int)_e;                                                         \
+    }                                                                         \
+  } while (0)
+
+#define ISC_LAUNCH_CHECK()                                                    \
+  do {                                                                        \
+    cudaError_t _e = cudaGetLastError();                                      \
+    if (_e != cudaSuccess) {                                                  \
+      isc::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return (int)_e;                                                         \
+    }                                                                         \
+  } while (0)
+
+#define ISC_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != 0) return _r;      \
+  } while (0)
+
+#define ISC_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      isc::set_error(__VA_ARGS__);      \
+      return ISC_ERR_ARG;               \
+    }                                   \
+  } while (0)
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+
+// Per-kernel-class accounting (isc_profile_* in include/isc.h). Every launcher opens a ProfScope:
+// it counts the launch and, when profiling is enabled, brackets it with CUDA events on the launch
+// stream and books the launch's ALGORITHMIC work (flops for GEMMs, HBM bytes for the rest).
+struct ProfScope {
+  ProfScope(int kclass, double work, cudaStream_t stream);
+  ~ProfScope();
+  int slot_;
+  cudaStream_t stream_;
+};
+
+// A dense operand in both representations: fp32 (SIMT path) and bf16 hi/lo planes (tcgen05).
+struct Operand {
+  const float* f32 = nullptr;
+  int64_t ld = 0;  // elements, fp32 view
+  const __nv_bfloat16* hi = nullptr;
+  const __nv_bfloat16* lo = nullptr;
+  int64_t ldp = 0;  // elements, plane view
+};
+
+// Where a GEMM (or a pointwise kernel) writes its result; any member may be null.
+struct Dest {
+  float* f32 = nullptr;
+  int64_t ld = 0;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int64_t ldp = 0;
+};
+
+struct Epilogue {
+  const float* bias = nullptr;    // [N]
+  const float* rowadd = nullptr;  // [ceil(M / rows_per_group), ld_rowadd]: per-image additive term
+  int64_t ld_rowadd = 0;
+  int rows_per_group = 1;
+  const float* addmat = nullptr;  // [M, ld_addmat]: per-row additive term
+  int64_t ld_addmat = 0;
+  int act = ACT_NONE;
+};
+
+// C = act(A[M,K] · W[N,K]^T + bias + rowadd + addmat)
+int gemm_simt(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K,
+              const Epilogue& ep, cudaStream_t stream);
+int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, int passes,
+            const Epilogue& ep, cudaStream_t stream);
+inline int gemm(int precision, const Operand& A, const Operand& W, const Dest& C, int M, int N,
+                int K, const Epilogue& ep, cudaStream_t stream) {
+  if (precision == ISC_PREC_FP32) return gemm_simt(A, W, C, M, N, K, ep, stream);
+  return gemm_tc(A, W, C, M, N, K, precision == ISC_PREC_BF16X3 ? 3 : 1, ep, stream);
+}
+
+// fp32 [rows, cols] -> bf16 hi (and lo = bf16(x - hi) when lo != null)
+int split_planes(const float* src, int64_t ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                 int64_t ld_dst, int64_t rows, int cols, cudaStream_t stream);
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// tanh with ~1e-7 absolute error: 1 - 2/(1+e^{2x}) arranged to avoid cancellation issues
+// beyond fp32 rounding of the result. Two MUFU ops (ex2, rcp).
+__device__ __forceinline__ float tanh_accurate(float x) {
+  float ax = fabsf(x);
+  float e = exp2f(-2.8853900817779268f * ax);  // e^{-2|x|}
+  float r = __fdividef(1.0f - e, 1.0f + e);
+  // small |x|: (1-e)/(1+e) loses relative accuracy; odd Taylor series is exact to fp32 there
+  if (ax < 0.04f) {
+    float x2 = ax * ax;
+    r = ax * (1.0f + x2 * (-0.33333334f + x2 * (0.13333334f - 0.053968254f * x2)));
+  }
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_accurate(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace isc

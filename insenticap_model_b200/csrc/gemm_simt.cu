@@ -1,0 +1,125 @@
+// fp32 CUDA-core GEMM (ISC_PREC_FP32): C = act(A · W^T + bias + rowadd + addmat).
+// Plain fp32 FMA accumulation — the strictest-parity arithmetic for the dense contractions of
+// /root/reference/models/captioner.py (nn.Linear / nn.LSTMCell); the tensor-core kernel in
+// gemm_tc.cu is the throughput path. Also holds the fp32 -> bf16 hi/lo plane splitter.
+#include "common.cuh"
+
+namespace isc {
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict__ A, long long lda,
+                                                        const float* __restrict__ W, long long ldw, int M, int N, int K,
+                                                        const float* __restrict__ bias, const float* __restrict__ rowadd,
+                                                        long long ld_rowadd, int rows_per_group,
+                                                        const float* __restrict__ addmat, long long ld_addmat, int act,
+                                                        float* __restrict__ C, long long ldc, __nv_bfloat16* hi,
+                                                        __nv_bfloat16* lo, long long ldp) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Ws[TK][TN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    // 64 rows x 16 k: 1024 elements per operand, 4 per thread, k fastest for coalescing
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = threadIdx.x + i * 256;
+      int r = e >> 4, k = e & 15;
+      float a = 0.f, w = 0.f;
+      if (k0 + k < K) {
+        if (m0 + r < M) a = A[(long long)(m0 + r) * lda + k0 + k];
+        if (n0 + r < N) w = W[(long long)(n0 + r) * ldw + k0 + k];
+      }
+      As[k][r] = a;
+      Ws[k][r] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (rowadd) v += rowadd[(long long)(m / rows_per_group) * ld_rowadd + n];
+      if (addmat) v += addmat[(long long)m * ld_addmat + n];
+      v = apply_act(v, act);
+      if (C) C[(long long)m * ldc + n] = v;
+      if (hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[(long long)m * ldp + n] = h;
+        if (lo) lo[(long long)m * ldp + n] = l;
+      }
+    }
+  }
+}
+
+__global__ void split_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, long long ld_dst, long long rows, int cols) {
+  const int cols4 = cols >> 2;  // cols % 4 == 0 enforced by the host
+  long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cols4;
+    int c = (int)(i - r * cols4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+    __nv_bfloat16 h[4], l[4];
+    split_bf16(v.x, h[0], l[0]);
+    split_bf16(v.y, h[1], l[1]);
+    split_bf16(v.z, h[2], l[2]);
+    split_bf16(v.w, h[3], l[3]);
+    *reinterpret_cast<uint2*>(hi + r * ld_dst + c) = *reinterpret_cast<uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + r * ld_dst + c) = *reinterpret_cast<uint2*>(l);
+  }
+}
+
+}  // namespace
+
+int gemm_simt(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, const Epilogue& ep,
+              cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  ISC_REQUIRE(A.f32 && W.f32, "gemm_simt: fp32 operands missing");
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  ProfScope ps(ISC_K_GEMM_SIMT, 2.0 * M * N * K, stream);
+  gemm_simt_kernel<<<grid, 256, 0, stream>>>(A.f32, A.ld, W.f32, W.ld, M, N, K, ep.bias, ep.rowadd, ep.ld_rowadd,
+                                             ep.rows_per_group > 0 ? ep.rows_per_group : 1, ep.addmat, ep.ld_addmat,
+                                             ep.act, C.f32, C.ld, C.hi, C.lo, C.ldp);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+int split_planes(const float* src, int64_t ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t ld_dst, int64_t rows,
+                 int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  ISC_REQUIRE(cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0,
+              "split_planes: cols/ld must be multiples of 4 and src 16-byte aligned");
+  long long total = rows * (cols / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps(ISC_K_POINTWISE, (double)rows * cols * (4.0 + 2.0 + (lo ? 2.0 : 0.0)), stream);
+  split_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, rows, cols);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace isc

@@ -1,0 +1,397 @@
+// tcgen05 (5th-gen tensor core) GEMM for sm_100a:  C = act(A · W^T + bias + rowadd + addmat)
+//
+//   A [M,K] and W [N,K] are K-major bf16 "planes". With passes == 3 every operand has a hi and a
+//   lo plane (x ~= hi + lo) and the kernel accumulates hi·hi + lo·hi + hi·lo in one fp32 TMEM
+//   accumulator ("bf16x3": fp32-level accuracy on the bf16 tensor pipe);
+//   with passes == 1 only the hi planes are read.
+//
+//   One 128x128 output tile per CTA. Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner +
+//   single-thread tcgen05.mma issuer, warps 2..5 = epilogue (one TMEM lane = one output row per
+//   thread). Operand tiles are 128 rows x 64 bf16 (128 B rows) in the 128B-swizzled K-major
+//   layout that both TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA shared-memory descriptor
+//   (layout type 2, SBO = 1024 B) understand; a ring of mbarrier-guarded stages decouples the
+//   producer from the issuer, tcgen05.commit releases stages and publishes the accumulator.
+//
+// This is the only dense-contraction kernel of the decode path in the tensor-core precisions:
+// LSTM gate GEMMs, attention projections, vocabulary logits and the prologue feature embeddings
+// (reference: nn.LSTMCell / nn.Linear calls in /root/reference/models/captioner.py:138-161).
+#include <cuda.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace isc {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int TILE_BYTES = BM * BK * 2;  // 16 KiB, one operand plane tile
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+
+template <int PASSES>
+struct Cfg {
+  static constexpr int kTilesPerStage = PASSES == 3 ? 4 : 2;  // A_hi,(A_lo),B_hi,(B_lo)
+  static constexpr int kStageBytes = kTilesPerStage * TILE_BYTES;
+  static constexpr int kStages = PASSES == 3 ? 3 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct EpiParams {
+  const float* bias;
+  const float* rowadd;
+  long long ld_rowadd;
+  int rows_per_group;
+  const float* addmat;
+  long long ld_addmat;
+  int act;
+  float* c;
+  long long ldc;
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  long long ldp;
+  int M, N, K;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must become a trap (an error code on the host), never a hang.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      printf("isc gemm_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row groups
+// 1024 B apart (cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30), SBO [32,46),
+// version [46,48) = 1, layout_type [61,64) = 2 for SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;            // LBO: unused for swizzled K-major
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
+  d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both
+// K-major, N at [17,23) in units of 8, M at [24,29) in units of 16.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ kernel
+template <int PASSES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const EpiParams ep) {
+  using C = Cfg<PASSES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + C::kStages;      // [kStages] MMA -> TMA
+  uint64_t* accum_bar = bars + 2 * C::kStages;  // MMA -> epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int num_kb = (ep.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+    if (PASSES == 3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+    }
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::kStages;
+        const uint32_t ph = (kb / C::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
+        uint8_t* st = smem + s * C::kStageBytes;
+        mbar_expect_tx(&full_bar[s], C::kStageBytes);
+        const int k0 = kb * BK;
+        if (PASSES == 3) {
+          tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
+          tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, &full_bar[s], k0, m0);
+          tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
+          tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, &full_bar[s], k0, n0);
+        } else {
+          tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
+          tma_load_2d(st + 1 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % C::kStages;
+        const uint32_t ph = (kb / C::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_fence_after();
+        const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+        const uint32_t a_hi = st, a_lo = st + TILE_BYTES;
+        const uint32_t b_hi = st + (PASSES == 3 ? 2 : 1) * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+          const uint32_t a = (p == 1) ? a_lo : a_hi;  // hi·hi, lo·hi, hi·lo
+          const uint32_t b = (p == 2) ? b_lo : b_hi;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per 16-element K step inside the 128 B swizzle atom
+            umma_bf16(tmem_base, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
+      }
+      umma_commit(accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(accum_bar, 0);
+    tcgen05_fence_after();
+    const bool row_ok = row < ep.M;
+    const float* radd = (ep.rowadd != nullptr && row_ok) ? ep.rowadd + (long long)(row / ep.rows_per_group) * ep.ld_rowadd
+                                                         : nullptr;
+    const float* madd = (ep.addmat != nullptr && row_ok) ? ep.addmat + (long long)row * ep.ld_addmat : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+      const int nbase = n0 + c * 32;
+      if (row_ok && nbase < ep.N) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = nbase + j;
+        if (n < ep.N) {
+          float x = v[j];
+          if (ep.bias) x += __ldg(ep.bias + n);
+          if (radd) x += __ldg(radd + n);
+          if (madd) x += __ldg(madd + n);
+          v[j] = apply_act(x, ep.act);
+        }
+      }
+      const bool full = (nbase + 32 <= ep.N);
+      if (ep.c) {
+        float* dst = ep.c + (long long)row * ep.ldc + nbase;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && nbase + j < ep.N; ++j) dst[j] = v[j];
+        }
+      }
+      if (ep.hi) {
+        __nv_bfloat16* dh = ep.hi + (long long)row * ep.ldp + nbase;
+        __nv_bfloat16* dl = ep.lo ? ep.lo + (long long)row * ep.ldp + nbase : nullptr;
+        for (int j = 0; j < 32 && nbase + j < ep.N; ++j) {
+          __nv_bfloat16 h, l;
+          split_bf16(v[j], h, l);
+          dh[j] = h;
+          if (dl) dl[j] = l;
+        }
+      }
+      }
+      __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 plane [rows, cols] with leading dimension ld (elements) -> 2D map, box 64 x 128, 128B swizzle.
+static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable from the driver");
+    return ISC_ERR_DEVICE;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) {
+    set_error("gemm_tc: operand plane must be 16-byte aligned with a 16-byte multiple row pitch");
+    return ISC_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld cols %lld ld %lld)", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return ISC_ERR_ARG;
+  }
+  return 0;
+}
+
+template <int PASSES>
+static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int N, int K, const Epilogue& e,
+                  cudaStream_t stream) {
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  ISC_TRY(make_map(&ma_hi, A.hi, M, K, A.ldp));
+  ISC_TRY(make_map(&mb_hi, W.hi, N, K, W.ldp));
+  if (PASSES == 3) {
+    ISC_TRY(make_map(&ma_lo, A.lo, M, K, A.ldp));
+    ISC_TRY(make_map(&mb_lo, W.lo, N, K, W.ldp));
+  } else {
+    ma_lo = ma_hi;
+    mb_lo = mb_hi;
+  }
+  EpiParams ep;
+  ep.bias = e.bias;
+  ep.rowadd = e.rowadd;
+  ep.ld_rowadd = e.ld_rowadd;
+  ep.rows_per_group = e.rows_per_group > 0 ? e.rows_per_group : 1;
+  ep.addmat = e.addmat;
+  ep.ld_addmat = e.ld_addmat;
+  ep.act = e.act;
+  ep.c = Cd.f32;
+  ep.ldc = Cd.ld;
+  ep.hi = Cd.hi;
+  ep.lo = Cd.lo;
+  ep.ldp = Cd.ldp;
+  ep.M = M;
+  ep.N = N;
+  ep.K = K;
+  ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<PASSES>::kSmemBytes));
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  gemm_tc_kernel<PASSES><<<grid, NUM_THREADS, Cfg<PASSES>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc
+
+int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, int passes, const Epilogue& ep,
+            cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc: K=%d must be a positive multiple of 8", K);
+  ISC_REQUIRE(A.hi && W.hi, "gemm_tc: bf16 hi planes missing");
+  if (passes == 3) {
+    ISC_REQUIRE(A.lo && W.lo, "gemm_tc: bf16 lo planes missing for the 3-pass mode");
+    return tc::launch<3>(A, W, C, M, N, K, ep, stream);
+  }
+  return tc::launch<1>(A, W, C, M, N, K, ep, stream);
+}
+
+}  // namespace isc

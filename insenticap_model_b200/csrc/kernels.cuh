@@ -1,0 +1,124 @@
+// Internal launcher declarations shared by the kernel translation units and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace isc {
+
+// Row-major destination written by the element-wise kernels: fp32 and/or bf16 hi/lo planes
+// (the planes are what the tcgen05 GEMM that consumes the row reads through TMA).
+struct RowDest {
+  float* f32 = nullptr;
+  long long ld = 0;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  long long ldp = 0;
+
+#ifdef __CUDACC__
+  __device__ __forceinline__ void store4(long long row, int col, float4 v) const {
+    if (f32) *reinterpret_cast<float4*>(f32 + row * ld + col) = v;
+    if (hi) {
+      __nv_bfloat16 h[4], l[4];
+      split_bf16(v.x, h[0], l[0]);
+      split_bf16(v.y, h[1], l[1]);
+      split_bf16(v.z, h[2], l[2]);
+      split_bf16(v.w, h[3], l[3]);
+      *reinterpret_cast<uint2*>(hi + row * ldp + col) = *reinterpret_cast<uint2*>(h);
+      if (lo) *reinterpret_cast<uint2*>(lo + row * ldp + col) = *reinterpret_cast<uint2*>(l);
+    }
+  }
+  __device__ __forceinline__ void store2(long long row, int col, float2 v) const {
+    if (f32) *reinterpret_cast<float2*>(f32 + row * ld + col) = v;
+    if (hi) {
+      __nv_bfloat16 h[2], l[2];
+      split_bf16(v.x, h[0], l[0]);
+      split_bf16(v.y, h[1], l[1]);
+      *reinterpret_cast<unsigned int*>(hi + row * ldp + col) = *reinterpret_cast<unsigned int*>(h);
+      if (lo) *reinterpret_cast<unsigned int*>(lo + row * ldp + col) = *reinterpret_cast<unsigned int*>(l);
+    }
+  }
+#endif
+};
+
+struct AttnParams {
+  int R = 1, L = 0, S = 0;
+  const float* hproj = nullptr;  // [M, ld_hproj]: [h2att(h) | h2word(h) | gate h2att(h)]
+  long long ld_hproj = 0;
+  const void* att = nullptr;    // [B,L,H] fp32 or bf16; null -> no content attention (seq2seq)
+  const void* p_att = nullptr;
+  const float* sw = nullptr;    // [B,S,H]; null -> no sentiment attention (xe)
+  const float* p_sw = nullptr;
+  const float* pre_word = nullptr;  // [B,H] label2word(sl)
+  const float* alpha_c = nullptr;   // [H]
+  const float* alpha_s = nullptr;   // [H]
+  RowDest cont_dst;
+  int cont_col = 0;
+  RowDest senti_dst;
+  int senti_col = 0;
+  float* cont_w = nullptr;  // [M, ld_cont_w] optional softmax weights
+  long long ld_cont_w = 0;
+  float* senti_w = nullptr;
+  long long ld_senti_w = 0;
+};
+
+int launch_embed_pack(const long long* it, const int* parent, const float* h_in, int M, int V, const float* emb,
+                      RowDest x1, RowDest x2, cudaStream_t stream);
+int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_prev, float* h_out, float* c_out,
+                          RowDest extra, int extra_col, int M, cudaStream_t stream);
+int launch_attention(const AttnParams& p, int B, bool bf16_feats, bool fast_tanh, cudaStream_t stream);
+int launch_gate_mix(const float* g3, const float* cs, const float* alpha, const float* alpha_b, RowDest ctx,
+                    float* gate_w, long long ld_gate_w, int M, cudaStream_t stream);
+int launch_embed_rows(const long long* ids, long long groups, long long n_per_group, int prepend_pad, int pad_id, int V,
+                      const float* emb, RowDest dst, cudaStream_t stream);
+int launch_embed_mean(const long long* ids, int B, int n, int V, const float* emb, RowDest dst, cudaStream_t stream);
+int launch_fill(float* p, long long n, float v, cudaStream_t stream);
+
+// ---- selection (kernels_select.cu) ---------------------------------------------------------
+// in-place log_softmax over rows of `x` [M, ld] (first V columns)
+int launch_log_softmax(float* x, long long ld, int M, int V, cudaStream_t stream);
+
+struct GreedyParams {
+  const float* logits = nullptr;  // [B, ld]
+  long long ld = 0;
+  int B = 0, V = 0, T = 0, t = 0;
+  int sample_mode = 0;            // 0 argmax, 1 external noise, 2 counter-based Gumbel
+  const float* noise = nullptr;   // [B, V] for this step (mode 1)
+  unsigned long long seed = 0;
+  int eos_id = 2;
+  long long* it = nullptr;        // [B] next input token (written)
+  int* unfinished = nullptr;      // [B] (read/write)
+  int* alive_count = nullptr;     // [T] number of unfinished rows after step t
+  long long* seq = nullptr;       // [B,T]
+  float* seq_logprobs = nullptr;  // [B,T]
+  float* seq_masks = nullptr;     // [B,T]
+};
+int launch_greedy_select(const GreedyParams& p, cudaStream_t stream);
+
+struct BeamParams {
+  const float* logits = nullptr;  // [B*K, ld]
+  long long ld = 0;
+  int B = 0, K = 0, V = 0, T = 0, t = 0;
+  int constraint = 1;
+  int pad_id = 0, sos_id = 1, eos_id = 2, unk_id = 3;
+  // beam state, ping-pong by step parity: *_in read, *_out written
+  const int* tok_in = nullptr;  // [B,K,T]
+  int* tok_out = nullptr;
+  const int* len_in = nullptr;  // [B,K]
+  int* len_out = nullptr;
+  const double* score_in = nullptr;  // [B,K]
+  double* score_out = nullptr;
+  const int* alive_in = nullptr;  // [B,K]
+  int* alive_out = nullptr;
+  long long* it = nullptr;  // [B*K] last word per beam: read as "last", written for the next step
+  int* parent = nullptr;    // [B*K] absolute state row each new beam continues from (written)
+};
+int launch_beam_select(const BeamParams& p, cudaStream_t stream);
+int launch_beam_init(long long* it, int* alive, int* len, double* score, int* parent, int B, int K, int sos_id,
+                     cudaStream_t stream);
+int launch_beam_finalize(const int* tok, const int* len, const double* score, long long* tokens_out, double* scores_out,
+                         int* lengths_out, int B, int K, int T, cudaStream_t stream);
+int launch_greedy_init(long long* it, int* unfinished, int B, int sos_id, cudaStream_t stream);
+// weights outputs must read as zero after the whole-batch early stop
+int launch_zero_if_stopped(float* p, long long row_stride, int row_len, int B, const int* alive_count, int t,
+                           cudaStream_t stream);
+
+}  // namespace isc

@@ -1,0 +1,354 @@
+// Token selection on the vocabulary logits: log_softmax (captioner.py:183), the greedy / sampled
+// pick of forward_rl (captioner.py:328-344) and the beam expansion + pooled stable top-K of
+// Captioner.sample (captioner.py:394-409). One CTA per row (per image for the beam), 128-bit
+// coalesced reads of the logits row, warp-shuffle + shared-memory block reductions.
+#include <math_constants.h>
+
+#include "kernels.cuh"
+
+namespace isc {
+namespace {
+
+constexpr int NT = 256;
+constexpr int KMAX = 8;
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < NT / 32; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) r += red[i];
+  return r;
+}
+// (value desc, index asc) argmax over the block; every thread gets the winner
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* redv, int* redi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > v || (ov == v && oi < idx)) {
+      v = ov;
+      idx = oi;
+    }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    redv[threadIdx.x >> 5] = v;
+    redi[threadIdx.x >> 5] = idx;
+  }
+  __syncthreads();
+  v = redv[0];
+  idx = redi[0];
+#pragma unroll
+  for (int i = 1; i < NT / 32; ++i) {
+    float ov = redv[i];
+    int oi = redi[i];
+    if (ov > v || (ov == v && oi < idx)) {
+      v = ov;
+      idx = oi;
+    }
+  }
+}
+
+// row statistics with 128-bit loads: max over the first V entries
+__device__ __forceinline__ float row_max(const float* row, int V, float* red) {
+  float mx = -CUDART_INF_F;
+  const int v4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 2) : 0;
+  for (int i = threadIdx.x; i < v4; i += NT) {
+    float4 x = reinterpret_cast<const float4*>(row)[i];  // plain load: the row may be rewritten in place
+    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+  }
+  for (int i = v4 * 4 + threadIdx.x; i < V; i += NT) mx = fmaxf(mx, row[i]);
+  return block_max(mx, red);
+}
+__device__ __forceinline__ float row_sumexp(const float* row, int V, float mx, float* red) {
+  float s = 0.f;
+  const int v4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 2) : 0;
+  for (int i = threadIdx.x; i < v4; i += NT) {
+    float4 x = reinterpret_cast<const float4*>(row)[i];  // plain load: the row may be rewritten in place
+    s += expf(x.x - mx) + expf(x.y - mx) + expf(x.z - mx) + expf(x.w - mx);
+  }
+  for (int i = v4 * 4 + threadIdx.x; i < V; i += NT) s += expf(row[i] - mx);
+  return block_sum(s, red);
+}
+
+__global__ void __launch_bounds__(NT) log_softmax_kernel(float* __restrict__ x, long long ld, int V) {
+  __shared__ float red[NT / 32];
+  float* row = x + (long long)blockIdx.x * ld;
+  const float mx = row_max(row, V, red);
+  const float ls = logf(row_sumexp(row, V, mx, red));
+  for (int i = threadIdx.x; i < V; i += NT) row[i] = (row[i] - mx) - ls;
+}
+
+__device__ __forceinline__ float gumbel_counter(unsigned long long seed, unsigned long long ctr) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (ctr + 1ULL);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  float u = ((float)(z >> 41) + 0.5f) * (1.0f / 8388608.0f);  // (0,1), 23 random bits
+  return -logf(-logf(u));
+}
+
+__global__ void __launch_bounds__(NT) greedy_select_kernel(GreedyParams p) {
+  __shared__ float red[NT / 32];
+  __shared__ float redv[NT / 32];
+  __shared__ int redi[NT / 32];
+  const int b = blockIdx.x;
+  const int t = p.t;
+  if (t > 0 && p.alive_count[t - 1] == 0) return;  // whole-batch early stop (captioner.py:343-344)
+  const float* row = p.logits + (long long)b * p.ld;
+  const int V = p.V;
+  // pass 1: max and (for plain argmax) its first index
+  float bv = -CUDART_INF_F;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += NT) {
+    float x = row[i];
+    if (x > bv) {
+      bv = x;
+      bi = i;
+    }
+  }
+  block_argmax(bv, bi, redv, redi);
+  const float mx = bv;
+  const float ls = logf(row_sumexp(row, V, mx, red));
+  int pick = bi;
+  float lp = (mx - mx) - ls;
+  if (p.sample_mode != 0) {
+    float sv = -CUDART_INF_F;
+    int si = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += NT) {
+      float g = (p.sample_mode == 1)
+                    ? p.noise[(long long)b * V + i]
+                    : gumbel_counter(p.seed, ((unsigned long long)t * p.B + b) * (unsigned long long)V + i);
+      float s = ((row[i] - mx) - ls) + g;
+      if (s > sv) {
+        sv = s;
+        si = i;
+      }
+    }
+    block_argmax(sv, si, redv, redi);
+    pick = si;
+    lp = (row[pick] - mx) - ls;
+  }
+  if (threadIdx.x == 0) {
+    const int unf = p.unfinished[b];
+    const long long tok = unf ? pick : 0;  // finished rows emit PAD (captioner.py:338)
+    p.seq[(long long)b * p.T + t] = tok;
+    p.seq_logprobs[(long long)b * p.T + t] = lp;  // written unmasked (captioner.py:340)
+    p.seq_masks[(long long)b * p.T + t] = unf ? 1.f : 0.f;
+    const int unf2 = unf && (tok != p.eos_id);
+    p.unfinished[b] = unf2;
+    p.it[b] = tok;
+    if (unf2) atomicAdd(p.alive_count + t, 1);
+  }
+}
+
+__global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
+  __shared__ float red[NT / 32];
+  __shared__ float redv[NT / 32];
+  __shared__ int redi[NT / 32];
+  __shared__ double pool_score[KMAX * KMAX + KMAX];
+  __shared__ int pool_parent[KMAX * KMAX + KMAX];
+  __shared__ int pool_word[KMAX * KMAX + KMAX];
+  __shared__ int pool_n;
+  __shared__ long long last_sm[KMAX];
+  __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
+  const int b = blockIdx.x, K = p.K, V = p.V, t = p.t, T = p.T;
+  if (threadIdx.x < K) last_sm[threadIdx.x] = p.it[b * K + threadIdx.x];
+  if (threadIdx.x == 0) pool_n = 0;
+  __syncthreads();
+  const bool mask_special = (p.pad_id != p.eos_id);
+
+  for (int k = 0; k < K; ++k) {
+    if (!p.alive_in[b * K + k]) continue;  // uniform across the block
+    const int last = (int)last_sm[k];
+    if (t > 0 && last == p.eos_id) {  // finished: carried unchanged (captioner.py:385-386)
+      if (threadIdx.x == 0) {
+        int n = pool_n;
+        pool_score[n] = p.score_in[b * K + k];
+        pool_parent[n] = k;
+        pool_word[n] = -1;
+        pool_n = n + 1;
+      }
+      __syncthreads();
+      continue;
+    }
+    const float* row = p.logits + (long long)(b * K + k) * p.ld;
+    float topv[KMAX];
+    int topi[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      topv[j] = -CUDART_INF_F;
+      topi[j] = 0x7fffffff;
+    }
+    float mx = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < V; i += NT) {
+      const float x = row[i];
+      mx = fmaxf(mx, x);
+      bool masked = (mask_special && (i == p.pad_id || i == p.sos_id || i == p.unk_id)) || (p.constraint && i == last);
+      if (!masked && x > topv[KMAX - 1]) {
+        topv[KMAX - 1] = x;
+        topi[KMAX - 1] = i;
+#pragma unroll
+        for (int j = KMAX - 1; j > 0; --j) {
+          if (topv[j] > topv[j - 1]) {
+            float tv = topv[j]; topv[j] = topv[j - 1]; topv[j - 1] = tv;
+            int ti = topi[j]; topi[j] = topi[j - 1]; topi[j - 1] = ti;
+          }
+        }
+      }
+    }
+    mx = block_max(mx, red);
+    const float ls = logf(row_sumexp(row, V, mx, red));
+    const double base = p.score_in[b * K + k];
+    for (int r = 0; r < K; ++r) {
+      float v = topv[0];
+      int idx = topi[0];
+      block_argmax(v, idx, redv, redi);
+      if (idx == topi[0] && idx != 0x7fffffff) {  // this thread owned the winner: pop it
+#pragma unroll
+        for (int j = 0; j < KMAX - 1; ++j) {
+          topv[j] = topv[j + 1];
+          topi[j] = topi[j + 1];
+        }
+        topv[KMAX - 1] = -CUDART_INF_F;
+        topi[KMAX - 1] = 0x7fffffff;
+      }
+      if (threadIdx.x == 0 && idx != 0x7fffffff) {
+        const float lp = (v - mx) - ls;  // log_softmax value of the candidate, fp32 like the reference
+        int n = pool_n;
+        pool_score[n] = base + (double)lp;  // python-float running sum (captioner.py:404-407)
+        pool_parent[n] = k;
+        pool_word[n] = idx;
+        pool_n = n + 1;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // stable top-K of the pool by score (python sorted(reverse=True) keeps pool order on ties)
+    const int n = pool_n;
+    unsigned long long taken = 0ULL;
+    int m = 0;
+    for (; m < K && m < n; ++m) {
+      int best = -1;
+      for (int i = 0; i < n; ++i) {
+        if ((taken >> i) & 1ULL) continue;
+        if (best < 0 || pool_score[i] > pool_score[best]) best = i;
+      }
+      taken |= 1ULL << best;
+      const int k = pool_parent[best], w = pool_word[best];
+      sel_parent[m] = k;
+      sel_word[m] = w;
+      p.score_out[b * K + m] = pool_score[best];
+      p.alive_out[b * K + m] = 1;
+      p.len_out[b * K + m] = p.len_in[b * K + k] + (w >= 0 ? 1 : 0);
+      p.parent[b * K + m] = b * K + k;
+      p.it[b * K + m] = (w >= 0) ? (long long)w : last_sm[k];
+    }
+    sel_n = m;
+    for (; m < K; ++m) {
+      p.score_out[b * K + m] = 0.0;
+      p.alive_out[b * K + m] = 0;
+      p.len_out[b * K + m] = 0;
+      p.parent[b * K + m] = b * K + m;
+      p.it[b * K + m] = p.sos_id;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * T; i += NT) {
+    const int j = i / T, tt = i - j * T;
+    int v = 0;
+    if (j < sel_n) {
+      const int k = sel_parent[j];
+      v = p.tok_in[(b * K + k) * T + tt];
+      if (sel_word[j] >= 0 && tt == p.len_in[b * K + k]) v = sel_word[j];
+    }
+    p.tok_out[(b * K + j) * T + tt] = v;
+  }
+}
+
+__global__ void beam_init_kernel(long long* it, int* alive, int* len, double* score, int* parent, int M, int K, int sos_id) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  it[m] = sos_id;
+  alive[m] = (m % K) == 0;  // a single <SOS> candidate per image at t = 0 (captioner.py:379)
+  len[m] = 0;
+  score[m] = 0.0;
+  parent[m] = m;
+}
+__global__ void beam_finalize_kernel(const int* tok, const int* len, const double* score, long long* tokens_out,
+                                     double* scores_out, int* lengths_out, int M, int T) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M * T) tokens_out[i] = tok[i];
+  if (i < M) {
+    scores_out[i] = score[i];
+    lengths_out[i] = len[i];
+  }
+}
+__global__ void greedy_init_kernel(long long* it, int* unfinished, int B, int sos_id) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  it[b] = sos_id;
+  unfinished[b] = 1;
+}
+
+}  // namespace
+
+int launch_log_softmax(float* x, long long ld, int M, int V, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  ProfScope ps(ISC_K_SELECT, (double)M * V * 4.0 * 2, stream);
+  log_softmax_kernel<<<M, NT, 0, stream>>>(x, ld, V);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_greedy_select(const GreedyParams& p, cudaStream_t stream) {
+  ProfScope ps(ISC_K_SELECT, (double)p.B * p.V * 4.0 * (p.sample_mode == 1 ? 2 : 1), stream);
+  greedy_select_kernel<<<p.B, NT, 0, stream>>>(p);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_beam_select(const BeamParams& p, cudaStream_t stream) {
+  ISC_REQUIRE(p.K >= 1 && p.K <= KMAX, "beam size %d not in 1..%d", p.K, KMAX);
+  ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.V * 4.0, stream);
+  beam_select_kernel<<<p.B, NT, 0, stream>>>(p);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_beam_init(long long* it, int* alive, int* len, double* score, int* parent, int B, int K, int sos_id,
+                     cudaStream_t stream) {
+  int M = B * K;
+  ProfScope ps(ISC_K_SELECT, (double)M * 32.0, stream);
+  beam_init_kernel<<<(M + 255) / 256, 256, 0, stream>>>(it, alive, len, score, parent, M, K, sos_id);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_beam_finalize(const int* tok, const int* len, const double* score, long long* tokens_out, double* scores_out,
+                         int* lengths_out, int B, int K, int T, cudaStream_t stream) {
+  int M = B * K;
+  ProfScope ps(ISC_K_SELECT, (double)M * T * 12.0, stream);
+  beam_finalize_kernel<<<(M * T + 255) / 256, 256, 0, stream>>>(tok, len, score, tokens_out, scores_out, lengths_out, M, T);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_greedy_init(long long* it, int* unfinished, int B, int sos_id, cudaStream_t stream) {
+  ProfScope ps(ISC_K_SELECT, (double)B * 12.0, stream);
+  greedy_init_kernel<<<(B + 255) / 256, 256, 0, stream>>>(it, unfinished, B, sos_id);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace isc

@@ -1,0 +1,381 @@
+// Non-GEMM kernels of one decode step (Captioner.forward_step, /root/reference/models/captioner.py:168-186)
+// and of the prologue. All are HBM-bound element-wise / reduction kernels: 128-bit accesses,
+// warp-shuffle reductions, one CTA per row (or per image for the attention, so the K beams of an
+// image share one pass over its region features).
+#include "kernels.cuh"
+
+namespace isc {
+
+// --------------------------------------------------------------------------------------------
+// embed + pack: builds the attention-LSTM input  X1[m] = [h_lang_prev | ReLU(E[it]) | h_att_prev]
+// (captioner.py:170-174; the step-invariant terms — the fc slice and W_ih[:,2H:3H]·sl of
+// xt = ReLU(E[it]) + sl — are hoisted into feats.pre_gates) and copies
+// h_lang_prev into X2[m, 2H:3H] for the language LSTM's recurrent term. Rows are read through
+// `parent` so that the beam reorder costs no separate gather.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) embed_pack_kernel(const long long* __restrict__ it, const int* __restrict__ parent,
+                                                         const float* __restrict__ h_in, long long M, int V,
+                                                         const float* __restrict__ emb, RowDest x1, RowDest x2) {
+  const int m = blockIdx.x;
+  const int src = parent ? parent[m] : m;
+  long long tok = it[m];
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  const int c = threadIdx.x * 4;
+  float4 hl = *reinterpret_cast<const float4*>(h_in + (1 * M + src) * H + c);
+  float4 ha = *reinterpret_cast<const float4*>(h_in + (0 * M + src) * H + c);
+  float4 e = *reinterpret_cast<const float4*>(emb + tok * H + c);
+  e.x = fmaxf(e.x, 0.f); e.y = fmaxf(e.y, 0.f); e.z = fmaxf(e.z, 0.f); e.w = fmaxf(e.w, 0.f);
+  x1.store4(m, c, hl);
+  x1.store4(m, H + c, e);
+  x1.store4(m, 2 * H + c, ha);
+  x2.store4(m, 2 * H + c, hl);
+}
+
+// --------------------------------------------------------------------------------------------
+// LSTM cell pointwise (nn.LSTMCell, gate order i,f,g,o): gates already hold W·x + biases.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) lstm_pointwise_kernel(const float* __restrict__ gates, const int* __restrict__ parent,
+                                                             const float* __restrict__ c_prev, float* __restrict__ h_out,
+                                                             float* __restrict__ c_out, RowDest extra, int extra_col) {
+  const int m = blockIdx.x;
+  const int src = parent ? parent[m] : m;
+  const int c = threadIdx.x * 4;
+  const float* g = gates + (long long)m * G4;
+  float4 gi = *reinterpret_cast<const float4*>(g + c);
+  float4 gf = *reinterpret_cast<const float4*>(g + H + c);
+  float4 gg = *reinterpret_cast<const float4*>(g + 2 * H + c);
+  float4 go = *reinterpret_cast<const float4*>(g + 3 * H + c);
+  float4 cp = *reinterpret_cast<const float4*>(c_prev + (long long)src * H + c);
+  float4 cn, hn;
+#define ISC_LSTM(X)                                                              \
+  cn.X = sigmoid_accurate(gf.X) * cp.X + sigmoid_accurate(gi.X) * tanhf(gg.X);   \
+  hn.X = sigmoid_accurate(go.X) * tanhf(cn.X);
+  ISC_LSTM(x) ISC_LSTM(y) ISC_LSTM(z) ISC_LSTM(w)
+#undef ISC_LSTM
+  *reinterpret_cast<float4*>(c_out + (long long)m * H + c) = cn;
+  *reinterpret_cast<float4*>(h_out + (long long)m * H + c) = hn;
+  extra.store4(m, extra_col + c, hn);
+}
+
+// --------------------------------------------------------------------------------------------
+// Attention (ContentAttention :23-35, SentiAttention :50-62): one CTA per image, R rows (beams)
+// of that image processed against one pass over p_att / att (and p_sw / sw).
+//   hproj[m] = [h2att(h) | h2word(h) | gate h2att(h)] (+ their biases), from the projection GEMM.
+// --------------------------------------------------------------------------------------------
+template <typename FeatT>
+struct FeatLoad;
+template <>
+struct FeatLoad<float> {
+  static constexpr int kChunks = 4;  // 4 x float4 per lane per 512-wide row
+  __device__ static __forceinline__ int col(int lane, int i) { return i * 128 + lane * 4; }
+  __device__ static __forceinline__ void load(const float* row, int lane, int i, float* v) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(row + col(lane, i)));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static constexpr int kWidth = 4;
+};
+template <>
+struct FeatLoad<__nv_bfloat16> {
+  static constexpr int kChunks = 2;  // 2 x (8 bf16 = 16 B) per lane
+  __device__ static __forceinline__ int col(int lane, int i) { return i * 256 + lane * 8; }
+  __device__ static __forceinline__ void load(const __nv_bfloat16* row, int lane, int i, float* v) {
+    uint4 t = __ldg(reinterpret_cast<const uint4*>(row + col(lane, i)));
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 f = __bfloat1622float2(p[q]);
+      v[2 * q] = f.x;
+      v[2 * q + 1] = f.y;
+    }
+  }
+  static constexpr int kWidth = 8;
+};
+
+template <typename FeatT, bool FAST_TANH>
+__device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
+                                           const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
+                                           float* __restrict__ score_smem /*[R][n_items]*/, int warp, int lane, int n_warps) {
+  using L = FeatLoad<FeatT>;
+  for (int l = warp; l < n_items; l += n_warps) {
+    const FeatT* row = p_feat + (long long)l * H;
+    float pv[L::kChunks][L::kWidth];
+#pragma unroll
+    for (int i = 0; i < L::kChunks; ++i) L::load(row, lane, i, pv[i]);
+    for (int r = 0; r < R; ++r) {
+      const float* q = q_smem + r * H;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < L::kChunks; ++i) {
+        const int c0 = L::col(lane, i);
+#pragma unroll
+        for (int j = 0; j < L::kWidth; ++j) {
+          float x = pv[i][j] + q[c0 + j];
+          float t = FAST_TANH ? tanh_fast(x) : tanh_accurate(x);
+          acc = fmaf(alpha_smem[c0 + j], t, acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) score_smem[r * n_items + l] = acc;
+    }
+  }
+}
+
+__device__ __forceinline__ void softmax_rows(float* score_smem, int n_items, int R, int warp, int lane, int n_warps,
+                                             float* w_out, long long ld_w, long long row0) {
+  for (int r = warp; r < R; r += n_warps) {
+    float* s = score_smem + r * n_items;
+    float mx = -INFINITY;
+    for (int l = lane; l < n_items; l += 32) mx = fmaxf(mx, s[l]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int l = lane; l < n_items; l += 32) {
+      float e = expf(s[l] - mx);
+      s[l] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int l = lane; l < n_items; l += 32) {
+      float w = s[l] / sum;
+      s[l] = w;
+      if (w_out) w_out[(row0 + r) * ld_w + l] = w;
+    }
+  }
+}
+
+template <typename FeatT>
+__device__ __forceinline__ float2 load2(const FeatT* p);
+template <>
+__device__ __forceinline__ float2 load2<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float2*>(p));
+}
+template <>
+__device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
+  unsigned int u = __ldg(reinterpret_cast<const unsigned int*>(p));
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+// context[r] = sum_l w[r][l] * feat[l] ; thread owns columns (2t, 2t+1)
+template <typename FeatT, int RMAX>
+__device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int n_items, int R,
+                                             const float* __restrict__ w_smem, RowDest dst, long long row0, int dst_col) {
+  const int c = threadIdx.x * 2;
+  float2 acc[RMAX];
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r) acc[r] = make_float2(0.f, 0.f);
+  int l = 0;
+  for (; l + 4 <= n_items; l += 4) {
+    float2 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[u] = load2<FeatT>(feat + (long long)(l + u) * H + c);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+        if (r < R) {
+          float w = w_smem[r * n_items + l + u];
+          acc[r].x = fmaf(w, a[u].x, acc[r].x);
+          acc[r].y = fmaf(w, a[u].y, acc[r].y);
+        }
+  }
+  for (; l < n_items; ++l) {
+    float2 a = load2<FeatT>(feat + (long long)l * H + c);
+#pragma unroll
+    for (int r = 0; r < RMAX; ++r)
+      if (r < R) {
+        float w = w_smem[r * n_items + l];
+        acc[r].x = fmaf(w, a.x, acc[r].x);
+        acc[r].y = fmaf(w, a.y, acc[r].y);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < RMAX; ++r)
+    if (r < R) dst.store2(row0 + r, dst_col + c, acc[r]);
+}
+
+template <typename FeatT, bool FAST_TANH>
+__global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
+  extern __shared__ float sm[];
+  const int R = p.R, L = p.L, S = p.S;
+  float* q_c = sm;                 // [R][H] content query  h2att(h)
+  float* q_s = q_c + R * H;        // [R][H] senti query    h2word(h) + label2word(sl)
+  float* alpha_c = q_s + R * H;    // [H]
+  float* alpha_s = alpha_c + H;    // [H]
+  float* sc_c = alpha_s + H;       // [R][L]
+  float* sc_s = sc_c + R * L;      // [R][S]
+  const int img = blockIdx.x;
+  const long long row0 = (long long)img * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < R * H; i += 256) {
+    int r = i / H, c = i - r * H;
+    const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
+    q_c[i] = hp[c];
+    q_s[i] = hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f);
+  }
+  for (int i = threadIdx.x; i < H; i += 256) {
+    alpha_c[i] = p.alpha_c[i];
+    alpha_s[i] = p.alpha_s[i];
+  }
+  __syncthreads();
+  const FeatT* att = reinterpret_cast<const FeatT*>(p.att);
+  const FeatT* p_att = reinterpret_cast<const FeatT*>(p.p_att);
+  if (att) {
+    score_rows<FeatT, FAST_TANH>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c, warp, lane, 8);
+  }
+  if (p.sw) {
+    score_rows<float, FAST_TANH>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, warp, lane, 8);
+  }
+  __syncthreads();
+  if (att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
+  if (p.sw) softmax_rows(sc_s, S, R, warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
+  __syncthreads();
+  if (att) weighted_sum<FeatT, 8>(att + (long long)img * L * H, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  if (p.sw) weighted_sum<float, 8>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+}
+
+int launch_attention(const AttnParams& p, int B, bool bf16_feats, bool fast_tanh, cudaStream_t stream) {
+  ISC_REQUIRE(p.R >= 1 && p.R <= 8, "attention: rows per image %d not in 1..8", p.R);
+  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * p.L + p.R * p.S);
+  // algorithmic HBM bytes: both feature tensors of every image once per launch (shared by its R rows),
+  // sentiment-word features, the R query rows in and the R context rows out
+  const double feat_b = bf16_feats ? 2.0 : 4.0;
+  const double bytes = (double)B * ((p.att ? 2.0 * p.L * H * feat_b : 0.0) + (p.sw ? 2.0 * p.S * H * 4.0 : 0.0) +
+                                    (double)p.R * (3.0 * H * 4.0 + 2.0 * H * 4.0));
+  ProfScope ps(ISC_K_ATTENTION, bytes, stream);
+  if (bf16_feats) {
+    auto k = fast_tanh ? attention_kernel<__nv_bfloat16, true> : attention_kernel<__nv_bfloat16, false>;
+    ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B, 256, smem, stream>>>(p);
+  } else {
+    auto k = fast_tanh ? attention_kernel<float, true> : attention_kernel<float, false>;
+    ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<B, 256, smem, stream>>>(p);
+  }
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// Gate (Attention.forward :108-117): g3 = tanh(cont2att(c) + senti2att(s) + h2att(h)) comes from
+// the GEMM epilogue; here w = sigmoid(att_alpha · g3 + b), ctx = w*c + (1-w)*s.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gate_mix_kernel(const float* __restrict__ g3, const float* __restrict__ cs,
+                                                       const float* __restrict__ alpha, const float* __restrict__ alpha_b,
+                                                       RowDest ctx, float* __restrict__ gate_w, long long ld_gate_w) {
+  __shared__ float red[4];
+  __shared__ float wsh;
+  const int m = blockIdx.x;
+  const int c = threadIdx.x * 4;
+  float4 g = *reinterpret_cast<const float4*>(g3 + (long long)m * H + c);
+  float4 a = *reinterpret_cast<const float4*>(alpha + c);
+  float part = g.x * a.x + g.y * a.y + g.z * a.z + g.w * a.w;
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float w = sigmoid_accurate(red[0] + red[1] + red[2] + red[3] + alpha_b[0]);
+    wsh = w;
+    if (gate_w) gate_w[(long long)m * ld_gate_w] = w;
+  }
+  __syncthreads();
+  const float w = wsh;
+  float4 cv = *reinterpret_cast<const float4*>(cs + (long long)m * 2 * H + c);
+  float4 sv = *reinterpret_cast<const float4*>(cs + (long long)m * 2 * H + H + c);
+  float4 o;
+  o.x = w * cv.x + (1.f - w) * sv.x;
+  o.y = w * cv.y + (1.f - w) * sv.y;
+  o.z = w * cv.z + (1.f - w) * sv.z;
+  o.w = w * cv.w + (1.f - w) * sv.w;
+  ctx.store4(m, c, o);
+}
+
+// --------------------------------------------------------------------------------------------
+// Prologue gathers: ReLU(E[id]) rows; concept mean; senti-word rows with the prepended PAD.
+// --------------------------------------------------------------------------------------------
+// out[row] = ReLU(emb[ids[row]]);  ids == null -> row's id comes from `fixed_id`
+__global__ void __launch_bounds__(128) embed_rows_kernel(const long long* __restrict__ ids, long long n_per_group,
+                                                         int prepend_pad, int pad_id, int V, const float* __restrict__ emb,
+                                                         RowDest dst) {
+  // rows are laid out [group][prepend_pad + n_per_group]; ids are [group][n_per_group]
+  const long long row = blockIdx.x;
+  const long long per = n_per_group + prepend_pad;
+  const long long grp = row / per;
+  const long long j = row - grp * per;
+  long long tok = (prepend_pad && j == 0) ? pad_id : ids[grp * n_per_group + (j - prepend_pad)];
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+  const int c = threadIdx.x * 4;
+  float4 e = *reinterpret_cast<const float4*>(emb + tok * H + c);
+  e.x = fmaxf(e.x, 0.f); e.y = fmaxf(e.y, 0.f); e.z = fmaxf(e.z, 0.f); e.w = fmaxf(e.w, 0.f);
+  dst.store4(row, c, e);
+}
+
+// out[b] = mean_j ReLU(emb[ids[b][j]])   (captioner.py:297-298)
+__global__ void __launch_bounds__(128) embed_mean_kernel(const long long* __restrict__ ids, int n, int V,
+                                                         const float* __restrict__ emb, RowDest dst) {
+  const long long b = blockIdx.x;
+  const int c = threadIdx.x * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < n; ++j) {
+    long long tok = ids[b * n + j];
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    float4 e = *reinterpret_cast<const float4*>(emb + tok * H + c);
+    acc.x += fmaxf(e.x, 0.f); acc.y += fmaxf(e.y, 0.f); acc.z += fmaxf(e.z, 0.f); acc.w += fmaxf(e.w, 0.f);
+  }
+  const float inv = 1.0f / (float)n;
+  // torch.mean divides the fp32 sum by n
+  acc.x = acc.x / (float)n; acc.y = acc.y / (float)n; acc.z = acc.z / (float)n; acc.w = acc.w / (float)n;
+  (void)inv;
+  dst.store4(b, c, acc);
+}
+
+__global__ void fill_kernel(float* p, long long n, float v) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------ host launchers
+int launch_embed_pack(const long long* it, const int* parent, const float* h_in, int M, int V, const float* emb,
+                      RowDest x1, RowDest x2, cudaStream_t stream) {
+  ProfScope ps(ISC_K_POINTWISE, (double)M * H * 4.0 * 7, stream);
+  embed_pack_kernel<<<M, 128, 0, stream>>>(it, parent, h_in, M, V, emb, x1, x2);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_prev, float* h_out, float* c_out,
+                          RowDest extra, int extra_col, int M, cudaStream_t stream) {
+  ProfScope ps(ISC_K_LSTM, (double)M * H * 4.0 * 8, stream);  // 4H gates + c in, h + c + h-copy out
+  lstm_pointwise_kernel<<<M, 128, 0, stream>>>(gates, parent, c_prev, h_out, c_out, extra, extra_col);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_gate_mix(const float* g3, const float* cs, const float* alpha, const float* alpha_b, RowDest ctx,
+                    float* gate_w, long long ld_gate_w, int M, cudaStream_t stream) {
+  ProfScope ps(ISC_K_POINTWISE, (double)M * H * 4.0 * 4, stream);
+  gate_mix_kernel<<<M, 128, 0, stream>>>(g3, cs, alpha, alpha_b, ctx, gate_w, ld_gate_w);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_embed_rows(const long long* ids, long long groups, long long n_per_group, int prepend_pad, int pad_id, int V,
+                      const float* emb, RowDest dst, cudaStream_t stream) {
+  long long rows = groups * (n_per_group + prepend_pad);
+  if (rows <= 0) return 0;
+  ProfScope ps(ISC_K_POINTWISE, (double)rows * H * 4.0 * 2, stream);
+  embed_rows_kernel<<<(unsigned)rows, 128, 0, stream>>>(ids, n_per_group, prepend_pad, pad_id, V, emb, dst);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_embed_mean(const long long* ids, int B, int n, int V, const float* emb, RowDest dst, cudaStream_t stream) {
+  ProfScope ps(ISC_K_POINTWISE, (double)B * H * 4.0 * (n + 1), stream);
+  embed_mean_kernel<<<B, 128, 0, stream>>>(ids, n, V, emb, dst);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_fill(float* p, long long n, float v, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps(ISC_K_POINTWISE, (double)n * 4.0, stream);
+  fill_kernel<<<blocks, 256, 0, stream>>>(p, n, v);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace isc
