@@ -405,7 +405,7 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     ap.ld_cont_w = io.ld_cont_w;
     ap.senti_w = io.senti_w;
     ap.ld_senti_w = io.ld_senti_w;
-    ISC_TRY(launch_attention(ap, B, c.precision == ISC_PREC_BF16, c.precision == ISC_PREC_BF16, c.s));
+    ISC_TRY(launch_attention(ap, B, c.precision == ISC_PREC_BF16, c.precision, c.s));  // tanh mode == precision id
   }
   if (rl) {
     Epilogue ep;

@@ -105,18 +105,11 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// tanh with ~1e-7 absolute error: 1 - 2/(1+e^{2x}) arranged to avoid cancellation issues
-// beyond fp32 rounding of the result. Two MUFU ops (ex2, rcp).
-__device__ __forceinline__ float tanh_accurate(float x) {
-  float ax = fabsf(x);
-  float e = exp2f(-2.8853900817779268f * ax);  // e^{-2|x|}
-  float r = __fdividef(1.0f - e, 1.0f + e);
-  // small |x|: (1-e)/(1+e) loses relative accuracy; odd Taylor series is exact to fp32 there
-  if (ax < 0.04f) {
-    float x2 = ax * ax;
-    r = ax * (1.0f + x2 * (-0.33333334f + x2 * (0.13333334f - 0.053968254f * x2)));
-  }
-  return copysignf(r, x);
+// tanh with ~2e-7 ABSOLUTE error: (1 - e) / (1 + e), e = exp(-2|x|). Two MUFU ops (ex2, rcp) and no
+// branch; the attention scores are sums of alpha_j * tanh(.), so absolute error is what matters.
+__device__ __forceinline__ float tanh_ex2(float x) {
+  float e = exp2f(-2.8853900817779268f * fabsf(x));
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -2,15 +2,18 @@
 //
 //   A [M,K] and W [N,K] are K-major bf16 "planes". With passes == 3 every operand has a hi and a
 //   lo plane (x ~= hi + lo) and the kernel accumulates hi·hi + lo·hi + hi·lo in one fp32 TMEM
-//   accumulator ("bf16x3": fp32-level accuracy on the bf16 tensor pipe);
-//   with passes == 1 only the hi planes are read.
+//   accumulator ("bf16x3": 16 mantissa bits per operand on the bf16 tensor pipe, SURVEY.md
+//   section 0); with passes == 1 only the hi planes are read.
 //
-//   One 128x128 output tile per CTA. Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner +
-//   single-thread tcgen05.mma issuer, warps 2..5 = epilogue (one TMEM lane = one output row per
-//   thread). Operand tiles are 128 rows x 64 bf16 (128 B rows) in the 128B-swizzled K-major
-//   layout that both TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA shared-memory descriptor
-//   (layout type 2, SBO = 1024 B) understand; a ring of mbarrier-guarded stages decouples the
-//   producer from the issuer, tcgen05.commit releases stages and publishes the accumulator.
+//   Persistent: one CTA per SM walks 128x128 output tiles (n fastest, so concurrent CTAs share an
+//   A panel in L2). Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
+//   tcgen05.mma issuer, warps 2..5 = epilogue. Operand tiles are 128 rows x 64 bf16 (128 B rows) in
+//   the 128B-swizzled K-major layout that both TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA
+//   shared-memory descriptor (layout type 2, SBO = 1024 B) understand. Three mbarrier pipelines:
+//   smem stages full/empty (TMA <-> MMA), and two TMEM accumulator stages full/empty
+//   (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1. The epilogue moves
+//   32x32 sub-tiles TMEM -> registers -> padded smem -> registers so that every global access
+//   (bias / additive terms in, fp32 and bf16 planes out) is a coalesced 128-bit access.
 //
 // This is the only dense-contraction kernel of the decode path in the tensor-core precisions:
 // LSTM gate GEMMs, attention projections, vocabulary logits and the prologue feature embeddings
@@ -28,14 +31,17 @@ namespace tc {
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int TILE_BYTES = BM * BK * 2;  // 16 KiB, one operand plane tile
 constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 128;
+constexpr int ACC_STAGES = 2;               // TMEM accumulator double buffer
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256 columns (power of two)
+constexpr int EPI_PITCH = 36;               // floats per staged row: 32 + 4 pad, keeps 16 B alignment
+constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;  // one 32x32 staging tile per epilogue warp
 
 template <int PASSES>
 struct Cfg {
   static constexpr int kTilesPerStage = PASSES == 3 ? 4 : 2;  // A_hi,(A_lo),B_hi,(B_lo)
   static constexpr int kStageBytes = kTilesPerStage * TILE_BYTES;
   static constexpr int kStages = PASSES == 3 ? 3 : 6;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct EpiParams {
@@ -144,6 +150,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ------------------------------------------------------------------ kernel
+__device__ __forceinline__ float4 load4_guarded(const float* p, int n, int N) {
+  // p points at column n of a row; columns >= N do not exist
+  if (n + 3 < N && (reinterpret_cast<uintptr_t>(p) & 15) == 0) return __ldg(reinterpret_cast<const float4*>(p));
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < N) r.x = __ldg(p);
+  if (n + 1 < N) r.y = __ldg(p + 1);
+  if (n + 2 < N) r.z = __ldg(p + 2);
+  if (n + 3 < N) r.w = __ldg(p + 3);
+  return r;
+}
+
 template <int PASSES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -152,17 +169,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   using C = Cfg<PASSES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* full_bar = bars;                    // [kStages] TMA -> MMA
-  uint64_t* empty_bar = bars + C::kStages;      // [kStages] MMA -> TMA
-  uint64_t* accum_bar = bars + 2 * C::kStages;  // MMA -> epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 1);
+  float* epi_smem = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + EPI_BYTES);
+  uint64_t* full_bar = bars;                           // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + C::kStages;             // [kStages] MMA -> TMA
+  uint64_t* acc_full = bars + 2 * C::kStages;          // [ACC_STAGES] MMA -> epilogue
+  uint64_t* acc_empty = acc_full + ACC_STAGES;         // [ACC_STAGES] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
   const int num_kb = (ep.K + BK - 1) / BK;
+  const int tiles_n = (ep.N + BN - 1) / BN;
+  const int tiles_m = (ep.M + BM - 1) / BM;
+  const int num_tiles = tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
@@ -175,7 +195,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
@@ -192,21 +215,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer (one elected lane) =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::kStages;
-        const uint32_t ph = (kb / C::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
-        uint8_t* st = smem + s * C::kStageBytes;
-        mbar_expect_tx(&full_bar[s], C::kStageBytes);
-        const int k0 = kb * BK;
-        if (PASSES == 3) {
-          tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
-          tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, &full_bar[s], k0, m0);
-          tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
-          tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, &full_bar[s], k0, n0);
-        } else {
-          tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
-          tma_load_2d(st + 1 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
+          uint8_t* st = smem + s * C::kStageBytes;
+          mbar_expect_tx(&full_bar[s], C::kStageBytes);
+          const int k0 = kb * BK;
+          if (PASSES == 3) {
+            tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
+            tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, &full_bar[s], k0, m0);
+            tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
+            tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, &full_bar[s], k0, n0);
+          } else {
+            tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
+            tma_load_2d(st + 1 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
+          }
         }
       }
     }
@@ -214,79 +241,119 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================== MMA issuer (one elected lane) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      uint32_t accumulate = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % C::kStages;
-        const uint32_t ph = (kb / C::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const int as = j & 1;
+        mbar_wait(&acc_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
-        const uint32_t st = smem_u32(smem + s * C::kStageBytes);
-        const uint32_t a_hi = st, a_lo = st + TILE_BYTES;
-        const uint32_t b_hi = st + (PASSES == 3 ? 2 : 1) * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
+        const uint32_t tmem_d = tmem_base + as * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + s * C::kStageBytes);
+          const uint32_t a_hi = st, a_lo = st + TILE_BYTES;
+          const uint32_t b_hi = st + (PASSES == 3 ? 2 : 1) * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
 #pragma unroll
-        for (int p = 0; p < PASSES; ++p) {
-          const uint32_t a = (p == 1) ? a_lo : a_hi;  // hi·hi, lo·hi, hi·lo
-          const uint32_t b = (p == 2) ? b_lo : b_hi;
+          for (int p = 0; p < PASSES; ++p) {
+            const uint32_t a = (p == 1) ? a_lo : a_hi;  // hi·hi, lo·hi, hi·lo
+            const uint32_t b = (p == 2) ? b_lo : b_hi;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 B per 16-element K step inside the 128 B swizzle atom
-            umma_bf16(tmem_base, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, accumulate);
-            accumulate = 1;
+            for (int k = 0; k < BK / 16; ++k) {
+              // +32 B per 16-element K step inside the 128 B swizzle atom
+              umma_bf16(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, accumulate);
+              accumulate = 1;
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the stage once the MMAs above have read it
+        umma_commit(&acc_full[as]);  // accumulator of this tile complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> global =====================
     const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
-    const int row = m0 + quarter * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-    const bool row_ok = row < ep.M;
-    const float* radd = (ep.rowadd != nullptr && row_ok) ? ep.rowadd + (long long)(row / ep.rows_per_group) * ep.ld_rowadd
-                                                         : nullptr;
-    const float* madd = (ep.addmat != nullptr && row_ok) ? ep.addmat + (long long)row * ep.ld_addmat : nullptr;
+    float* sc = epi_smem + (warp - 2) * 32 * EPI_PITCH;
+    const int r_off = lane >> 3, c4 = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int as = j & 1;
+      mbar_wait(&acc_full[as], (j >> 1) & 1);
+      tcgen05_fence_after();
+      const int row_base = m0 + quarter * 32;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      float v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
-      const int nbase = n0 + c * 32;
-      if (row_ok && nbase < ep.N) {
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + c * 32, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = nbase + j;
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(sc + lane * EPI_PITCH + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const int n = n0 + c * 32 + c4 * 4;
         if (n < ep.N) {
-          float x = v[j];
-          if (ep.bias) x += __ldg(ep.bias + n);
-          if (radd) x += __ldg(radd + n);
-          if (madd) x += __ldg(madd + n);
-          v[j] = apply_act(x, ep.act);
-        }
-      }
-      const bool full = (nbase + 32 <= ep.N);
-      if (ep.c) {
-        float* dst = ep.c + (long long)row * ep.ldc + nbase;
-        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias) b4 = load4_guarded(ep.bias + n, n, ep.N);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && nbase + j < ep.N; ++j) dst[j] = v[j];
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + r_off;
+            const long long row = row_base + r;
+            if (row < ep.M) {
+              float4 x = *reinterpret_cast<const float4*>(sc + r * EPI_PITCH + c4 * 4);
+              x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+              if (ep.rowadd) {
+                float4 t = load4_guarded(ep.rowadd + (row / ep.rows_per_group) * ep.ld_rowadd + n, n, ep.N);
+                x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+              }
+              if (ep.addmat) {
+                float4 t = load4_guarded(ep.addmat + row * ep.ld_addmat + n, n, ep.N);
+                x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+              }
+              x.x = apply_act(x.x, ep.act); x.y = apply_act(x.y, ep.act);
+              x.z = apply_act(x.z, ep.act); x.w = apply_act(x.w, ep.act);
+              const bool full4 = n + 3 < ep.N;
+              if (ep.c) {
+                float* dst = ep.c + row * ep.ldc + n;
+                if (full4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                  *reinterpret_cast<float4*>(dst) = x;
+                } else {
+                  dst[0] = x.x;
+                  if (n + 1 < ep.N) dst[1] = x.y;
+                  if (n + 2 < ep.N) dst[2] = x.z;
+                  if (n + 3 < ep.N) dst[3] = x.w;
+                }
+              }
+              if (ep.hi) {
+                __nv_bfloat16 h[4], l[4];
+                split_bf16(x.x, h[0], l[0]);
+                split_bf16(x.y, h[1], l[1]);
+                split_bf16(x.z, h[2], l[2]);
+                split_bf16(x.w, h[3], l[3]);
+                __nv_bfloat16* dh = ep.hi + row * ep.ldp + n;
+                __nv_bfloat16* dl = ep.lo ? ep.lo + row * ep.ldp + n : nullptr;
+                if (full4 && (reinterpret_cast<uintptr_t>(dh) & 7) == 0) {
+                  *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(h);
+                  if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(l);
+                } else {
+                  for (int q = 0; q < 4 && n + q < ep.N; ++q) {
+                    dh[q] = h[q];
+                    if (dl) dl[q] = l[q];
+                  }
+                }
+              }
+            }
+          }
         }
+        __syncwarp();  // staging tile is reused by the next chunk
       }
-      if (ep.hi) {
-        __nv_bfloat16* dh = ep.hi + (long long)row * ep.ldp + nbase;
-        __nv_bfloat16* dl = ep.lo ? ep.lo + (long long)row * ep.ldp + nbase : nullptr;
-        for (int j = 0; j < 32 && nbase + j < ep.N; ++j) {
-          __nv_bfloat16 h, l;
-          split_bf16(v[j], h, l);
-          dh[j] = h;
-          if (dl) dl[j] = l;
-        }
+      // release the accumulator stage to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
       }
-      }
-      __syncwarp();  // reconverge before the next warp-collective tcgen05.ld
     }
   }
 
@@ -314,6 +381,17 @@ static EncodeTiledFn get_encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   });
   return fn;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 // bf16 plane [rows, cols] with leading dimension ld (elements) -> 2D map, box 64 x 128, 128B swizzle.
@@ -373,7 +451,9 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.K = K;
   ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 Cfg<PASSES>::kSmemBytes));
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const int sms = num_sms();
+  dim3 grid(tiles < sms ? tiles : sms);  // persistent: one CTA per SM walks the tile list
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
   gemm_tc_kernel<PASSES><<<grid, NUM_THREADS, Cfg<PASSES>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep);
   ISC_LAUNCH_CHECK();

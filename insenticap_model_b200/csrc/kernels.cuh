@@ -64,7 +64,7 @@ int launch_embed_pack(const long long* it, const int* parent, const float* h_in,
                       RowDest x1, RowDest x2, cudaStream_t stream);
 int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_prev, float* h_out, float* c_out,
                           RowDest extra, int extra_col, int M, cudaStream_t stream);
-int launch_attention(const AttnParams& p, int B, bool bf16_feats, bool fast_tanh, cudaStream_t stream);
+int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode, cudaStream_t stream);
 int launch_gate_mix(const float* g3, const float* cs, const float* alpha, const float* alpha_b, RowDest ctx,
                     float* gate_w, long long ld_gate_w, int M, cudaStream_t stream);
 int launch_embed_rows(const long long* ids, long long groups, long long n_per_group, int prepend_pad, int pad_id, int V,

@@ -155,6 +155,13 @@ __global__ void __launch_bounds__(NT) greedy_select_kernel(GreedyParams p) {
   }
 }
 
+// Beam expansion + pooled stable top-K, one CTA per image.
+// Per live beam row: pass 1 = thread-local maxima with 128-bit loads; the (K+4)-th largest thread
+// maximum is a threshold tau that at least K unmasked entries reach (<= 4 entries are masked);
+// pass 2 = sum of exp for the log-softmax normaliser + collection of the few entries >= tau;
+// thread 0 ranks them (value desc, index asc). Then the pool of all rows is ranked stably.
+constexpr int CAND_CAP = 512;
+
 __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
   __shared__ float red[NT / 32];
   __shared__ float redv[NT / 32];
@@ -165,6 +172,9 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
   __shared__ int pool_n;
   __shared__ long long last_sm[KMAX];
   __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
+  __shared__ float cand_v[CAND_CAP];
+  __shared__ int cand_i[CAND_CAP];
+  __shared__ int cand_n;
   const int b = blockIdx.x, K = p.K, V = p.V, t = p.t, T = p.T;
   if (threadIdx.x < K) last_sm[threadIdx.x] = p.it[b * K + threadIdx.x];
   if (threadIdx.x == 0) pool_n = 0;
@@ -186,56 +196,74 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
       continue;
     }
     const float* row = p.logits + (long long)(b * K + k) * p.ld;
-    float topv[KMAX];
-    int topi[KMAX];
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) {
-      topv[j] = -CUDART_INF_F;
-      topi[j] = 0x7fffffff;
+    const int v4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 2) : 0;
+    // ---- pass 1: thread-local maximum
+    float tmax = -CUDART_INF_F;
+    for (int i = threadIdx.x; i < v4; i += NT) {
+      float4 x = reinterpret_cast<const float4*>(row)[i];
+      tmax = fmaxf(fmaxf(tmax, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
     }
-    float mx = -CUDART_INF_F;
-    for (int i = threadIdx.x; i < V; i += NT) {
-      const float x = row[i];
-      mx = fmaxf(mx, x);
-      bool masked = (mask_special && (i == p.pad_id || i == p.sos_id || i == p.unk_id)) || (p.constraint && i == last);
-      if (!masked && x > topv[KMAX - 1]) {
-        topv[KMAX - 1] = x;
-        topi[KMAX - 1] = i;
-#pragma unroll
-        for (int j = KMAX - 1; j > 0; --j) {
-          if (topv[j] > topv[j - 1]) {
-            float tv = topv[j]; topv[j] = topv[j - 1]; topv[j - 1] = tv;
-            int ti = topi[j]; topi[j] = topi[j - 1]; topi[j - 1] = ti;
+    for (int i = v4 * 4 + threadIdx.x; i < V; i += NT) tmax = fmaxf(tmax, row[i]);
+    const float mx = block_max(tmax, red);
+    float tau = -CUDART_INF_F;
+    {
+      float mine = tmax;
+      const int need = (K + 4 < NT) ? K + 4 : NT;
+      for (int r = 0; r < need; ++r) {
+        float v = mine;
+        int idx = threadIdx.x;
+        block_argmax(v, idx, redv, redi);
+        if (idx == (int)threadIdx.x) mine = -CUDART_INF_F;
+        tau = v;
+      }
+    }
+    if (threadIdx.x == 0) cand_n = 0;
+    __syncthreads();
+    // ---- pass 2: normaliser + candidates
+    float s = 0.f;
+    auto visit = [&](float x, int i) {
+      s += __expf(x - mx);
+      if (x >= tau) {
+        const bool masked = (mask_special && (i == p.pad_id || i == p.sos_id || i == p.unk_id)) || (p.constraint && i == last);
+        if (!masked) {
+          int slot = atomicAdd(&cand_n, 1);
+          if (slot < CAND_CAP) {
+            cand_v[slot] = x;
+            cand_i[slot] = i;
           }
         }
       }
+    };
+    for (int i = threadIdx.x; i < v4; i += NT) {
+      float4 x = reinterpret_cast<const float4*>(row)[i];
+      visit(x.x, 4 * i);
+      visit(x.y, 4 * i + 1);
+      visit(x.z, 4 * i + 2);
+      visit(x.w, 4 * i + 3);
     }
-    mx = block_max(mx, red);
-    const float ls = logf(row_sumexp(row, V, mx, red));
-    const double base = p.score_in[b * K + k];
-    for (int r = 0; r < K; ++r) {
-      float v = topv[0];
-      int idx = topi[0];
-      block_argmax(v, idx, redv, redi);
-      if (idx == topi[0] && idx != 0x7fffffff) {  // this thread owned the winner: pop it
-#pragma unroll
-        for (int j = 0; j < KMAX - 1; ++j) {
-          topv[j] = topv[j + 1];
-          topi[j] = topi[j + 1];
+    for (int i = v4 * 4 + threadIdx.x; i < V; i += NT) visit(row[i], i);
+    const float ls = logf(block_sum(s, red));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int n = cand_n < CAND_CAP ? cand_n : CAND_CAP;
+      const double base = p.score_in[b * K + k];
+      for (int r = 0; r < K; ++r) {
+        int best = -1;
+        for (int i = 0; i < n; ++i) {
+          if (cand_i[i] < 0) continue;
+          if (best < 0 || cand_v[i] > cand_v[best] || (cand_v[i] == cand_v[best] && cand_i[i] < cand_i[best])) best = i;
         }
-        topv[KMAX - 1] = -CUDART_INF_F;
-        topi[KMAX - 1] = 0x7fffffff;
+        if (best < 0) break;
+        const float lp = (cand_v[best] - mx) - ls;  // log_softmax value, fp32 like the reference
+        int np = pool_n;
+        pool_score[np] = base + (double)lp;  // python-float running sum (captioner.py:404-407)
+        pool_parent[np] = k;
+        pool_word[np] = cand_i[best];
+        pool_n = np + 1;
+        cand_i[best] = -1;
       }
-      if (threadIdx.x == 0 && idx != 0x7fffffff) {
-        const float lp = (v - mx) - ls;  // log_softmax value of the candidate, fp32 like the reference
-        int n = pool_n;
-        pool_score[n] = base + (double)lp;  // python-float running sum (captioner.py:404-407)
-        pool_parent[n] = k;
-        pool_word[n] = idx;
-        pool_n = n + 1;
-      }
-      __syncthreads();
     }
+    __syncthreads();
   }
   __syncthreads();
   if (threadIdx.x == 0) {

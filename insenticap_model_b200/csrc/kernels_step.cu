@@ -91,7 +91,7 @@ struct FeatLoad<__nv_bfloat16> {
   static constexpr int kWidth = 8;
 };
 
-template <typename FeatT, bool FAST_TANH>
+template <typename FeatT, int TANH_MODE>
 __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
                                            const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
                                            float* __restrict__ score_smem /*[R][n_items]*/, int warp, int lane, int n_warps) {
@@ -110,7 +110,7 @@ __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int
 #pragma unroll
         for (int j = 0; j < L::kWidth; ++j) {
           float x = pv[i][j] + q[c0 + j];
-          float t = FAST_TANH ? tanh_fast(x) : tanh_accurate(x);
+          float t = TANH_MODE == 2 ? tanh_fast(x) : (TANH_MODE == 1 ? tanh_ex2(x) : tanhf(x));
           acc = fmaf(alpha_smem[c0 + j], t, acc);
         }
       }
@@ -192,7 +192,9 @@ __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int
     if (r < R) dst.store2(row0 + r, dst_col + c, acc[r]);
 }
 
-template <typename FeatT, bool FAST_TANH>
+// TANH_MODE: 0 = libdevice tanhf (ISC_PREC_FP32), 1 = ex2-based, |err| ~ 2e-7 (ISC_PREC_BF16X3),
+// 2 = tanh.approx.f32, one MUFU (ISC_PREC_BF16)
+template <typename FeatT, int TANH_MODE>
 __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   extern __shared__ float sm[];
   const int R = p.R, L = p.L, S = p.S;
@@ -219,10 +221,10 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   const FeatT* att = reinterpret_cast<const FeatT*>(p.att);
   const FeatT* p_att = reinterpret_cast<const FeatT*>(p.p_att);
   if (att) {
-    score_rows<FeatT, FAST_TANH>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c, warp, lane, 8);
+    score_rows<FeatT, TANH_MODE>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c, warp, lane, 8);
   }
   if (p.sw) {
-    score_rows<float, FAST_TANH>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, warp, lane, 8);
+    score_rows<float, TANH_MODE>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, warp, lane, 8);
   }
   __syncthreads();
   if (att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   if (p.sw) weighted_sum<float, 8>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
 }
 
-int launch_attention(const AttnParams& p, int B, bool bf16_feats, bool fast_tanh, cudaStream_t stream) {
+int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode, cudaStream_t stream) {
   ISC_REQUIRE(p.R >= 1 && p.R <= 8, "attention: rows per image %d not in 1..8", p.R);
   size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * p.L + p.R * p.S);
   // algorithmic HBM bytes: both feature tensors of every image once per launch (shared by its R rows),
@@ -241,15 +243,13 @@ int launch_attention(const AttnParams& p, int B, bool bf16_feats, bool fast_tanh
   const double bytes = (double)B * ((p.att ? 2.0 * p.L * H * feat_b : 0.0) + (p.sw ? 2.0 * p.S * H * 4.0 : 0.0) +
                                     (double)p.R * (3.0 * H * 4.0 + 2.0 * H * 4.0));
   ProfScope ps(ISC_K_ATTENTION, bytes, stream);
-  if (bf16_feats) {
-    auto k = fast_tanh ? attention_kernel<__nv_bfloat16, true> : attention_kernel<__nv_bfloat16, false>;
-    ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<B, 256, smem, stream>>>(p);
-  } else {
-    auto k = fast_tanh ? attention_kernel<float, true> : attention_kernel<float, false>;
-    ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<B, 256, smem, stream>>>(p);
-  }
+  void (*k)(AttnParams) = nullptr;
+  if (bf16_feats)
+    k = tanh_mode == 2 ? attention_kernel<__nv_bfloat16, 2> : (tanh_mode == 1 ? attention_kernel<__nv_bfloat16, 1> : attention_kernel<__nv_bfloat16, 0>);
+  else
+    k = tanh_mode == 2 ? attention_kernel<float, 2> : (tanh_mode == 1 ? attention_kernel<float, 1> : attention_kernel<float, 0>);
+  ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<B, 256, smem, stream>>>(p);
   ISC_LAUNCH_CHECK();
   return 0;
 }
