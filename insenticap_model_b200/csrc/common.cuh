@@ -108,8 +108,11 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 // tanh with ~2e-7 ABSOLUTE error: (1 - e) / (1 + e), e = exp(-2|x|). Two MUFU ops (ex2, rcp) and no
 // branch; the attention scores are sums of alpha_j * tanh(.), so absolute error is what matters.
 __device__ __forceinline__ float tanh_ex2(float x) {
-  float e = exp2f(-2.8853900817779268f * fabsf(x));
-  return copysignf(__fdividef(1.0f - e, 1.0f + e), x);
+  float e, r;
+  // e = 2^(-2|x| log2 e) <= 1: the raw MUFU op needs no range fix-up (underflow flushes to 0 -> tanh = 1)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * fabsf(x)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return copysignf((1.0f - e) * r, x);
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -11,8 +11,8 @@
 //   the 128B-swizzled K-major layout that both TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA
 //   shared-memory descriptor (layout type 2, SBO = 1024 B) understand. Three mbarrier pipelines:
 //   smem stages full/empty (TMA <-> MMA), and two TMEM accumulator stages full/empty
-//   (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1. The epilogue moves
-//   32x32 sub-tiles TMEM -> registers -> padded smem -> registers so that every global access
+//   (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1. The 8 epilogue warps
+//   move 32x32 sub-tiles TMEM -> registers -> XOR-swizzled smem -> registers so that every global access
 //   (bias / additive terms in, fp32 and bf16 planes out) is a coalesced 128-bit access.
 //
 // This is the only dense-contraction kernel of the decode path in the tensor-core precisions:
@@ -30,11 +30,11 @@ namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int TILE_BYTES = BM * BK * 2;  // 16 KiB, one operand plane tile
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                // two per TMEM lane quarter, each owns half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2;               // TMEM accumulator double buffer
 constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256 columns (power of two)
-constexpr int EPI_PITCH = 36;               // floats per staged row: 32 + 4 pad, keeps 16 B alignment
-constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;  // one 32x32 staging tile per epilogue warp
+constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one XOR-swizzled 32x32 fp32 staging tile per epilogue warp
 
 template <int PASSES>
 struct Cfg {
@@ -161,7 +161,14 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int n, int N) {
   return r;
 }
 
-template <int PASSES>
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+  if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int PASSES, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -197,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], EPI_WARPS);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -273,50 +280,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> smem transpose -> global =====================
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> global =====================
+    const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
-    float* sc = epi_smem + (warp - 2) * 32 * EPI_PITCH;
+    const int half = ew >> 2;      // which 64 of the tile's 128 columns this warp drains
+    float4* sc = reinterpret_cast<float4*>(epi_smem) + ew * 32 * 8;  // 32 rows x 8 float4, slot ^= row & 7
     const int r_off = lane >> 3, c4 = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
+    const bool c_vec = ep.c && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && ((ep.ldc & 3) == 0);
+    const bool p_vec = ep.hi && ((reinterpret_cast<uintptr_t>(ep.hi) & 7) == 0) && ((ep.ldp & 3) == 0) &&
+                       (!ep.lo || (reinterpret_cast<uintptr_t>(ep.lo) & 7) == 0);
+    const bool radd_vec = ep.rowadd && ((reinterpret_cast<uintptr_t>(ep.rowadd) & 15) == 0) && ((ep.ld_rowadd & 3) == 0);
+    const bool madd_vec = ep.addmat && ((reinterpret_cast<uintptr_t>(ep.addmat) & 15) == 0) && ((ep.ld_addmat & 3) == 0);
+    const bool bias_vec = ep.bias && ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int as = j & 1;
+      const int row0 = m0 + quarter * 32 + r_off;  // this lane's rows: row0 + 4*i, i = 0..7
+      int nvalid = (ep.M - row0 + 3) >> 2;
+      nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
+      const float* radd[8];
+      if (ep.rowadd) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          radd[i] = ep.rowadd + (long long)((unsigned)(row0 + 4 * i) / (unsigned)ep.rows_per_group) * ep.ld_rowadd;
+      }
       mbar_wait(&acc_full[as], (j >> 1) & 1);
       tcgen05_fence_after();
-      const int row_base = m0 + quarter * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + c * 32, v);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(sc + lane * EPI_PITCH + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          sc[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
         const int n = n0 + c * 32 + c4 * 4;
         if (n < ep.N) {
+          const bool full4 = n + 3 < ep.N;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias) b4 = load4_guarded(ep.bias + n, n, ep.N);
+          if (ep.bias) b4 = (full4 && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + r_off;
-            const long long row = row_base + r;
-            if (row < ep.M) {
-              float4 x = *reinterpret_cast<const float4*>(sc + r * EPI_PITCH + c4 * 4);
+            if (i < nvalid) {
+              const int r = 4 * i + r_off;
+              const long long row = row0 + 4 * i;
+              float4 x = sc[r * 8 + (c4 ^ (r & 7))];
               x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
               if (ep.rowadd) {
-                float4 t = load4_guarded(ep.rowadd + (row / ep.rows_per_group) * ep.ld_rowadd + n, n, ep.N);
+                float4 t = (full4 && radd_vec) ? __ldg(reinterpret_cast<const float4*>(radd[i] + n)) : load4_guarded(radd[i] + n, n, ep.N);
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
               if (ep.addmat) {
-                float4 t = load4_guarded(ep.addmat + row * ep.ld_addmat + n, n, ep.N);
+                const float* mp = ep.addmat + row * ep.ld_addmat + n;
+                float4 t = (full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N);
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
-              x.x = apply_act(x.x, ep.act); x.y = apply_act(x.y, ep.act);
-              x.z = apply_act(x.z, ep.act); x.w = apply_act(x.w, ep.act);
-              const bool full4 = n + 3 < ep.N;
+              x.x = act_ct<ACT>(x.x); x.y = act_ct<ACT>(x.y); x.z = act_ct<ACT>(x.z); x.w = act_ct<ACT>(x.w);
               if (ep.c) {
                 float* dst = ep.c + row * ep.ldc + n;
-                if (full4 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                if (full4 && c_vec) {
                   *reinterpret_cast<float4*>(dst) = x;
                 } else {
                   dst[0] = x.x;
@@ -333,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 split_bf16(x.w, h[3], l[3]);
                 __nv_bfloat16* dh = ep.hi + row * ep.ldp + n;
                 __nv_bfloat16* dl = ep.lo ? ep.lo + row * ep.ldp + n : nullptr;
-                if (full4 && (reinterpret_cast<uintptr_t>(dh) & 7) == 0) {
+                if (full4 && p_vec) {
                   *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(h);
                   if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(l);
                 } else {
@@ -420,6 +444,16 @@ static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, i
   return 0;
 }
 
+template <int PASSES, int ACT>
+static int launch_kernel(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+                         const CUtensorMap& mb_lo, const EpiParams& ep, int grid, cudaStream_t stream) {
+  ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<PASSES>::kSmemBytes));
+  gemm_tc_kernel<PASSES, ACT><<<grid, NUM_THREADS, Cfg<PASSES>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int PASSES>
 static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int N, int K, const Epilogue& e,
                   cudaStream_t stream) {
@@ -449,15 +483,13 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.M = M;
   ep.N = N;
   ep.K = K;
-  ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<PASSES>::kSmemBytes));
   const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   const int sms = num_sms();
-  dim3 grid(tiles < sms ? tiles : sms);  // persistent: one CTA per SM walks the tile list
+  const int grid = tiles < sms ? tiles : sms;  // persistent: one CTA per SM walks the tile list
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
-  gemm_tc_kernel<PASSES><<<grid, NUM_THREADS, Cfg<PASSES>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep);
-  ISC_LAUNCH_CHECK();
-  return 0;
+  if (e.act == ACT_RELU) return launch_kernel<PASSES, ACT_RELU>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
+  if (e.act == ACT_TANH) return launch_kernel<PASSES, ACT_TANH>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
+  return launch_kernel<PASSES, ACT_NONE>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
 }
 
 }  // namespace tc

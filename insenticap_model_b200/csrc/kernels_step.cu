@@ -91,31 +91,46 @@ struct FeatLoad<__nv_bfloat16> {
   static constexpr int kWidth = 8;
 };
 
-template <typename FeatT, int TANH_MODE>
+// RT > 0: rows per image known at compile time (fully unrolled); RT == 0: runtime R <= 8.
+template <typename FeatT, int TANH_MODE, int RT>
 __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
                                            const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
                                            float* __restrict__ score_smem /*[R][n_items]*/, int warp, int lane, int n_warps) {
   using L = FeatLoad<FeatT>;
+  constexpr int RU = RT > 0 ? RT : 8;
+  float al[L::kChunks][L::kWidth];  // this lane's slice of alpha stays in registers
+#pragma unroll
+  for (int i = 0; i < L::kChunks; ++i)
+#pragma unroll
+    for (int j = 0; j < L::kWidth; ++j) al[i][j] = alpha_smem[L::col(lane, i) + j];
   for (int l = warp; l < n_items; l += n_warps) {
     const FeatT* row = p_feat + (long long)l * H;
     float pv[L::kChunks][L::kWidth];
 #pragma unroll
     for (int i = 0; i < L::kChunks; ++i) L::load(row, lane, i, pv[i]);
-    for (int r = 0; r < R; ++r) {
-      const float* q = q_smem + r * H;
-      float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < L::kChunks; ++i) {
-        const int c0 = L::col(lane, i);
+    for (int r = 0; r < RU; ++r) {
+      if (RT > 0 || r < R) {
+        const float* q = q_smem + r * H;
+        float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < L::kWidth; ++j) {
-          float x = pv[i][j] + q[c0 + j];
-          float t = TANH_MODE == 2 ? tanh_fast(x) : (TANH_MODE == 1 ? tanh_ex2(x) : tanhf(x));
-          acc = fmaf(alpha_smem[c0 + j], t, acc);
+        for (int i = 0; i < L::kChunks; ++i) {
+          const int c0 = L::col(lane, i);
+#pragma unroll
+          for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
+            const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
+            const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x = pv[i][j4 + j] + qq[j];
+              float t = TANH_MODE == 2 ? tanh_fast(x) : (TANH_MODE == 1 ? tanh_ex2(x) : tanhf(x));
+              acc = fmaf(al[i][j4 + j], t, acc);
+            }
+          }
         }
+        acc = warp_sum(acc);
+        if (lane == 0) score_smem[r * n_items + l] = acc;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) score_smem[r * n_items + l] = acc;
     }
   }
 }
@@ -154,56 +169,62 @@ __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
-// context[r] = sum_l w[r][l] * feat[l] ; thread owns columns (2t, 2t+1)
-template <typename FeatT, int RMAX>
+// context[r] = sum_l w[r][l] * feat[l] ; thread owns columns (2t, 2t+1); weights are read from smem four
+// items at a time (128-bit broadcast loads) when the row length allows it
+template <typename FeatT, int RT>
 __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int n_items, int R,
                                              const float* __restrict__ w_smem, RowDest dst, long long row0, int dst_col) {
+  constexpr int RU = RT > 0 ? RT : 8;
   const int c = threadIdx.x * 2;
-  float2 acc[RMAX];
+  float2 acc[RU];
 #pragma unroll
-  for (int r = 0; r < RMAX; ++r) acc[r] = make_float2(0.f, 0.f);
+  for (int r = 0; r < RU; ++r) acc[r] = make_float2(0.f, 0.f);
   int l = 0;
-  for (; l + 4 <= n_items; l += 4) {
-    float2 a[4];
+  if ((n_items & 3) == 0 && (reinterpret_cast<uintptr_t>(w_smem) & 15) == 0) {
+    for (; l + 4 <= n_items; l += 4) {
+      float2 a[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) a[u] = load2<FeatT>(feat + (long long)(l + u) * H + c);
+      for (int u = 0; u < 4; ++u) a[u] = load2<FeatT>(feat + (long long)(l + u) * H + c);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-      for (int r = 0; r < RMAX; ++r)
-        if (r < R) {
-          float w = w_smem[r * n_items + l + u];
-          acc[r].x = fmaf(w, a[u].x, acc[r].x);
-          acc[r].y = fmaf(w, a[u].y, acc[r].y);
+      for (int r = 0; r < RU; ++r)
+        if (RT > 0 || r < R) {
+          const float4 w = *reinterpret_cast<const float4*>(w_smem + r * n_items + l);
+          acc[r].x = fmaf(w.x, a[0].x, acc[r].x); acc[r].y = fmaf(w.x, a[0].y, acc[r].y);
+          acc[r].x = fmaf(w.y, a[1].x, acc[r].x); acc[r].y = fmaf(w.y, a[1].y, acc[r].y);
+          acc[r].x = fmaf(w.z, a[2].x, acc[r].x); acc[r].y = fmaf(w.z, a[2].y, acc[r].y);
+          acc[r].x = fmaf(w.w, a[3].x, acc[r].x); acc[r].y = fmaf(w.w, a[3].y, acc[r].y);
         }
+    }
   }
   for (; l < n_items; ++l) {
     float2 a = load2<FeatT>(feat + (long long)l * H + c);
 #pragma unroll
-    for (int r = 0; r < RMAX; ++r)
-      if (r < R) {
+    for (int r = 0; r < RU; ++r)
+      if (RT > 0 || r < R) {
         float w = w_smem[r * n_items + l];
         acc[r].x = fmaf(w, a.x, acc[r].x);
         acc[r].y = fmaf(w, a.y, acc[r].y);
       }
   }
 #pragma unroll
-  for (int r = 0; r < RMAX; ++r)
-    if (r < R) dst.store2(row0 + r, dst_col + c, acc[r]);
+  for (int r = 0; r < RU; ++r)
+    if (RT > 0 || r < R) dst.store2(row0 + r, dst_col + c, acc[r]);
 }
 
-// TANH_MODE: 0 = libdevice tanhf (ISC_PREC_FP32), 1 = ex2-based, |err| ~ 2e-7 (ISC_PREC_BF16X3),
+// TANH_MODE: 0 = libdevice tanhf (ISC_PREC_FP32), 1 = ex2/rcp based, |err| ~ 2e-7 (ISC_PREC_BF16X3),
 // 2 = tanh.approx.f32, one MUFU (ISC_PREC_BF16)
-template <typename FeatT, int TANH_MODE>
+template <typename FeatT, int TANH_MODE, int RT>
 __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
-  extern __shared__ float sm[];
-  const int R = p.R, L = p.L, S = p.S;
+  extern __shared__ __align__(16) float sm[];
+  const int R = RT > 0 ? RT : p.R, L = p.L, S = p.S;
+  const int Lp = (L + 3) & ~3, Sp = (S + 3) & ~3;  // padded score rows keep 16-byte alignment
   float* q_c = sm;                 // [R][H] content query  h2att(h)
   float* q_s = q_c + R * H;        // [R][H] senti query    h2word(h) + label2word(sl)
   float* alpha_c = q_s + R * H;    // [H]
   float* alpha_s = alpha_c + H;    // [H]
   float* sc_c = alpha_s + H;       // [R][L]
-  float* sc_s = sc_c + R * L;      // [R][S]
+  float* sc_s = sc_c + R * Lp;     // [R][S]
+  (void)Sp;
   const int img = blockIdx.x;
   const long long row0 = (long long)img * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,38 +241,45 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   __syncthreads();
   const FeatT* att = reinterpret_cast<const FeatT*>(p.att);
   const FeatT* p_att = reinterpret_cast<const FeatT*>(p.p_att);
-  if (att) {
-    score_rows<FeatT, TANH_MODE>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c, warp, lane, 8);
-  }
-  if (p.sw) {
-    score_rows<float, TANH_MODE>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, warp, lane, 8);
-  }
+  if (att) score_rows<FeatT, TANH_MODE, RT>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c, warp, lane, 8);
+  if (p.sw) score_rows<float, TANH_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, warp, lane, 8);
   __syncthreads();
   if (att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
   if (p.sw) softmax_rows(sc_s, S, R, warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
   __syncthreads();
-  if (att) weighted_sum<FeatT, 8>(att + (long long)img * L * H, L, R, sc_c, p.cont_dst, row0, p.cont_col);
-  if (p.sw) weighted_sum<float, 8>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+  if (att) weighted_sum<FeatT, RT>(att + (long long)img * L * H, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  if (p.sw) weighted_sum<float, RT>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+}
+
+template <typename FeatT, int TANH_MODE>
+static int launch_attention_t(const AttnParams& p, int B, size_t smem, cudaStream_t stream) {
+  void (*k)(AttnParams) = nullptr;
+  switch (p.R) {
+    case 1: k = attention_kernel<FeatT, TANH_MODE, 1>; break;
+    case 3: k = attention_kernel<FeatT, TANH_MODE, 3>; break;
+    case 5: k = attention_kernel<FeatT, TANH_MODE, 5>; break;
+    default: k = attention_kernel<FeatT, TANH_MODE, 0>; break;
+  }
+  ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<B, 256, smem, stream>>>(p);
+  ISC_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode, cudaStream_t stream) {
   ISC_REQUIRE(p.R >= 1 && p.R <= 8, "attention: rows per image %d not in 1..8", p.R);
-  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * p.L + p.R * p.S);
+  ISC_REQUIRE((bf16_feats && tanh_mode == 2) || (!bf16_feats && tanh_mode != 2), "attention: feature dtype / tanh mode mismatch");
+  const int Lp = (p.L + 3) & ~3, Sp = (p.S + 3) & ~3;
+  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp);
   // algorithmic HBM bytes: both feature tensors of every image once per launch (shared by its R rows),
   // sentiment-word features, the R query rows in and the R context rows out
   const double feat_b = bf16_feats ? 2.0 : 4.0;
   const double bytes = (double)B * ((p.att ? 2.0 * p.L * H * feat_b : 0.0) + (p.sw ? 2.0 * p.S * H * 4.0 : 0.0) +
                                     (double)p.R * (3.0 * H * 4.0 + 2.0 * H * 4.0));
   ProfScope ps(ISC_K_ATTENTION, bytes, stream);
-  void (*k)(AttnParams) = nullptr;
-  if (bf16_feats)
-    k = tanh_mode == 2 ? attention_kernel<__nv_bfloat16, 2> : (tanh_mode == 1 ? attention_kernel<__nv_bfloat16, 1> : attention_kernel<__nv_bfloat16, 0>);
-  else
-    k = tanh_mode == 2 ? attention_kernel<float, 2> : (tanh_mode == 1 ? attention_kernel<float, 1> : attention_kernel<float, 0>);
-  ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<B, 256, smem, stream>>>(p);
-  ISC_LAUNCH_CHECK();
-  return 0;
+  if (bf16_feats) return launch_attention_t<__nv_bfloat16, 2>(p, B, smem, stream);
+  if (tanh_mode == 1) return launch_attention_t<float, 1>(p, B, smem, stream);
+  return launch_attention_t<float, 0>(p, B, smem, stream);
 }
 
 // --------------------------------------------------------------------------------------------
