@@ -218,6 +218,10 @@ struct DecodeWs {
   int* alive[2];
   float* fcsl;
   Planes pfcsl;
+  float* cand_lp;
+  int* cand_word;
+  int* cand_count;
+  int* ticket;
   long long ld_logits;
   size_t total;
 };
@@ -262,6 +266,10 @@ DecodeWs carve_decode(const isc_dims_t& d, int precision, int M, void* base) {
   }
   w.fcsl = b.take<float>(m * 2 * H);
   planes(w.pfcsl, m * 2 * H);
+  w.cand_lp = b.take<float>(m * 8);
+  w.cand_word = b.take<int>(m * 8);
+  w.cand_count = b.take<int>(m);
+  w.ticket = b.take<int>(m);
   w.total = (b.off + 255) & ~size_t(255);
   return w;
 }
@@ -878,6 +886,7 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
   ISC_CUDA(cudaMemsetAsync(w.state_h[0], 0, st, c.s));
   ISC_CUDA(cudaMemsetAsync(w.state_c[0], 0, st, c.s));
   ISC_CUDA(cudaMemsetAsync(w.tok[0], 0, (size_t)M * T * sizeof(int), c.s));
+  ISC_CUDA(cudaMemsetAsync(w.ticket, 0, (size_t)B * sizeof(int), c.s));
   ISC_TRY(launch_beam_init(w.it, w.alive[0], w.len[0], w.score[0], w.parent, B, K, dims->sos_id, c.s));
   for (int t = 0; t < T; ++t) {
     StepIO io;
@@ -913,6 +922,10 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
     bp.alive_out = w.alive[(t + 1) & 1];
     bp.it = w.it;
     bp.parent = w.parent;
+    bp.cand_lp = w.cand_lp;
+    bp.cand_word = w.cand_word;
+    bp.cand_count = w.cand_count;
+    bp.ticket = w.ticket;
     ISC_TRY(launch_beam_select(bp, c.s));
   }
   return launch_beam_finalize(w.tok[T & 1], w.len[T & 1], w.score[T & 1], reinterpret_cast<long long*>(tokens), scores,

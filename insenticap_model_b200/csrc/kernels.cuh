@@ -110,6 +110,11 @@ struct BeamParams {
   int* alive_out = nullptr;
   long long* it = nullptr;  // [B*K] last word per beam: read as "last", written for the next step
   int* parent = nullptr;    // [B*K] absolute state row each new beam continues from (written)
+  // scratch: per-row candidates published by the row CTAs, per-image ticket counter (zeroed once)
+  float* cand_lp = nullptr;  // [B*K, 8]
+  int* cand_word = nullptr;  // [B*K, 8]
+  int* cand_count = nullptr; // [B*K]
+  int* ticket = nullptr;     // [B]
 };
 int launch_beam_select(const BeamParams& p, cudaStream_t stream);
 int launch_beam_init(long long* it, int* alive, int* len, double* score, int* parent, int B, int K, int sos_id,

@@ -155,47 +155,33 @@ __global__ void __launch_bounds__(NT) greedy_select_kernel(GreedyParams p) {
   }
 }
 
-// Beam expansion + pooled stable top-K, one CTA per image.
-// Per live beam row: pass 1 = thread-local maxima with 128-bit loads; the (K+4)-th largest thread
-// maximum is a threshold tau that at least K unmasked entries reach (<= 4 entries are masked);
-// pass 2 = sum of exp for the log-softmax normaliser + collection of the few entries >= tau;
-// thread 0 ranks them (value desc, index asc). Then the pool of all rows is ranked stably.
+// Beam expansion + pooled stable top-K. One CTA per beam ROW scans its logits:
+//   pass 1 = thread-local maxima with 128-bit loads; the (K+4)-th largest thread maximum is a threshold
+//   tau that at least K unmasked entries reach (<= 4 entries are masked);
+//   pass 2 = sum of exp for the log-softmax normaliser + collection of the few entries >= tau;
+//   thread 0 ranks them (value desc, index asc) and publishes the row's K candidates.
+// The LAST CTA of an image to finish (atomic ticket) pools the candidates of the image's rows with the
+// carried finished beams and ranks them stably by fp64 score (captioner.py:409).
 constexpr int CAND_CAP = 512;
 
 __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
   __shared__ float red[NT / 32];
-  __shared__ float redv[NT / 32];
-  __shared__ int redi[NT / 32];
-  __shared__ double pool_score[KMAX * KMAX + KMAX];
-  __shared__ int pool_parent[KMAX * KMAX + KMAX];
-  __shared__ int pool_word[KMAX * KMAX + KMAX];
-  __shared__ int pool_n;
-  __shared__ long long last_sm[KMAX];
-  __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
   __shared__ float cand_v[CAND_CAP];
   __shared__ int cand_i[CAND_CAP];
   __shared__ int cand_n;
-  const int b = blockIdx.x, K = p.K, V = p.V, t = p.t, T = p.T;
-  if (threadIdx.x < K) last_sm[threadIdx.x] = p.it[b * K + threadIdx.x];
-  if (threadIdx.x == 0) pool_n = 0;
-  __syncthreads();
+  __shared__ int is_last;
+  __shared__ float gmax[32];
+  __shared__ float stat[2];
+  __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
+  const int m = blockIdx.x, K = p.K, V = p.V, t = p.t, T = p.T;
+  const int b = m / K;
   const bool mask_special = (p.pad_id != p.eos_id);
+  const int last = (int)p.it[m];
+  const bool alive = p.alive_in[m] != 0;
+  const bool finished = alive && t > 0 && last == p.eos_id;  // carried unchanged (captioner.py:385-386)
 
-  for (int k = 0; k < K; ++k) {
-    if (!p.alive_in[b * K + k]) continue;  // uniform across the block
-    const int last = (int)last_sm[k];
-    if (t > 0 && last == p.eos_id) {  // finished: carried unchanged (captioner.py:385-386)
-      if (threadIdx.x == 0) {
-        int n = pool_n;
-        pool_score[n] = p.score_in[b * K + k];
-        pool_parent[n] = k;
-        pool_word[n] = -1;
-        pool_n = n + 1;
-      }
-      __syncthreads();
-      continue;
-    }
-    const float* row = p.logits + (long long)(b * K + k) * p.ld;
+  if (alive && !finished) {
+    const float* row = p.logits + (long long)m * p.ld;
     const int v4 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0) ? (V >> 2) : 0;
     // ---- pass 1: thread-local maximum
     float tmax = -CUDART_INF_F;
@@ -204,19 +190,30 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
       tmax = fmaxf(fmaxf(tmax, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
     }
     for (int i = v4 * 4 + threadIdx.x; i < V; i += NT) tmax = fmaxf(tmax, row[i]);
-    const float mx = block_max(tmax, red);
-    float tau = -CUDART_INF_F;
+    // 32 group maxima (8 lanes each); warp 0 ranks them: row max and the (K+4)-th largest as threshold
     {
-      float mine = tmax;
-      const int need = (K + 4 < NT) ? K + 4 : NT;
-      for (int r = 0; r < need; ++r) {
-        float v = mine;
-        int idx = threadIdx.x;
-        block_argmax(v, idx, redv, redi);
-        if (idx == (int)threadIdx.x) mine = -CUDART_INF_F;
-        tau = v;
+      float g = tmax;
+      g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, 1));
+      g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, 2));
+      g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, 4));
+      if ((threadIdx.x & 7) == 0) gmax[threadIdx.x >> 3] = g;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        const float v = gmax[threadIdx.x];
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float o = __shfl_sync(0xffffffffu, v, j);
+          rank += (o > v || (o == v && j < (int)threadIdx.x)) ? 1 : 0;
+        }
+        const int need = (K + 4 < 32) ? K + 4 : 32;
+        if (rank == need - 1) stat[1] = v;
+        if (rank == 0) stat[0] = v;
       }
+      __syncthreads();
     }
+    const float mx = stat[0];
+    const float tau = stat[1];
     if (threadIdx.x == 0) cand_n = 0;
     __syncthreads();
     // ---- pass 2: normaliser + candidates
@@ -246,54 +243,86 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
     __syncthreads();
     if (threadIdx.x == 0) {
       const int n = cand_n < CAND_CAP ? cand_n : CAND_CAP;
-      const double base = p.score_in[b * K + k];
-      for (int r = 0; r < K; ++r) {
+      int r = 0;
+      for (; r < K; ++r) {
         int best = -1;
         for (int i = 0; i < n; ++i) {
           if (cand_i[i] < 0) continue;
           if (best < 0 || cand_v[i] > cand_v[best] || (cand_v[i] == cand_v[best] && cand_i[i] < cand_i[best])) best = i;
         }
         if (best < 0) break;
-        const float lp = (cand_v[best] - mx) - ls;  // log_softmax value, fp32 like the reference
-        int np = pool_n;
-        pool_score[np] = base + (double)lp;  // python-float running sum (captioner.py:404-407)
-        pool_parent[np] = k;
-        pool_word[np] = cand_i[best];
-        pool_n = np + 1;
+        p.cand_lp[m * KMAX + r] = (cand_v[best] - mx) - ls;  // log_softmax value, fp32 like the reference
+        p.cand_word[m * KMAX + r] = cand_i[best];
         cand_i[best] = -1;
       }
+      p.cand_count[m] = r;
     }
-    __syncthreads();
+  }
+  // ---- ticket: the last CTA of this image merges
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int prev = atomicAdd(p.ticket + b, 1);
+    is_last = (prev == K - 1);
+    if (is_last) {
+      p.ticket[b] = 0;  // re-armed for the next step
+      __threadfence();
+    }
   }
   __syncthreads();
+  if (!is_last) return;
+
   if (threadIdx.x == 0) {
+    double pool_score[KMAX * KMAX + KMAX];
+    int pool_parent[KMAX * KMAX + KMAX], pool_word[KMAX * KMAX + KMAX];
+    long long lasts[KMAX];
+    int n = 0;
+    for (int kk = 0; kk < K; ++kk) {
+      const int mm = b * K + kk;
+      lasts[kk] = p.it[mm];
+      if (!p.alive_in[mm]) continue;
+      const double base = p.score_in[mm];
+      if (t > 0 && lasts[kk] == p.eos_id) {
+        pool_score[n] = base;
+        pool_parent[n] = kk;
+        pool_word[n] = -1;
+        ++n;
+      } else {
+        const int cnt = __ldcg(p.cand_count + mm);
+        for (int r = 0; r < cnt; ++r) {
+          // python-float running sum of fp32 log-probs (captioner.py:404-407)
+          pool_score[n] = base + (double)__ldcg(p.cand_lp + mm * KMAX + r);
+          pool_parent[n] = kk;
+          pool_word[n] = __ldcg(p.cand_word + mm * KMAX + r);
+          ++n;
+        }
+      }
+    }
     // stable top-K of the pool by score (python sorted(reverse=True) keeps pool order on ties)
-    const int n = pool_n;
     unsigned long long taken = 0ULL;
-    int m = 0;
-    for (; m < K && m < n; ++m) {
+    int j = 0;
+    for (; j < K && j < n; ++j) {
       int best = -1;
       for (int i = 0; i < n; ++i) {
         if ((taken >> i) & 1ULL) continue;
         if (best < 0 || pool_score[i] > pool_score[best]) best = i;
       }
       taken |= 1ULL << best;
-      const int k = pool_parent[best], w = pool_word[best];
-      sel_parent[m] = k;
-      sel_word[m] = w;
-      p.score_out[b * K + m] = pool_score[best];
-      p.alive_out[b * K + m] = 1;
-      p.len_out[b * K + m] = p.len_in[b * K + k] + (w >= 0 ? 1 : 0);
-      p.parent[b * K + m] = b * K + k;
-      p.it[b * K + m] = (w >= 0) ? (long long)w : last_sm[k];
+      const int kk = pool_parent[best], w = pool_word[best];
+      sel_parent[j] = kk;
+      sel_word[j] = w;
+      p.score_out[b * K + j] = pool_score[best];
+      p.alive_out[b * K + j] = 1;
+      p.len_out[b * K + j] = p.len_in[b * K + kk] + (w >= 0 ? 1 : 0);
+      p.parent[b * K + j] = b * K + kk;
+      p.it[b * K + j] = (w >= 0) ? (long long)w : lasts[kk];
     }
-    sel_n = m;
-    for (; m < K; ++m) {
-      p.score_out[b * K + m] = 0.0;
-      p.alive_out[b * K + m] = 0;
-      p.len_out[b * K + m] = 0;
-      p.parent[b * K + m] = b * K + m;
-      p.it[b * K + m] = p.sos_id;
+    sel_n = j;
+    for (; j < K; ++j) {
+      p.score_out[b * K + j] = 0.0;
+      p.alive_out[b * K + j] = 0;
+      p.len_out[b * K + j] = 0;
+      p.parent[b * K + j] = b * K + j;
+      p.it[b * K + j] = p.sos_id;
     }
   }
   __syncthreads();
@@ -301,9 +330,9 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
     const int j = i / T, tt = i - j * T;
     int v = 0;
     if (j < sel_n) {
-      const int k = sel_parent[j];
-      v = p.tok_in[(b * K + k) * T + tt];
-      if (sel_word[j] >= 0 && tt == p.len_in[b * K + k]) v = sel_word[j];
+      const int kk = sel_parent[j];
+      v = p.tok_in[(b * K + kk) * T + tt];
+      if (sel_word[j] >= 0 && tt == p.len_in[b * K + kk]) v = sel_word[j];
     }
     p.tok_out[(b * K + j) * T + tt] = v;
   }
@@ -351,8 +380,9 @@ int launch_greedy_select(const GreedyParams& p, cudaStream_t stream) {
 }
 int launch_beam_select(const BeamParams& p, cudaStream_t stream) {
   ISC_REQUIRE(p.K >= 1 && p.K <= KMAX, "beam size %d not in 1..%d", p.K, KMAX);
+  ISC_REQUIRE(p.cand_lp && p.cand_word && p.cand_count && p.ticket, "beam_select: scratch buffers missing");
   ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.V * 4.0, stream);
-  beam_select_kernel<<<p.B, NT, 0, stream>>>(p);
+  beam_select_kernel<<<p.B * p.K, NT, 0, stream>>>(p);
   ISC_LAUNCH_CHECK();
   return 0;
 }

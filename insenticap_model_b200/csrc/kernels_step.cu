@@ -72,6 +72,10 @@ struct FeatLoad<float> {
     float4 t = __ldg(reinterpret_cast<const float4*>(row + col(lane, i)));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  __device__ static __forceinline__ void load_shared(const float* row, int lane, int i, float* v) {
+    float4 t = *reinterpret_cast<const float4*>(row + col(lane, i));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
   static constexpr int kWidth = 4;
 };
 template <>
@@ -80,6 +84,13 @@ struct FeatLoad<__nv_bfloat16> {
   __device__ static __forceinline__ int col(int lane, int i) { return i * 256 + lane * 8; }
   __device__ static __forceinline__ void load(const __nv_bfloat16* row, int lane, int i, float* v) {
     uint4 t = __ldg(reinterpret_cast<const uint4*>(row + col(lane, i)));
+    unpack(t, v);
+  }
+  __device__ static __forceinline__ void load_shared(const __nv_bfloat16* row, int lane, int i, float* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(row + col(lane, i));
+    unpack(t, v);
+  }
+  __device__ static __forceinline__ void unpack(const uint4& t, float* v) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -93,46 +104,77 @@ struct FeatLoad<__nv_bfloat16> {
 
 // RT > 0: rows per image known at compile time (fully unrolled); RT == 0: runtime R <= 8.
 template <typename FeatT, int TANH_MODE, int RT>
-__device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
-                                           const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
-                                           float* __restrict__ score_smem /*[R][n_items]*/, int warp, int lane, int n_warps) {
+__device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kChunks][FeatLoad<FeatT>::kWidth],
+                                          const float (&al)[FeatLoad<FeatT>::kChunks][FeatLoad<FeatT>::kWidth], int l,
+                                          int n_items, int R, const float* __restrict__ q_smem,
+                                          float* __restrict__ score_smem, int lane) {
   using L = FeatLoad<FeatT>;
   constexpr int RU = RT > 0 ? RT : 8;
+#pragma unroll
+  for (int r = 0; r < RU; ++r) {
+    if (RT > 0 || r < R) {
+      const float* q = q_smem + r * H;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < L::kChunks; ++i) {
+        const int c0 = L::col(lane, i);
+#pragma unroll
+        for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
+          const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
+          const float x[4] = {pv[i][j4] + qv.x, pv[i][j4 + 1] + qv.y, pv[i][j4 + 2] + qv.z, pv[i][j4 + 3] + qv.w};
+          float t[4];
+          if (TANH_MODE == 1) {
+            tanh4_ex2(x, t);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = TANH_MODE == 2 ? tanh_fast(x[j]) : tanhf(x[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc = fmaf(al[i][j4 + j], t[j], acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) score_smem[r * n_items + l] = acc;
+    }
+  }
+}
+
+// One warp scores items l = warp, warp + n_warps, ...  The item's 512-wide row is staged gmem -> smem with
+// cp.async (no registers held across the long SFU-bound scoring of the previous row): a 2-slot ring per warp.
+// Every lane reads back exactly the 16-byte chunks it copied itself, so no cross-lane barrier is needed.
+template <typename FeatT, int TANH_MODE, int RT>
+__device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
+                                           const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
+                                           float* __restrict__ score_smem /*[R][n_items]*/, FeatT* __restrict__ ring /*[2][H]*/,
+                                           int warp, int lane, int n_warps) {
+  using L = FeatLoad<FeatT>;
   float al[L::kChunks][L::kWidth];  // this lane's slice of alpha stays in registers
 #pragma unroll
   for (int i = 0; i < L::kChunks; ++i)
 #pragma unroll
     for (int j = 0; j < L::kWidth; ++j) al[i][j] = alpha_smem[L::col(lane, i) + j];
-  for (int l = warp; l < n_items; l += n_warps) {
-    const FeatT* row = p_feat + (long long)l * H;
-    float pv[L::kChunks][L::kWidth];
+  auto prefetch = [&](int l, int slot) {
+    if (l < n_items) {
 #pragma unroll
-    for (int i = 0; i < L::kChunks; ++i) L::load(row, lane, i, pv[i]);
-#pragma unroll
-    for (int r = 0; r < RU; ++r) {
-      if (RT > 0 || r < R) {
-        const float* q = q_smem + r * H;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < L::kChunks; ++i) {
-          const int c0 = L::col(lane, i);
-#pragma unroll
-          for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
-            const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
-            const float qq[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x = pv[i][j4 + j] + qq[j];
-              float t = TANH_MODE == 2 ? tanh_fast(x) : (TANH_MODE == 1 ? tanh_ex2(x) : tanhf(x));
-              acc = fmaf(al[i][j4 + j], t, acc);
-            }
-          }
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) score_smem[r * n_items + l] = acc;
+      for (int i = 0; i < L::kChunks; ++i) {
+        const FeatT* src = p_feat + (long long)l * H + L::col(lane, i);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + slot * H + L::col(lane, i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(warp, 0);
+  int it = 0;
+  for (int l = warp; l < n_items; l += n_warps, ++it) {
+    prefetch(l + n_warps, (it + 1) & 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    float pv[L::kChunks][L::kWidth];
+#pragma unroll
+    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it & 1) * H, lane, i, pv[i]);
+    score_one<FeatT, TANH_MODE, RT>(pv, al, l, n_items, R, q_smem, score_smem, lane);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __device__ __forceinline__ void softmax_rows(float* score_smem, int n_items, int R, int warp, int lane, int n_warps,
@@ -181,6 +223,23 @@ __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int
   for (int r = 0; r < RU; ++r) acc[r] = make_float2(0.f, 0.f);
   int l = 0;
   if ((n_items & 3) == 0 && (reinterpret_cast<uintptr_t>(w_smem) & 15) == 0) {
+    for (; l + 8 <= n_items; l += 8) {  // 8 rows (8 x 8 B per thread) in flight
+      float2 a[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = load2<FeatT>(feat + (long long)(l + u) * H + c);
+#pragma unroll
+      for (int r = 0; r < RU; ++r)
+        if (RT > 0 || r < R) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float4 w = *reinterpret_cast<const float4*>(w_smem + r * n_items + l + 4 * hh);
+            acc[r].x = fmaf(w.x, a[4 * hh].x, acc[r].x); acc[r].y = fmaf(w.x, a[4 * hh].y, acc[r].y);
+            acc[r].x = fmaf(w.y, a[4 * hh + 1].x, acc[r].x); acc[r].y = fmaf(w.y, a[4 * hh + 1].y, acc[r].y);
+            acc[r].x = fmaf(w.z, a[4 * hh + 2].x, acc[r].x); acc[r].y = fmaf(w.z, a[4 * hh + 2].y, acc[r].y);
+            acc[r].x = fmaf(w.w, a[4 * hh + 3].x, acc[r].x); acc[r].y = fmaf(w.w, a[4 * hh + 3].y, acc[r].y);
+          }
+        }
+    }
     for (; l + 4 <= n_items; l += 4) {
       float2 a[4];
 #pragma unroll
@@ -224,7 +283,7 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   float* alpha_s = alpha_c + H;    // [H]
   float* sc_c = alpha_s + H;       // [R][L]
   float* sc_s = sc_c + R * Lp;     // [R][S]
-  (void)Sp;
+  float* ring_base = sc_s + R * Sp;  // [8 warps][2 slots][H] fp32 worth of staging (bf16 rows use half)
   const int img = blockIdx.x;
   const long long row0 = (long long)img * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,8 +300,12 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   __syncthreads();
   const FeatT* att = reinterpret_cast<const FeatT*>(p.att);
   const FeatT* p_att = reinterpret_cast<const FeatT*>(p.p_att);
-  if (att) score_rows<FeatT, TANH_MODE, RT>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c, warp, lane, 8);
-  if (p.sw) score_rows<float, TANH_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, warp, lane, 8);
+  if (att)
+    score_rows<FeatT, TANH_MODE, RT>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c,
+                                     reinterpret_cast<FeatT*>(ring_base + warp * 2 * H), warp, lane, 8);
+  if (p.sw)
+    score_rows<float, TANH_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring_base + warp * 2 * H,
+                                     warp, lane, 8);
   __syncthreads();
   if (att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
   if (p.sw) softmax_rows(sc_s, S, R, warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
@@ -270,7 +333,7 @@ int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode,
   ISC_REQUIRE(p.R >= 1 && p.R <= 8, "attention: rows per image %d not in 1..8", p.R);
   ISC_REQUIRE((bf16_feats && tanh_mode == 2) || (!bf16_feats && tanh_mode != 2), "attention: feature dtype / tanh mode mismatch");
   const int Lp = (p.L + 3) & ~3, Sp = (p.S + 3) & ~3;
-  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp);
+  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp + 8 * 2 * H);
   // algorithmic HBM bytes: both feature tensors of every image once per launch (shared by its R rows),
   // sentiment-word features, the R query rows in and the R context rows out
   const double feat_b = bf16_feats ? 2.0 : 4.0;
