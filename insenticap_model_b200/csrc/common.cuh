@@ -115,12 +115,14 @@ __device__ __forceinline__ float tanh_ex2(float x) {
   return copysignf((1.0f - e) * r, x);
 }
 // Four tanh values sharing ONE reciprocal: 1/d_i = (prod_j d_j)^-1 * prod_{j != i} d_j with d_i = 1 + e_i in
-// [1,2]. 1.25 MUFU ops per value instead of 2 — the attention score loop is SFU-bound otherwise.
-__device__ __forceinline__ void tanh4_ex2(const float x[4], float t[4]) {
+// [1,2]. 1.25 MUFU ops per value instead of 2 — the attention score loop is SFU/issue-bound otherwise.
+// Inputs are PRE-SCALED: xs = 2*log2(e)*x, so e = 2^-|xs| = exp(-2|x|) needs no multiply.
+constexpr float kTanhScale = 2.8853900817779268f;  // 2 * log2(e)
+__device__ __forceinline__ void tanh4_ex2_scaled(const float xs[4], float t[4]) {
   float e[4], d[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(-2.8853900817779268f * fabsf(x[i])));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(-fabsf(xs[i])));
     d[i] = 1.0f + e[i];
   }
   const float p01 = d[0] * d[1], p23 = d[2] * d[3];
@@ -129,7 +131,7 @@ __device__ __forceinline__ void tanh4_ex2(const float x[4], float t[4]) {
   const float r01 = r * p23, r23 = r * p01;
   const float inv[4] = {r01 * d[1], r01 * d[0], r23 * d[3], r23 * d[2]};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) t[i] = copysignf((1.0f - e[i]) * inv[i], x[i]);
+  for (int i = 0; i < 4; ++i) t[i] = copysignf(fmaf(-e[i], inv[i], inv[i]), xs[i]);  // (1 - e) / (1 + e)
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

@@ -121,10 +121,11 @@ __device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kCh
 #pragma unroll
         for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
           const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
+          // TANH_MODE 1: pv and q both carry the 2*log2(e) factor already
           const float x[4] = {pv[i][j4] + qv.x, pv[i][j4 + 1] + qv.y, pv[i][j4 + 2] + qv.z, pv[i][j4 + 3] + qv.w};
           float t[4];
           if (TANH_MODE == 1) {
-            tanh4_ex2(x, t);
+            tanh4_ex2_scaled(x, t);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) t[j] = TANH_MODE == 2 ? tanh_fast(x[j]) : tanhf(x[j]);
@@ -171,7 +172,13 @@ __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     float pv[L::kChunks][L::kWidth];
 #pragma unroll
-    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it & 1) * H, lane, i, pv[i]);
+    for (int i = 0; i < L::kChunks; ++i) {
+      L::load_shared(ring + (it & 1) * H, lane, i, pv[i]);
+      if (TANH_MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < L::kWidth; ++j) pv[i][j] *= kTanhScale;  // once per item, shared by its R rows
+      }
+    }
     score_one<FeatT, TANH_MODE, RT>(pv, al, l, n_items, R, q_smem, score_smem, lane);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -290,8 +297,9 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   for (int i = threadIdx.x; i < R * H; i += 256) {
     int r = i / H, c = i - r * H;
     const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
-    q_c[i] = hp[c];
-    q_s[i] = hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f);
+    const float qs = TANH_MODE == 1 ? kTanhScale : 1.0f;  // queries pre-scaled for the ex2-based tanh
+    q_c[i] = qs * hp[c];
+    q_s[i] = qs * (hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f));
   }
   for (int i = threadIdx.x; i < H; i += 256) {
     alpha_c[i] = p.alpha_c[i];
