@@ -85,9 +85,9 @@ typedef struct isc_weights {
 typedef struct isc_feats {
   float* fc;        /* [B,H]   ReLU(fc_embed(fc_feats)); in seq2seq mode = cpt_feats */
   void*  att;       /* [B,L,H] ReLU(att_embed(att_feats)); fp32, or bf16 when ISC_PREC_BF16 */
-  void*  p_att;     /* [B,L,H] ReLU(att2att(att)); same dtype as att */
+  void*  p_att;     /* [B,L,H] ReLU(att2att(att)); same dtype as att. ISC_PREC_BF16X3: exp(-2 * that) */
   float* sw;        /* [B,S,H] ReLU(word_embed([PAD|senti_words])) */
-  float* p_sw;      /* [B,S,H] ReLU(senti2att(sw)) */
+  float* p_sw;      /* [B,S,H] ReLU(senti2att(sw)). ISC_PREC_BF16X3: exp(-2 * that) */
   float* sl;        /* [B,H]   ReLU(senti_label_embed(labels)) */
   float* pre_gates; /* [B,4H]  W_ih[:,H:2H]·fc + W_ih[:,2H:3H]·sl + b_ih + b_hh (hoisted) */
   float* pre_word;  /* [B,H]   label2word(sl) (hoisted out of SentiAttention.forward) */
@@ -121,6 +121,14 @@ int isc_prologue(const isc_dims_t* dims, const void* packed, int precision,
                  const int64_t* senti_words, const int64_t* senti_labels,
                  int B, int seq2seq, const isc_feats_t* out,
                  void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* Convert caller-supplied, already-embedded fp32 features (the att_feats / p_att_feats /
+ * p_senti_word_feats arguments of Captioner.forward_step, captioner.py:168) into the
+ * representation isc_feats_t holds for `precision`: bf16 for ISC_PREC_BF16 (att, p_att), and for
+ * ISC_PREC_BF16X3 the PROJECTED tensors (p_att, p_sw; projected != 0) become exp(-2 x), which is
+ * what the attention kernel's tanh reads there; everything else is a copy. n elements. */
+int isc_convert_features(int precision, int projected, const float* src, void* dst, int64_t n,
+                         isc_stream_t stream);
 
 /* Recompute only the hoisted terms (pre_gates, pre_word) from feats->fc / feats->sl:
  * used when the caller supplies already-embedded features (Captioner.forward_step API). */

@@ -73,6 +73,7 @@ SIGNATURES = {
     "isc_prologue_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int]),
     "isc_prologue": (C.c_int, [_PD, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _PF,
                                _vp, _sz, _vp]),
+    "isc_convert_features": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _i64, _vp]),
     "isc_hoist": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _PF, _vp, _sz, _vp]),
     "isc_decode_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int]),
     "isc_decode_step": (C.c_int, [_PD, _vp, C.c_int, _PF, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64,

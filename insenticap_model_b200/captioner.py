@@ -177,6 +177,16 @@ class Captioner(nn.Module):
             setattr(f, name, t.data_ptr() if t is not None else None)
         return f
 
+    def _convert_features(self, x, projected, dtype):
+        """Caller-embedded fp32 features -> the representation the kernels read (isc_convert_features)."""
+        dev = self._device()
+        x = x.float().contiguous()
+        out = torch.empty(x.shape, dtype=dtype, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().isc_convert_features(self._prec, 1 if projected else 0, _lib.ptr(x), _lib.ptr(out),
+                                                        x.numel(), _lib.stream_ptr(dev)), "isc_convert_features")
+        return out
+
     def _check_inference(self, what):
         if self.training:
             raise NotImplementedError(
@@ -251,12 +261,12 @@ class Captioner(nn.Module):
         n_regions, S = self.n_regions, self.num_senti_words + 1
         if att_feats is not None:
             n_regions = att_feats.shape[1]
-            t["att"] = att_feats.to(self._feat_dtype()).contiguous()
-            t["p_att"] = p_att_feats.to(self._feat_dtype()).contiguous()
+            t["att"] = self._convert_features(att_feats, False, self._feat_dtype())
+            t["p_att"] = self._convert_features(p_att_feats, True, self._feat_dtype())
         if senti_word_feats is not None:
             S = senti_word_feats.shape[1]
             t["sw"] = senti_word_feats.float().contiguous()
-            t["p_sw"] = p_senti_word_feats.float().contiguous()
+            t["p_sw"] = self._convert_features(p_senti_word_feats, True, torch.float32)
         if senti_labels is not None:
             t["sl"] = senti_labels.float().contiguous()
             t["pre_word"] = torch.empty(M, 512, **f32)

@@ -93,6 +93,19 @@ int check_precision(int p) {
   return 0;
 }
 
+// Representation of the PROJECTED attention features (feats.p_att, feats.p_sw): ReLU(.) as in the reference,
+// except in ISC_PREC_BF16X3 where the attention kernel's e-product tanh reads exp(-2 * ReLU(.)).
+int proj_act(int precision) { return precision == ISC_PREC_BF16X3 ? ACT_EXPNEG2_RELU : ACT_RELU; }
+
+__global__ void proj_convert_kernel(const float* __restrict__ src, float* __restrict__ dst_f32,
+                                    __nv_bfloat16* __restrict__ dst_bf16, long long n, int expneg2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = src[i];
+    if (dst_bf16) dst_bf16[i] = __float2bfloat16_rn(v);
+    else dst_f32[i] = expneg2 ? exp_neg2(fmaxf(v, -1.0f)) : v;
+  }
+}
+
 // ------------------------------------------------------------------ bump allocator
 struct Bump {
   uint8_t* base;
@@ -709,7 +722,7 @@ int isc_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
       ISC_TRY(gemm(precision, operand(raw, D, praw, D), pk.Watt.op(), dst, (int)rows, H, D, ep, c.s));
       Epilogue ep2;
       ep2.bias = pk.ba2a;
-      ep2.act = ACT_RELU;
+      ep2.act = proj_act(precision);
       Dest d2;
       if (precision == ISC_PREC_BF16) {
         d2.hi = reinterpret_cast<bf16*>(out->p_att) + (long long)b0 * L * H;
@@ -728,7 +741,7 @@ int isc_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
                               rowdest(out->sw, H, ptmp, H), c.s));
     Epilogue ep;
     ep.bias = pk.bs2a;
-    ep.act = ACT_RELU;
+    ep.act = proj_act(precision);
     Dest dst;
     dst.f32 = out->p_sw;
     dst.ld = H;
@@ -962,6 +975,23 @@ int isc_teacher_forced(const isc_dims_t* dims, const void* packed, int precision
     ISC_TRY(run_step(c, w, B, 1, io));
     ISC_TRY(launch_log_softmax(io.logits, io.ld_logits, B, (int)V, c.s));
   }
+  return 0;
+}
+
+int isc_convert_features(int precision, int projected, const float* src, void* dst, int64_t n, isc_stream_t stream) {
+  ISC_TRY(check_device());
+  ISC_TRY(check_precision(precision));
+  ISC_REQUIRE(src && dst && n >= 0, "bad convert_features arguments");
+  if (n == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  const bool bf = precision == ISC_PREC_BF16;
+  ProfScope ps(ISC_K_POINTWISE, (double)n * (bf ? 6.0 : 8.0), s);
+  proj_convert_kernel<<<blocks, 256, 0, s>>>(src, bf ? nullptr : static_cast<float*>(dst),
+                                             bf ? static_cast<__nv_bfloat16*>(dst) : nullptr, n,
+                                             projected && precision == ISC_PREC_BF16X3);
+  ISC_LAUNCH_CHECK();
   return 0;
 }
 

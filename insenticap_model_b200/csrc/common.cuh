@@ -45,7 +45,9 @@ void set_error(const char* fmt, ...);
     }                                   \
   } while (0)
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+// ACT_EXPNEG2_RELU: exp(-2 * relu(v)) — the representation of the projected attention features that the
+// e-product tanh of the bf16x3 attention kernel reads (tanh2_eprod below)
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_EXPNEG2_RELU = 3 };
 
 // Per-kernel-class accounting (isc_profile_* in include/isc.h). Every launcher opens a ProfScope:
 // it counts the launch and, when profiling is enabled, brackets it with CUDA events on the launch
@@ -114,24 +116,23 @@ __device__ __forceinline__ float tanh_ex2(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return copysignf((1.0f - e) * r, x);
 }
-// Four tanh values sharing ONE reciprocal: 1/d_i = (prod_j d_j)^-1 * prod_{j != i} d_j with d_i = 1 + e_i in
-// [1,2]. 1.25 MUFU ops per value instead of 2 — the attention score loop is SFU/issue-bound otherwise.
-// Inputs are PRE-SCALED: xs = 2*log2(e)*x, so e = 2^-|xs| = exp(-2|x|) needs no multiply.
-constexpr float kTanhScale = 2.8853900817779268f;  // 2 * log2(e)
-__device__ __forceinline__ void tanh4_ex2_scaled(const float xs[4], float t[4]) {
-  float e[4], d[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(-fabsf(xs[i])));
-    d[i] = 1.0f + e[i];
-  }
-  const float p01 = d[0] * d[1], p23 = d[2] * d[3];
+// tanh(p + q) from PRE-EXPONENTIATED operands: with ea = exp(-2p), eb = exp(-2q), e = ea * eb,
+//   tanh(p + q) = (1 - e) / (1 + e).
+// No ex2 in the inner loop, and two values share ONE reciprocal (1/d0 = d1 / (d0 d1)), so a value costs
+// 0.5 MUFU + 6 FMA-pipe instructions instead of 2 MUFU + ~9. Absolute error ~2e-7 (relative error of e is
+// a few ulp and |d tanh / d ln e| <= 1/2). Domain: ea in [0, ~7] (p >= -1; p is a ReLU output) and
+// eb <= kExpClamp (q >= -20), so that d0 * d1 cannot overflow; an underflowing ea only occurs where
+// tanh has saturated to 1 anyway.
+constexpr float kExpClamp = 2.3e17f;  // ~exp(40)
+__device__ __forceinline__ float exp_neg2(float x) { return fminf(expf(-2.0f * x), kExpClamp); }
+__device__ __forceinline__ void tanh2_eprod(float ea0, float ea1, float eb0, float eb1, float& t0, float& t1) {
+  const float e0 = ea0 * eb0, e1 = ea1 * eb1;
+  const float d0 = 1.0f + e0, d1 = 1.0f + e1;
   float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
-  const float r01 = r * p23, r23 = r * p01;
-  const float inv[4] = {r01 * d[1], r01 * d[0], r23 * d[3], r23 * d[2]};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) t[i] = copysignf(fmaf(-e[i], inv[i], inv[i]), xs[i]);  // (1 - e) / (1 + e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  const float i0 = r * d1, i1 = r * d0;
+  t0 = fmaf(-e0, i0, i0);
+  t1 = fmaf(-e1, i1, i1);
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -143,6 +144,7 @@ __device__ __forceinline__ float sigmoid_accurate(float x) { return 1.0f / (1.0f
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   if (act == ACT_TANH) return tanhf(v);
+  if (act == ACT_EXPNEG2_RELU) return exp_neg2(fmaxf(v, 0.0f));
   return v;
 }
 

@@ -165,6 +165,7 @@ template <int ACT>
 __device__ __forceinline__ float act_ct(float v) {
   if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == ACT_TANH) return tanhf(v);
+  if (ACT == ACT_EXPNEG2_RELU) return exp_neg2(fmaxf(v, 0.0f));
   return v;
 }
 
@@ -489,6 +490,8 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
   if (e.act == ACT_RELU) return launch_kernel<PASSES, ACT_RELU>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
   if (e.act == ACT_TANH) return launch_kernel<PASSES, ACT_TANH>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
+  if (e.act == ACT_EXPNEG2_RELU)
+    return launch_kernel<PASSES, ACT_EXPNEG2_RELU>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
   return launch_kernel<PASSES, ACT_NONE>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
 }
 

@@ -121,12 +121,13 @@ __device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kCh
 #pragma unroll
         for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
           const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
-          // TANH_MODE 1: pv and q both carry the 2*log2(e) factor already
-          const float x[4] = {pv[i][j4] + qv.x, pv[i][j4 + 1] + qv.y, pv[i][j4 + 2] + qv.z, pv[i][j4 + 3] + qv.w};
           float t[4];
           if (TANH_MODE == 1) {
-            tanh4_ex2_scaled(x, t);
+            // pv = exp(-2 p), q = exp(-2 q): tanh(p + q) = (1 - pv q) / (1 + pv q), one reciprocal per pair
+            tanh2_eprod(pv[i][j4], pv[i][j4 + 1], qv.x, qv.y, t[0], t[1]);
+            tanh2_eprod(pv[i][j4 + 2], pv[i][j4 + 3], qv.z, qv.w, t[2], t[3]);
           } else {
+            const float x[4] = {pv[i][j4] + qv.x, pv[i][j4 + 1] + qv.y, pv[i][j4 + 2] + qv.z, pv[i][j4 + 3] + qv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) t[j] = TANH_MODE == 2 ? tanh_fast(x[j]) : tanhf(x[j]);
           }
@@ -172,13 +173,7 @@ __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     float pv[L::kChunks][L::kWidth];
 #pragma unroll
-    for (int i = 0; i < L::kChunks; ++i) {
-      L::load_shared(ring + (it & 1) * H, lane, i, pv[i]);
-      if (TANH_MODE == 1) {
-#pragma unroll
-        for (int j = 0; j < L::kWidth; ++j) pv[i][j] *= kTanhScale;  // once per item, shared by its R rows
-      }
-    }
+    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it & 1) * H, lane, i, pv[i]);
     score_one<FeatT, TANH_MODE, RT>(pv, al, l, n_items, R, q_smem, score_smem, lane);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -277,7 +272,8 @@ __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int
     if (RT > 0 || r < R) dst.store2(row0 + r, dst_col + c, acc[r]);
 }
 
-// TANH_MODE: 0 = libdevice tanhf (ISC_PREC_FP32), 1 = ex2/rcp based, |err| ~ 2e-7 (ISC_PREC_BF16X3),
+// TANH_MODE: 0 = libdevice tanhf (ISC_PREC_FP32); 1 = e-product tanh, |err| ~ 2e-7 (ISC_PREC_BF16X3): p_att and
+// p_sw hold exp(-2 * projected feature) (written by the prologue GEMM epilogue, ACT_EXPNEG2_RELU);
 // 2 = tanh.approx.f32, one MUFU (ISC_PREC_BF16)
 template <typename FeatT, int TANH_MODE, int RT>
 __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
@@ -297,9 +293,11 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   for (int i = threadIdx.x; i < R * H; i += 256) {
     int r = i / H, c = i - r * H;
     const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
-    const float qs = TANH_MODE == 1 ? kTanhScale : 1.0f;  // queries pre-scaled for the ex2-based tanh
-    q_c[i] = qs * hp[c];
-    q_s[i] = qs * (hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f));
+    const float qc = hp[c];
+    const float qw = hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f);
+    // TANH_MODE 1: queries (like the projected features) are kept as exp(-2 x) for the e-product tanh
+    q_c[i] = TANH_MODE == 1 ? exp_neg2(qc) : qc;
+    q_s[i] = TANH_MODE == 1 ? exp_neg2(qw) : qw;
   }
   for (int i = threadIdx.x; i < H; i += 256) {
     alpha_c[i] = p.alpha_c[i];

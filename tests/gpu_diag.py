@@ -79,7 +79,7 @@ def _decode(precision):
     h0 = torch.randn(2, B, 512, generator=g) * 0.3
     c0 = torch.randn(2, B, 512, generator=g) * 0.3
     it = torch.randint(0, V, (B,), generator=g)
-    lp, (h1, c1) = m.forward_step(it.cuda(), (h0.cuda(), c0.cuda()), t["fc"], t["att"], t["p_att"], t["sw"], t["p_sw"], t["sl"])
+    lp, (h1, c1) = m.forward_step(it.cuda(), (h0.cuda(), c0.cuda()), t["fc"], t["att"], f["p_att"].cuda(), t["sw"], f["p_sw"].cuda(), t["sl"])
     torch.cuda.synchronize()
     with torch.no_grad():
         lp_o, (h_o, c_o), (cw, sw, gw) = O.step(p, it, (h0, c0), f, want_weights=True)
