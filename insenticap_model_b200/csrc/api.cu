@@ -231,6 +231,8 @@ struct DecodeWs {
   int* alive[2];
   float* fcsl;
   Planes pfcsl;
+  float* rec;  // LogitsSelect records of the fused logits epilogue [M][np][SEL_REC] (tensor-core precisions)
+  int np;
   float* cand_lp;
   int* cand_word;
   int* cand_count;
@@ -279,6 +281,8 @@ DecodeWs carve_decode(const isc_dims_t& d, int precision, int M, void* base) {
   }
   w.fcsl = b.take<float>(m * 2 * H);
   planes(w.pfcsl, m * 2 * H);
+  w.np = logits_slices(d.vocab);
+  w.rec = tc ? b.take<float>(m * w.np * SEL_REC) : nullptr;
   w.cand_lp = b.take<float>(m * 8);
   w.cand_word = b.take<int>(m * 8);
   w.cand_count = b.take<int>(m);
@@ -355,6 +359,7 @@ struct StepIO {
   long long ld_senti_w = 0;
   float* gate_w = nullptr;
   long long ld_gate_w = 0;
+  LogitsSelect sel;  // sel.rec != null: the classifier GEMM emits selection records instead of logits
 };
 
 // One decode step over M rows (captioner.py:168-186), raw classifier logits out.
@@ -459,7 +464,11 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     dst.f32 = io.logits;
     dst.ld = io.ld_logits;
     Operand a = operand(io.h_out + m * H, H, w.phL, H);
-    ISC_TRY(gemm(c.precision, a, pk.W5.op(), dst, M, c.d.vocab, H, ep, c.s));
+    if (io.sel.rec) {
+      ISC_TRY(gemm_tc_logits(a, pk.W5.op(), M, c.d.vocab, H, c.precision == ISC_PREC_BF16X3 ? 3 : 1, pk.b5, io.sel, c.s));
+    } else {
+      ISC_TRY(gemm(c.precision, a, pk.W5.op(), dst, M, c.d.vocab, H, ep, c.s));
+    }
   }
   return 0;
 }
@@ -495,7 +504,7 @@ ProWs carve_prologue(const isc_dims_t& d, int precision, int B, void* base) {
   ProWs w;
   memset(&w, 0, sizeof(w));
   const bool tc = precision != ISC_PREC_FP32, x3 = precision == ISC_PREC_BF16X3;
-  w.chunk = B < 64 ? B : 64;
+  w.chunk = B < 96 ? B : 96;  // 96 x 196 rows = 147 row tiles x 2 wide column tiles = 2 waves on 148 SMs
   const size_t rows = (size_t)w.chunk * d.n_regions;
   if (tc) {
     w.raw_hi = b.take<bf16>(rows * d.feat_dim);
@@ -836,8 +845,13 @@ int isc_decode_greedy(const isc_dims_t* dims, const void* packed, int precision,
   ISC_CUDA(cudaMemsetAsync(w.alive_count, 0, T_MAX * sizeof(int), c.s));
   ISC_TRY(launch_greedy_init(w.it, w.unfinished, B, dims->sos_id, c.s));
   const int L = dims->n_regions, S = dims->n_senti, V = dims->vocab;
+  const bool fused = precision != ISC_PREC_FP32 && sample_mode == 0;  // argmax straight from the GEMM epilogue
   for (int t = 0; t < T; ++t) {
     StepIO io;
+    if (fused) {
+      io.sel.rec = w.rec;
+      io.sel.np = w.np;
+    }
     io.it = w.it;
     io.parent = nullptr;
     io.h_in = w.state_h[t & 1];
@@ -860,8 +874,10 @@ int isc_decode_greedy(const isc_dims_t* dims, const void* packed, int precision,
     }
     ISC_TRY(run_step(c, w, B, 1, io));
     GreedyParams g;
-    g.logits = w.logits;
+    g.logits = fused ? nullptr : w.logits;
     g.ld = w.ld_logits;
+    g.rec = io.sel.rec;
+    g.np = io.sel.np;
     g.B = B;
     g.V = V;
     g.T = T;
@@ -901,8 +917,19 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
   ISC_CUDA(cudaMemsetAsync(w.tok[0], 0, (size_t)M * T * sizeof(int), c.s));
   ISC_CUDA(cudaMemsetAsync(w.ticket, 0, (size_t)B * sizeof(int), c.s));
   ISC_TRY(launch_beam_init(w.it, w.alive[0], w.len[0], w.score[0], w.parent, B, K, dims->sos_id, c.s));
+  const bool fused = precision != ISC_PREC_FP32 && K <= SEL_K;  // masks + top-K inside the logits GEMM epilogue
   for (int t = 0; t < T; ++t) {
     StepIO io;
+    if (fused) {
+      io.sel.rec = w.rec;
+      io.sel.np = w.np;
+      io.sel.last = w.it;
+      io.sel.constraint = decoding_constraint ? 1 : 0;
+      io.sel.mask_special = dims->pad_id != dims->eos_id;
+      io.sel.pad_id = dims->pad_id;
+      io.sel.sos_id = dims->sos_id;
+      io.sel.unk_id = dims->unk_id;
+    }
     io.it = w.it;
     io.parent = t > 0 ? w.parent : nullptr;
     io.h_in = w.state_h[t & 1];
@@ -913,8 +940,10 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
     io.ld_logits = w.ld_logits;
     ISC_TRY(run_step(c, w, M, K, io));
     BeamParams bp;
-    bp.logits = w.logits;
+    bp.logits = fused ? nullptr : w.logits;
     bp.ld = w.ld_logits;
+    bp.rec = io.sel.rec;
+    bp.np = io.sel.np;
     bp.B = B;
     bp.K = K;
     bp.V = dims->vocab;

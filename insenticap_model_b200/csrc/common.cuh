@@ -87,11 +87,46 @@ struct Epilogue {
   int act = ACT_NONE;
 };
 
+// Fused vocabulary-logit epilogue of the tensor-core GEMM: the [M,V] logits are never written. Every epilogue
+// thread owns one row and one 128-column slice of a 128x256 tile and emits one record
+//   {slice max, sum exp(x - max), -, -, v[SEL_K], idx[SEL_K]}     (SEL_REC floats)
+// with the SEL_K largest UNMASKED logits of the slice (value desc, column asc). A small merge kernel turns the
+// np = 2 * ceil(V / 256) records of a row into its log-softmax normaliser and its top-K (kernels_select.cu).
+// Masks follow Captioner.sample (captioner.py:394-399): PAD/SOS/UNK when pad != eos, the previous word when
+// decoding_constraint is set.
+constexpr int SEL_K = 4;
+constexpr int SEL_REC = 4 + 2 * SEL_K;
+struct LogitsSelect {
+  float* rec = nullptr;             // [M][np][SEL_REC]
+  int np = 0;
+  const long long* last = nullptr;  // [M] previous word per row, or null
+  int constraint = 0, mask_special = 0, pad_id = 0, sos_id = 0, unk_id = 0;
+};
+
+// sorted insertion into a (value desc) list; equal values keep their arrival order
+template <int KS>
+__device__ __forceinline__ void topk_insert(float (&v)[KS], int (&idx)[KS], float x, int n) {
+  bool c[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) c[k] = x > v[k];
+#pragma unroll
+  for (int k = KS - 1; k > 0; --k) {
+    v[k] = c[k] ? (c[k - 1] ? v[k - 1] : x) : v[k];
+    idx[k] = c[k] ? (c[k - 1] ? idx[k - 1] : n) : idx[k];
+  }
+  v[0] = c[0] ? x : v[0];
+  idx[0] = c[0] ? n : idx[0];
+}
+
 // C = act(A[M,K] · W[N,K]^T + bias + rowadd + addmat)
 int gemm_simt(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K,
               const Epilogue& ep, cudaStream_t stream);
 int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, int passes,
             const Epilogue& ep, cudaStream_t stream);
+// tensor-core GEMM whose epilogue emits LogitsSelect records instead of C (bias added; N = vocabulary)
+int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
+                   const LogitsSelect& sel, cudaStream_t stream);
+inline int logits_slices(int V) { return 2 * ((V + 255) / 256); }
 inline int gemm(int precision, const Operand& A, const Operand& W, const Dest& C, int M, int N,
                 int K, const Epilogue& ep, cudaStream_t stream) {
   if (precision == ISC_PREC_FP32) return gemm_simt(A, W, C, M, N, K, ep, stream);

@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstring>
 #include <mutex>
 
 #include "common.cuh"
@@ -28,21 +29,30 @@
 namespace isc {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int TILE_BYTES = BM * BK * 2;  // 16 KiB, one operand plane tile
+constexpr int BM = 128;
 constexpr int EPI_WARPS = 8;                // two per TMEM lane quarter, each owns half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2;               // TMEM accumulator double buffer
-constexpr int TMEM_COLS = ACC_STAGES * BN;  // 256 columns (power of two)
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one XOR-swizzled 32x32 fp32 staging tile per epilogue warp
 
-template <int PASSES>
+// BN = 128 for the step GEMMs (M = 3072 rows: more, smaller tiles fill 148 SMs better), BN = 256 where there are many
+// tiles (vocabulary logits, prologue): 25 % less L2 -> smem traffic per flop, which is what bounds this kernel.
+template <int PASSES, int BN>
 struct Cfg {
-  static constexpr int kTilesPerStage = PASSES == 3 ? 4 : 2;  // A_hi,(A_lo),B_hi,(B_lo)
-  static constexpr int kStageBytes = kTilesPerStage * TILE_BYTES;
-  static constexpr int kStages = PASSES == 3 ? 3 : 6;
+  static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
+  // K extent of one pipeline stage. 64 bf16 = one 128-byte swizzle row; the wide split-bf16 tile uses 32 (64-byte
+  // swizzle) so that four 48 KiB stages fit instead of two 96 KiB ones — two stages cannot keep enough bytes in
+  // flight to cover the L2 latency.
+  static constexpr int kBK = (PASSES == 3 && BN == 256) ? 32 : 64;
+  static constexpr int kATileBytes = BM * kBK * 2;
+  static constexpr int kBTileBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kPlanes * (kATileBytes + kBTileBytes);  // A_hi,(A_lo),B_hi,(B_lo)
+  static constexpr int kStages = 192 * 1024 / kStageBytes;  // x3: 3 / 4 stages, bf16: 6 / 4
+  static constexpr int kTmemCols = ACC_STAGES * BN;  // 256 / 512 columns (power of two)
   static constexpr int kSmemBytes = kStages * kStageBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+enum { EPI_STD = 0, EPI_LOGITS = 1 };
 
 struct EpiParams {
   const float* bias;
@@ -58,6 +68,8 @@ struct EpiParams {
   __nv_bfloat16* lo;
   long long ldp;
   int M, N, K;
+  // EPI_LOGITS: per (row, 128-column slice) online-softmax partials + top candidates instead of the logits
+  LogitsSelect sel;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -106,13 +118,15 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 // UMMA shared-memory descriptor: K-major tile, 128-byte swizzle, rows of 128 B, 8-row groups
 // 1024 B apart (cute::UMMA::SmemDescriptor: start [0,14), LBO [16,30), SBO [32,46),
 // version [46,48) = 1, layout_type [61,64) = 2 for SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// ROW_BYTES = 128: SWIZZLE_128B (layout type 2), 64: SWIZZLE_64B (layout type 4); SBO = 8 rows.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;            // LBO: unused for swizzled K-major
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
-  d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  d |= static_cast<uint64_t>(1) << 16;                     // LBO: unused for swizzled K-major
+  d |= static_cast<uint64_t>((8 * ROW_BYTES) >> 4) << 32;  // SBO
+  d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(ROW_BYTES == 128 ? 2 : 4) << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 x bf16, both
@@ -169,12 +183,12 @@ __device__ __forceinline__ float act_ct(float v) {
   return v;
 }
 
-template <int PASSES, int ACT>
+template <int PASSES, int BN, int ACT, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const EpiParams ep) {
-  using C = Cfg<PASSES>;
+  using C = Cfg<PASSES, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_smem = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
@@ -187,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int BK = C::kBK;
   const int num_kb = (ep.K + BK - 1) / BK;
   const int tiles_n = (ep.N + BN - 1) / BN;
   const int tiles_m = (ep.M + BM - 1) / BM;
@@ -211,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
+                 "r"(C::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -231,17 +246,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
           uint8_t* st = smem + s * C::kStageBytes;
+          uint8_t* stb = st + C::kPlanes * C::kATileBytes;
           mbar_expect_tx(&full_bar[s], C::kStageBytes);
           const int k0 = kb * BK;
-          if (PASSES == 3) {
-            tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
-            tma_load_2d(st + 1 * TILE_BYTES, &map_a_lo, &full_bar[s], k0, m0);
-            tma_load_2d(st + 2 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
-            tma_load_2d(st + 3 * TILE_BYTES, &map_b_lo, &full_bar[s], k0, n0);
-          } else {
-            tma_load_2d(st + 0 * TILE_BYTES, &map_a_hi, &full_bar[s], k0, m0);
-            tma_load_2d(st + 1 * TILE_BYTES, &map_b_hi, &full_bar[s], k0, n0);
-          }
+          tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
+          if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
+          tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
+          if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
         }
       }
     }
@@ -262,8 +273,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint32_t st = smem_u32(smem + s * C::kStageBytes);
-          const uint32_t a_hi = st, a_lo = st + TILE_BYTES;
-          const uint32_t b_hi = st + (PASSES == 3 ? 2 : 1) * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
+          const uint32_t a_hi = st, a_lo = st + C::kATileBytes;
+          const uint32_t b_hi = st + C::kPlanes * C::kATileBytes, b_lo = b_hi + C::kBTileBytes;
 #pragma unroll
           for (int p = 0; p < PASSES; ++p) {
             const uint32_t a = (p == 1) ? a_lo : a_hi;  // hi·hi, lo·hi, hi·lo
@@ -271,7 +282,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // +32 B per 16-element K step inside the 128 B swizzle atom
-              umma_bf16(tmem_d, umma_desc_sw128(a + k * 32), umma_desc_sw128(b + k * 32), idesc, accumulate);
+              umma_bf16(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc, accumulate);
               accumulate = 1;
             }
           }
@@ -280,11 +291,91 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         umma_commit(&acc_full[as]);  // accumulator of this tile complete
       }
     }
+  } else if (EPI == EPI_LOGITS) {
+    // ===================== epilogue: softmax partials + top candidates per (row, 128-column slice) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int half = ew >> 2;      // which half of the tile's columns this warp scans
+    constexpr int SLICE = BN / 2;
+    float* bias_s = epi_smem + ew * SLICE;  // this warp's bias slice
+    const LogitsSelect& sel = ep.sel;
+    constexpr float kLog2e = 1.4426950408889634f;
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const int tn = tile % tiles_n;
+      const int m0 = (tile / tiles_n) * BM, n_base = tn * BN + half * SLICE;
+      const int as = j & 1;
+      const int row = m0 + quarter * 32 + lane;
+      for (int i = lane; i < SLICE; i += 32) bias_s[i] = (ep.bias && n_base + i < ep.N) ? __ldg(ep.bias + n_base + i) : 0.f;
+      const int last_w = (sel.constraint && sel.last && row < ep.M) ? (int)__ldg(sel.last + row) : -1;
+      __syncwarp();
+      float mx = -INFINITY, sum = 0.f;
+      float cv[SEL_K];
+      int ci[SEL_K];
+#pragma unroll
+      for (int k = 0; k < SEL_K; ++k) {
+        cv[k] = -INFINITY;
+        ci[k] = 0x7fffffff;
+      }
+      mbar_wait(&acc_full[as], (j >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < SLICE / 32; ++cc) {
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * SLICE + cc * 32, v);
+        const int nb = n_base + cc * 32;
+        if (nb >= ep.N) break;  // warp-uniform: the rest of the slice is past the vocabulary
+        float cm = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          v[q] = (nb + q < ep.N) ? v[q] + bias_s[cc * 32 + q] : -INFINITY;
+          cm = fmaxf(cm, v[q]);
+        }
+        const float mn = fmaxf(mx, cm);  // finite: column nb is inside the vocabulary
+        float part = 0.f;
+        const float mn2 = mn * kLog2e;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          float e;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(v[q], kLog2e, -mn2)));
+          part += e;
+        }
+        float scale;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(scale) : "f"((mx - mn) * kLog2e));  // mx = -inf -> 0
+        sum = fmaf(sum, scale, part);
+        mx = mn;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          if (v[q] > cv[SEL_K - 1]) {
+            const int n = nb + q;
+            const bool masked = (sel.mask_special && (n == sel.pad_id || n == sel.sos_id || n == sel.unk_id)) || n == last_w;
+            if (!masked) topk_insert<SEL_K>(cv, ci, v[q], n);
+          }
+        }
+      }
+      // the accumulator stage is drained: release it to the MMA warp before the stores
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+      }
+      if (row < ep.M) {
+        float4* r4 = reinterpret_cast<float4*>(sel.rec + ((long long)row * sel.np + (tn * 2 + half)) * SEL_REC);
+        r4[0] = make_float4(mx, sum, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < SEL_K; k += 4) {
+          r4[1 + k / 4] = make_float4(cv[k], cv[k + 1], cv[k + 2], cv[k + 3]);
+          r4[1 + SEL_K / 4 + k / 4] = make_float4(__int_as_float(ci[k]), __int_as_float(ci[k + 1]), __int_as_float(ci[k + 2]),
+                                                  __int_as_float(ci[k + 3]));
+        }
+      }
+      __syncwarp();  // bias slice is rewritten for the next tile
+    }
   } else {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> global =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
-    const int half = ew >> 2;      // which 64 of the tile's 128 columns this warp drains
+    const int half = ew >> 2;      // which half of the tile's columns this warp drains
     float4* sc = reinterpret_cast<float4*>(epi_smem) + ew * 32 * 8;  // 32 rows x 8 float4, slot ^= row & 7
     const int r_off = lane >> 3, c4 = lane & 7;  // transposed view: 4 rows x 8 float4 per warp access
     const bool c_vec = ep.c && ((reinterpret_cast<uintptr_t>(ep.c) & 15) == 0) && ((ep.ldc & 3) == 0);
@@ -309,8 +400,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       mbar_wait(&acc_full[as], (j >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + c * 32, v);
 #pragma unroll
@@ -386,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
   }
 }
 
@@ -419,8 +510,9 @@ static int num_sms() {
   return n;
 }
 
-// bf16 plane [rows, cols] with leading dimension ld (elements) -> 2D map, box 64 x 128, 128B swizzle.
-static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int64_t cols, int64_t ld) {
+// bf16 plane [rows, cols] with leading dimension ld (elements) -> 2D map, box box_k x box_rows, swizzle = row bytes.
+static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    int box_k) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled unavailable from the driver");
@@ -432,10 +524,11 @@ static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, i
   }
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_k), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %lld cols %lld ld %lld)", (int)r, (long long)rows,
@@ -445,29 +538,47 @@ static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int64_t rows, i
   return 0;
 }
 
-template <int PASSES, int ACT>
-static int launch_kernel(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
-                         const CUtensorMap& mb_lo, const EpiParams& ep, int grid, cudaStream_t stream) {
-  ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<PASSES>::kSmemBytes));
-  gemm_tc_kernel<PASSES, ACT><<<grid, NUM_THREADS, Cfg<PASSES>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, ep);
+struct Maps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+template <int PASSES, int BN, int ACT, int EPI>
+static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStream_t stream) {
+  ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES, BN, ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg<PASSES, BN>::kSmemBytes));
+  gemm_tc_kernel<PASSES, BN, ACT, EPI><<<grid, NUM_THREADS, Cfg<PASSES, BN>::kSmemBytes, stream>>>(m.a_hi, m.a_lo, m.b_hi,
+                                                                                                 m.b_lo, ep);
   ISC_LAUNCH_CHECK();
   return 0;
 }
 
-template <int PASSES>
+template <int PASSES, int BN>
+static int make_maps(Maps& m, const Operand& A, const Operand& W, int M, int N, int K) {
+  constexpr int BK = Cfg<PASSES, BN>::kBK;
+  ISC_TRY(make_map(&m.a_hi, A.hi, M, K, A.ldp, BM, BK));
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, BN, BK));
+  if (PASSES == 3) {
+    ISC_TRY(make_map(&m.a_lo, A.lo, M, K, A.ldp, BM, BK));
+    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, BN, BK));
+  } else {
+    m.a_lo = m.a_hi;
+    m.b_lo = m.b_hi;
+  }
+  return 0;
+}
+
+template <int BN>
+static int persistent_grid(int M, int N) {
+  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const int sms = num_sms();
+  return tiles < sms ? tiles : sms;  // one CTA per SM walks the tile list
+}
+
+template <int PASSES, int BN>
 static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int N, int K, const Epilogue& e,
                   cudaStream_t stream) {
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  ISC_TRY(make_map(&ma_hi, A.hi, M, K, A.ldp));
-  ISC_TRY(make_map(&mb_hi, W.hi, N, K, W.ldp));
-  if (PASSES == 3) {
-    ISC_TRY(make_map(&ma_lo, A.lo, M, K, A.ldp));
-    ISC_TRY(make_map(&mb_lo, W.lo, N, K, W.ldp));
-  } else {
-    ma_lo = ma_hi;
-    mb_lo = mb_hi;
-  }
+  Maps m;
+  ISC_TRY((make_maps<PASSES, BN>(m, A, W, M, N, K)));
   EpiParams ep;
   ep.bias = e.bias;
   ep.rowadd = e.rowadd;
@@ -484,15 +595,43 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.M = M;
   ep.N = N;
   ep.K = K;
-  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
-  const int sms = num_sms();
-  const int grid = tiles < sms ? tiles : sms;  // persistent: one CTA per SM walks the tile list
+  const int grid = persistent_grid<BN>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
-  if (e.act == ACT_RELU) return launch_kernel<PASSES, ACT_RELU>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
-  if (e.act == ACT_TANH) return launch_kernel<PASSES, ACT_TANH>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
-  if (e.act == ACT_EXPNEG2_RELU)
-    return launch_kernel<PASSES, ACT_EXPNEG2_RELU>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
-  return launch_kernel<PASSES, ACT_NONE>(ma_hi, ma_lo, mb_hi, mb_lo, ep, grid, stream);
+  switch (e.act) {
+    case ACT_RELU: return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD>(m, ep, grid, stream);
+    case ACT_TANH: return launch_kernel<PASSES, BN, ACT_TANH, EPI_STD>(m, ep, grid, stream);
+    case ACT_EXPNEG2_RELU: return launch_kernel<PASSES, BN, ACT_EXPNEG2_RELU, EPI_STD>(m, ep, grid, stream);
+    default: return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD>(m, ep, grid, stream);
+  }
+}
+
+template <int PASSES>
+static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K, const float* bias,
+                         const LogitsSelect& sel, cudaStream_t stream) {
+  constexpr int BN = 256;
+  Maps m;
+  ISC_TRY((make_maps<PASSES, BN>(m, A, W, M, N, K)));
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias;
+  ep.rows_per_group = 1;
+  ep.M = M;
+  ep.N = N;
+  ep.K = K;
+  ep.sel = sel;
+  const int grid = persistent_grid<BN>(M, N);
+  ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS>(m, ep, grid, stream);
+}
+
+// 128x256 tiles move 25 % fewer operand bytes per flop (a tile costs ~1.5x a 128x128 one for 2x the work) but
+// quantise worse on 148 SMs: pick the shape with the smaller waves x tile-cost estimate.
+static bool use_wide_tiles(int M, int N) {
+  if (N < 256) return false;
+  const long long sms = num_sms(), tm = (M + BM - 1) / BM;
+  const long long narrow = (tm * ((N + 127) / 128) + sms - 1) / sms * 2;
+  const long long wide = (tm * ((N + 255) / 256) + sms - 1) / sms * 3;
+  return wide < narrow;
 }
 
 }  // namespace tc
@@ -502,11 +641,24 @@ int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int
   if (M <= 0 || N <= 0) return 0;
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc: K=%d must be a positive multiple of 8", K);
   ISC_REQUIRE(A.hi && W.hi, "gemm_tc: bf16 hi planes missing");
+  const bool wide = tc::use_wide_tiles(M, N);
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc: bf16 lo planes missing for the 3-pass mode");
-    return tc::launch<3>(A, W, C, M, N, K, ep, stream);
+    return wide ? tc::launch<3, 256>(A, W, C, M, N, K, ep, stream) : tc::launch<3, 128>(A, W, C, M, N, K, ep, stream);
   }
-  return tc::launch<1>(A, W, C, M, N, K, ep, stream);
+  return wide ? tc::launch<1, 256>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128>(A, W, C, M, N, K, ep, stream);
+}
+
+int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
+                   const LogitsSelect& sel, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_logits: K=%d must be a positive multiple of 8", K);
+  ISC_REQUIRE(A.hi && W.hi && sel.rec && sel.np == logits_slices(N), "gemm_tc_logits: planes / records missing");
+  if (passes == 3) {
+    ISC_REQUIRE(A.lo && W.lo, "gemm_tc_logits: bf16 lo planes missing for the 3-pass mode");
+    return tc::launch_logits<3>(A, W, M, N, K, bias, sel, stream);
+  }
+  return tc::launch_logits<1>(A, W, M, N, K, bias, sel, stream);
 }
 
 }  // namespace isc

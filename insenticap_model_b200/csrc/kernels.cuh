@@ -87,6 +87,8 @@ struct GreedyParams {
   long long* it = nullptr;        // [B] next input token (written)
   int* unfinished = nullptr;      // [B] (read/write)
   int* alive_count = nullptr;     // [T] number of unfinished rows after step t
+  const float* rec = nullptr;     // fused argmax path (sample_mode 0): [B][np][SEL_REC], logits is null then
+  int np = 0;
   long long* seq = nullptr;       // [B,T]
   float* seq_logprobs = nullptr;  // [B,T]
   float* seq_masks = nullptr;     // [B,T]
@@ -111,6 +113,9 @@ struct BeamParams {
   long long* it = nullptr;  // [B*K] last word per beam: read as "last", written for the next step
   int* parent = nullptr;    // [B*K] absolute state row each new beam continues from (written)
   // scratch: per-row candidates published by the row CTAs, per-image ticket counter (zeroed once)
+  // fused path: records written by the logits GEMM epilogue (common.cuh LogitsSelect); logits is null then
+  const float* rec = nullptr;  // [B*K][np][SEL_REC]
+  int np = 0;
   float* cand_lp = nullptr;  // [B*K, 8]
   int* cand_word = nullptr;  // [B*K, 8]
   int* cand_count = nullptr; // [B*K]

@@ -155,6 +155,143 @@ __global__ void __launch_bounds__(NT) greedy_select_kernel(GreedyParams p) {
   }
 }
 
+// Pool the candidates of an image's rows with its carried finished beams and keep the K best by fp64 score,
+// stably (captioner.py:404-409); then write the new beam state. Called by every thread of ONE block per image,
+// after the rows' candidates (cand_lp / cand_word / cand_count) are visible.
+__device__ __forceinline__ void beam_pool(const BeamParams& p, int b) {
+  __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
+  const int K = p.K, t = p.t, T = p.T;
+  if (threadIdx.x == 0) {
+    double pool_score[KMAX * KMAX + KMAX];
+    int pool_parent[KMAX * KMAX + KMAX], pool_word[KMAX * KMAX + KMAX];
+    long long lasts[KMAX];
+    int n = 0;
+    for (int kk = 0; kk < K; ++kk) {
+      const int mm = b * K + kk;
+      lasts[kk] = p.it[mm];
+      if (!p.alive_in[mm]) continue;
+      const double base = p.score_in[mm];
+      if (t > 0 && lasts[kk] == p.eos_id) {
+        pool_score[n] = base;
+        pool_parent[n] = kk;
+        pool_word[n] = -1;
+        ++n;
+      } else {
+        const int cnt = __ldcg(p.cand_count + mm);
+        for (int r = 0; r < cnt; ++r) {
+          // python-float running sum of fp32 log-probs (captioner.py:404-407)
+          pool_score[n] = base + (double)__ldcg(p.cand_lp + mm * KMAX + r);
+          pool_parent[n] = kk;
+          pool_word[n] = __ldcg(p.cand_word + mm * KMAX + r);
+          ++n;
+        }
+      }
+    }
+    // stable top-K of the pool by score (python sorted(reverse=True) keeps pool order on ties)
+    unsigned long long taken = 0ULL;
+    int j = 0;
+    for (; j < K && j < n; ++j) {
+      int best = -1;
+      for (int i = 0; i < n; ++i) {
+        if ((taken >> i) & 1ULL) continue;
+        if (best < 0 || pool_score[i] > pool_score[best]) best = i;
+      }
+      taken |= 1ULL << best;
+      const int kk = pool_parent[best], w = pool_word[best];
+      sel_parent[j] = kk;
+      sel_word[j] = w;
+      p.score_out[b * K + j] = pool_score[best];
+      p.alive_out[b * K + j] = 1;
+      p.len_out[b * K + j] = p.len_in[b * K + kk] + (w >= 0 ? 1 : 0);
+      p.parent[b * K + j] = b * K + kk;
+      p.it[b * K + j] = (w >= 0) ? (long long)w : lasts[kk];
+    }
+    sel_n = j;
+    for (; j < K; ++j) {
+      p.score_out[b * K + j] = 0.0;
+      p.alive_out[b * K + j] = 0;
+      p.len_out[b * K + j] = 0;
+      p.parent[b * K + j] = b * K + j;
+      p.it[b * K + j] = p.sos_id;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * T; i += blockDim.x) {
+    const int j = i / T, tt = i - j * T;
+    int v = 0;
+    if (j < sel_n) {
+      const int kk = sel_parent[j];
+      v = p.tok_in[(b * K + kk) * T + tt];
+      if (sel_word[j] >= 0 && tt == p.len_in[b * K + kk]) v = sel_word[j];
+    }
+    p.tok_out[(b * K + j) * T + tt] = v;
+  }
+}
+
+// ---- merge of the LogitsSelect records written by the logits GEMM epilogue (common.cuh) --------------------
+// One warp reduces the np records of a row to the row max, log(sum exp) and the row's K <= SEL_K best unmasked
+// logits (value desc, column asc). Results are broadcast to every lane.
+__device__ __forceinline__ void merge_row(const float* __restrict__ rec, int np, int K, int lane, float& mx_out,
+                                          float& lse_out, float (&out_v)[SEL_K], int (&out_i)[SEL_K]) {
+  float mx = -CUDART_INF_F;
+  for (int pi = lane; pi < np; pi += 32) mx = fmaxf(mx, __ldcg(rec + (long long)pi * SEL_REC));
+  mx = warp_max(mx);
+  float sum = 0.f;
+  float cv[SEL_K];
+  int ci[SEL_K];
+#pragma unroll
+  for (int k = 0; k < SEL_K; ++k) {
+    cv[k] = -CUDART_INF_F;
+    ci[k] = 0x7fffffff;
+  }
+  for (int pi = lane; pi < np; pi += 32) {
+    const float4* r4 = reinterpret_cast<const float4*>(rec + (long long)pi * SEL_REC);
+    const float4 h = __ldcg(r4);
+    if (h.x > -CUDART_INF_F) sum += h.y * __expf(h.x - mx);
+#pragma unroll
+    for (int q = 0; q < SEL_K / 4; ++q) {
+      const float4 v4 = __ldcg(r4 + 1 + q), i4 = __ldcg(r4 + 1 + SEL_K / 4 + q);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      const int ii[4] = {__float_as_int(i4.x), __float_as_int(i4.y), __float_as_int(i4.z), __float_as_int(i4.w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (vv[e] > cv[SEL_K - 1]) topk_insert<SEL_K>(cv, ci, vv[e], ii[e]);
+    }
+  }
+  sum = warp_sum(sum);
+  mx_out = mx;
+  lse_out = logf(sum);
+#pragma unroll
+  for (int r = 0; r < SEL_K; ++r) {
+    out_v[r] = -CUDART_INF_F;
+    out_i[r] = 0x7fffffff;
+    if (r < K) {
+      float bv = cv[0];
+      int bi = ci[0];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      out_v[r] = bv;
+      out_i[r] = bi;
+      if (ci[0] == bi) {  // the winning lane pops its head
+#pragma unroll
+        for (int k = 0; k + 1 < SEL_K; ++k) {
+          cv[k] = cv[k + 1];
+          ci[k] = ci[k + 1];
+        }
+        cv[SEL_K - 1] = -CUDART_INF_F;
+        ci[SEL_K - 1] = 0x7fffffff;
+      }
+    }
+  }
+}
+
 // Beam expansion + pooled stable top-K. One CTA per beam ROW scans its logits:
 //   pass 1 = thread-local maxima with 128-bit loads; the (K+4)-th largest thread maximum is a threshold
 //   tau that at least K unmasked entries reach (<= 4 entries are masked);
@@ -172,8 +309,7 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
   __shared__ int is_last;
   __shared__ float gmax[32];
   __shared__ float stat[2];
-  __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
-  const int m = blockIdx.x, K = p.K, V = p.V, t = p.t, T = p.T;
+  const int m = blockIdx.x, K = p.K, V = p.V, t = p.t;
   const int b = m / K;
   const bool mask_special = (p.pad_id != p.eos_id);
   const int last = (int)p.it[m];
@@ -271,70 +407,60 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
   __syncthreads();
   if (!is_last) return;
 
-  if (threadIdx.x == 0) {
-    double pool_score[KMAX * KMAX + KMAX];
-    int pool_parent[KMAX * KMAX + KMAX], pool_word[KMAX * KMAX + KMAX];
-    long long lasts[KMAX];
-    int n = 0;
-    for (int kk = 0; kk < K; ++kk) {
-      const int mm = b * K + kk;
-      lasts[kk] = p.it[mm];
-      if (!p.alive_in[mm]) continue;
-      const double base = p.score_in[mm];
-      if (t > 0 && lasts[kk] == p.eos_id) {
-        pool_score[n] = base;
-        pool_parent[n] = kk;
-        pool_word[n] = -1;
-        ++n;
-      } else {
-        const int cnt = __ldcg(p.cand_count + mm);
-        for (int r = 0; r < cnt; ++r) {
-          // python-float running sum of fp32 log-probs (captioner.py:404-407)
-          pool_score[n] = base + (double)__ldcg(p.cand_lp + mm * KMAX + r);
-          pool_parent[n] = kk;
-          pool_word[n] = __ldcg(p.cand_word + mm * KMAX + r);
-          ++n;
+  beam_pool(p, b);
+}
+
+// Fused path: the logits GEMM already produced per-slice partials; one CTA per image (4 warps, a warp per row)
+// merges them and pools the image's beams.
+__global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
+  const int b = blockIdx.x, K = p.K, t = p.t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int kk = warp; kk < K; kk += 4) {
+    const int m = b * K + kk;
+    const bool alive = p.alive_in[m] != 0;
+    const bool finished = alive && t > 0 && (int)p.it[m] == p.eos_id;
+    if (alive && !finished) {
+      float mx, lse, v[SEL_K];
+      int w[SEL_K];
+      merge_row(p.rec + (long long)m * p.np * SEL_REC, p.np, K, lane, mx, lse, v, w);
+      if (lane == 0) {
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < SEL_K; ++r) {
+          if (r < K && v[r] > -CUDART_INF_F) {
+            p.cand_lp[m * KMAX + r] = (v[r] - mx) - lse;  // log_softmax value, fp32 like the reference
+            p.cand_word[m * KMAX + r] = w[r];
+            cnt = r + 1;
+          }
         }
+        p.cand_count[m] = cnt;
       }
-    }
-    // stable top-K of the pool by score (python sorted(reverse=True) keeps pool order on ties)
-    unsigned long long taken = 0ULL;
-    int j = 0;
-    for (; j < K && j < n; ++j) {
-      int best = -1;
-      for (int i = 0; i < n; ++i) {
-        if ((taken >> i) & 1ULL) continue;
-        if (best < 0 || pool_score[i] > pool_score[best]) best = i;
-      }
-      taken |= 1ULL << best;
-      const int kk = pool_parent[best], w = pool_word[best];
-      sel_parent[j] = kk;
-      sel_word[j] = w;
-      p.score_out[b * K + j] = pool_score[best];
-      p.alive_out[b * K + j] = 1;
-      p.len_out[b * K + j] = p.len_in[b * K + kk] + (w >= 0 ? 1 : 0);
-      p.parent[b * K + j] = b * K + kk;
-      p.it[b * K + j] = (w >= 0) ? (long long)w : lasts[kk];
-    }
-    sel_n = j;
-    for (; j < K; ++j) {
-      p.score_out[b * K + j] = 0.0;
-      p.alive_out[b * K + j] = 0;
-      p.len_out[b * K + j] = 0;
-      p.parent[b * K + j] = b * K + j;
-      p.it[b * K + j] = p.sos_id;
     }
   }
+  __threadfence_block();
   __syncthreads();
-  for (int i = threadIdx.x; i < K * T; i += NT) {
-    const int j = i / T, tt = i - j * T;
-    int v = 0;
-    if (j < sel_n) {
-      const int kk = sel_parent[j];
-      v = p.tok_in[(b * K + kk) * T + tt];
-      if (sel_word[j] >= 0 && tt == p.len_in[b * K + kk]) v = sel_word[j];
-    }
-    p.tok_out[(b * K + j) * T + tt] = v;
+  beam_pool(p, b);
+}
+
+// Fused greedy pick (sample_max = 1): a warp per row takes the argmax and the normaliser from the records.
+__global__ void __launch_bounds__(256) greedy_merge_kernel(GreedyParams p) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int t = p.t;
+  if (b >= p.B) return;
+  if (t > 0 && p.alive_count[t - 1] == 0) return;  // whole-batch early stop (captioner.py:343-344)
+  float mx, lse, v[SEL_K];
+  int w[SEL_K];
+  merge_row(p.rec + (long long)b * p.np * SEL_REC, p.np, 1, lane, mx, lse, v, w);
+  if (lane == 0) {
+    const int unf = p.unfinished[b];
+    const long long tok = unf ? w[0] : 0;  // finished rows emit PAD (captioner.py:338)
+    p.seq[(long long)b * p.T + t] = tok;
+    p.seq_logprobs[(long long)b * p.T + t] = (v[0] - mx) - lse;  // written unmasked (captioner.py:340)
+    p.seq_masks[(long long)b * p.T + t] = unf ? 1.f : 0.f;
+    const int unf2 = unf && (tok != p.eos_id);
+    p.unfinished[b] = unf2;
+    p.it[b] = tok;
+    if (unf2) atomicAdd(p.alive_count + t, 1);
   }
 }
 
@@ -373,6 +499,13 @@ int launch_log_softmax(float* x, long long ld, int M, int V, cudaStream_t stream
   return 0;
 }
 int launch_greedy_select(const GreedyParams& p, cudaStream_t stream) {
+  if (p.rec) {
+    ISC_REQUIRE(p.sample_mode == 0, "fused greedy pick only serves sample_max = 1");
+    ProfScope ps(ISC_K_SELECT, (double)p.B * p.np * SEL_REC * 4.0, stream);
+    greedy_merge_kernel<<<(p.B + 7) / 8, 256, 0, stream>>>(p);
+    ISC_LAUNCH_CHECK();
+    return 0;
+  }
   ProfScope ps(ISC_K_SELECT, (double)p.B * p.V * 4.0 * (p.sample_mode == 1 ? 2 : 1), stream);
   greedy_select_kernel<<<p.B, NT, 0, stream>>>(p);
   ISC_LAUNCH_CHECK();
@@ -381,6 +514,13 @@ int launch_greedy_select(const GreedyParams& p, cudaStream_t stream) {
 int launch_beam_select(const BeamParams& p, cudaStream_t stream) {
   ISC_REQUIRE(p.K >= 1 && p.K <= KMAX, "beam size %d not in 1..%d", p.K, KMAX);
   ISC_REQUIRE(p.cand_lp && p.cand_word && p.cand_count && p.ticket, "beam_select: scratch buffers missing");
+  if (p.rec) {
+    ISC_REQUIRE(p.K <= SEL_K, "fused beam merge serves beam sizes up to %d", SEL_K);
+    ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.np * SEL_REC * 4.0, stream);
+    beam_merge_kernel<<<p.B, 128, 0, stream>>>(p);
+    ISC_LAUNCH_CHECK();
+    return 0;
+  }
   ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.V * 4.0, stream);
   beam_select_kernel<<<p.B * p.K, NT, 0, stream>>>(p);
   ISC_LAUNCH_CHECK();

@@ -29,7 +29,8 @@ def _cfg1():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
-@pytest.mark.parametrize("shape", [(300, 200, 136), (128, 128, 64), (1, 10000, 512), (640, 512, 2048), (3072, 2048, 1536)])
+@pytest.mark.parametrize("shape", [(300, 200, 136), (128, 128, 64), (1, 10000, 512), (640, 512, 2048), (3072, 2048, 1536),
+                                   (3072, 1536, 512), (18816, 512, 64)])  # the last two take the 128x256-tile kernel
 def test_gemm(precision, shape):
     import ctypes as C
     from insenticap_model_b200 import _lib
