@@ -107,6 +107,9 @@ class Captioner(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        self.use_cuda_graph = False  # beam_search: capture the device-side call once and replay it
+        self._graphs = {}
+        self._copy_stream = None
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
         self.fc_feats = self.cpt_feats = None
 
@@ -377,17 +380,86 @@ class Captioner(nn.Module):
         return seq, lps, masks
 
     def beam_search(self, fc_feats, att_feats, senti_words=None, senti_labels=None, beam_size=3,
-                    decoding_constraint=1, max_seq_len=16):
+                    decoding_constraint=1, max_seq_len=16, host_chunk=256):
         """Batched beam search: Captioner.sample (captioner.py:351-420) for B images at once.
-        Returns tokens int64 [B,K,T] (EOS included, 0 padded), scores float64 [B,K], lengths int32 [B,K]."""
+        Returns tokens int64 [B,K,T] (EOS included, 0 padded), scores float64 [B,K], lengths int32 [B,K].
+
+        Inputs may be CUDA tensors, or HOST tensors (pinned for speed): host batches are cut into sub-batches of
+        ``host_chunk`` images whose H2D copies run on a copy stream while the previous sub-batch decodes
+        (images are independent, so the result is bit-identical to the one-batch call); the results then come
+        back as pinned host tensors. With ``self.use_cuda_graph`` the whole device-side call (~190 launches) is
+        captured once per (input buffers, shapes) and replayed; outputs are then reused by the next replay."""
+        if not fc_feats.is_cuda:
+            return self._beam_search_host(fc_feats, att_feats, senti_words, senti_labels, beam_size,
+                                          decoding_constraint, max_seq_len, host_chunk)
+        if not self.use_cuda_graph:
+            return self._beam_search_device(fc_feats, att_feats, senti_words, senti_labels, beam_size,
+                                            decoding_constraint, max_seq_len)
+        args = (fc_feats, att_feats, senti_words, senti_labels)
+        self.pack_weights()
+        key = tuple((a.data_ptr(), tuple(a.shape), a.dtype) if a is not None else None for a in args) + (
+            int(beam_size), int(bool(decoding_constraint)), int(max_seq_len), self._packed_key)
+        hit = self._graphs.get(key)
+        if hit is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            # eager run first: sizes the workspaces outside the capture and surfaces argument errors
+            self._beam_search_device(*args, beam_size, decoding_constraint, max_seq_len)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._beam_search_device(*args, beam_size, decoding_constraint, max_seq_len)
+            hit = self._graphs[key] = (g, out, args)  # args kept alive: the graph holds their addresses
+        hit[0].replay()
+        return hit[1]
+
+    def _beam_search_host(self, fc_feats, att_feats, senti_words, senti_labels, beam_size, decoding_constraint,
+                          max_seq_len, host_chunk):
+        dev = self._device()
+        B, K, T = fc_feats.shape[0], int(beam_size), int(max_seq_len)
+        cur = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        cs.wait_stream(cur)
+        staged = []
+        for lo in range(0, B, int(host_chunk)):  # enqueue every H2D copy up front: the copy engine runs ahead
+            hi = min(B, lo + int(host_chunk))
+            with torch.cuda.stream(cs):
+                d = [x[lo:hi].to(dev, non_blocking=True) if x is not None else None
+                     for x in (fc_feats, att_feats, senti_words, senti_labels)]
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            staged.append((lo, hi, d, ev))
+        tokens = torch.empty(B, K, T, dtype=torch.long, device=dev)
+        scores = torch.empty(B, K, dtype=torch.float64, device=dev)
+        lengths = torch.empty(B, K, dtype=torch.int32, device=dev)
+        for lo, hi, d, ev in staged:
+            cur.wait_event(ev)
+            for x in d:
+                if x is not None:
+                    x.record_stream(cur)
+            self._beam_search_device(*d, K, decoding_constraint, T, out=(tokens[lo:hi], scores[lo:hi], lengths[lo:hi]))
+        outs = []
+        for x in (tokens, scores, lengths):
+            h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+            h.copy_(x, non_blocking=True)
+            outs.append(h)
+        return tuple(outs)
+
+    def _beam_search_device(self, fc_feats, att_feats, senti_words, senti_labels, beam_size, decoding_constraint,
+                            max_seq_len, out=None):
         dev = self._device()
         lib = _lib.load()
         t, B = self.prologue(fc_feats, att_feats, None, senti_words, senti_labels)
         d = t["_dims"]
         K, T = int(beam_size), int(max_seq_len)
-        tokens = torch.empty(B, K, T, dtype=torch.long, device=dev)
-        scores = torch.empty(B, K, dtype=torch.float64, device=dev)
-        lengths = torch.empty(B, K, dtype=torch.int32, device=dev)
+        if out is None:
+            tokens = torch.empty(B, K, T, dtype=torch.long, device=dev)
+            scores = torch.empty(B, K, dtype=torch.float64, device=dev)
+            lengths = torch.empty(B, K, dtype=torch.int32, device=dev)
+        else:
+            tokens, scores, lengths = out
         ws = self._decode_ws(d, B * K, dev)
         feats = self._make_feats(t)
         with torch.cuda.device(dev):

@@ -301,3 +301,27 @@ def test_large_batch_greedy_vs_oracle_with_tie_tolerance():
     assert ties <= 2, ties
     same = (seq.cpu() == seq_o).all(1)
     np.testing.assert_allclose(lp.cpu()[same].numpy(), lp_o[same].numpy(), **LP_TOL)
+
+
+def test_beam_graph_replay_and_host_pipeline_match_eager():
+    """CUDA-graph replay and the pipelined host-input path of Captioner.beam_search are the same computation
+    as the eager device call: bit-identical tokens, scores and lengths (images are independent)."""
+    V, B, (fc, att, cpts, sentis, labels) = _cfg1()
+    m = model(V, 0, "bf16x3")
+    dev_in = to_cuda(fc, att, sentis, labels)
+    ref = [x.clone() for x in m.beam_search(*dev_in, beam_size=3, max_seq_len=T)]
+    m.use_cuda_graph = True
+    try:
+        for _ in range(3):
+            got = m.beam_search(*dev_in, beam_size=3, max_seq_len=T)
+        torch.cuda.synchronize()
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    finally:
+        m.use_cuda_graph = False
+        m._graphs.clear()
+    host = m.beam_search(fc.pin_memory(), att.pin_memory(), sentis.pin_memory(), labels.pin_memory(), beam_size=3,
+                         max_seq_len=T, host_chunk=3)
+    torch.cuda.synchronize()
+    for a, b in zip(host, ref):
+        assert not a.is_cuda and torch.equal(a, b.cpu())
