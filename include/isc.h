@@ -94,6 +94,18 @@ typedef struct isc_feats {
   float* cpt_feats; /* [B,H]   ReLU(cpt2fc(mean ReLU(word_embed(cpt_words)))) or NULL */
 } isc_feats_t;
 
+/* Training-mode dropout (nn.Dropout(p), captioner.py:132): uint8 KEEP masks (1 = keep) supplied by the caller so
+ * that a run is reproducible and testable against the reference with the same masks; NULL = no dropout on
+ * that tensor. Kept values are multiplied by scale = 1 / (1 - p). */
+typedef struct isc_dropout {
+  const uint8_t* fc;  /* [B,H]   on the fc embedding (:200/:296); seq2seq: on cpt_feats (:250) */
+  const uint8_t* att; /* [B,L,H] on the region embedding, before att2att (:210/:304) */
+  const uint8_t* sw;  /* [B,S,H] on the sentiment-word embedding, before senti2att (:258/:311) */
+  const uint8_t* sl;  /* [B,H]   on the sentiment-label embedding (:214/:262/:315) */
+  const uint8_t* out; /* [T,B,H] on h_lang before the classifier, one mask per step (:182) */
+  float scale;
+} isc_dropout_t;
+
 const char* isc_version(void);
 const char* isc_last_error(void);
 
@@ -120,7 +132,8 @@ int isc_prologue(const isc_dims_t* dims, const void* packed, int precision,
                  const int64_t* cpt_words, int n_cpt,
                  const int64_t* senti_words, const int64_t* senti_labels,
                  int B, int seq2seq, const isc_feats_t* out,
-                 void* workspace, size_t workspace_bytes, isc_stream_t stream);
+                 void* workspace, size_t workspace_bytes, isc_stream_t stream,
+                 const isc_dropout_t* dropout /* NULL: eval mode */);
 
 /* Convert caller-supplied, already-embedded fp32 features (the att_feats / p_att_feats /
  * p_senti_word_feats arguments of Captioner.forward_step, captioner.py:168) into the
@@ -161,7 +174,9 @@ int isc_decode_greedy(const isc_dims_t* dims, const void* packed, int precision,
                       const float* noise, uint64_t seed,
                       int64_t* seq, float* seq_logprobs, float* seq_masks,
                       float* cont_w, float* senti_w, float* gate_w,
-                      void* workspace, size_t workspace_bytes, isc_stream_t stream);
+                      void* workspace, size_t workspace_bytes, isc_stream_t stream,
+                      const uint8_t* out_mask /* [T,B,H] keep mask on h_lang (captioner.py:182) or NULL */,
+                      float drop_scale);
 
 /* ---- batched beam search: Captioner.sample, captioner.py:378-420, for B images at once -----
  * K = beam_size <= 8. tokens int64 [B,K,T] (EOS included, zero padded), scores fp64 [B,K]
@@ -179,6 +194,56 @@ int isc_teacher_forced(const isc_dims_t* dims, const void* packed, int precision
                        const isc_feats_t* feats, int B, int n_steps,
                        const int64_t* inputs, int64_t ld_inputs, float* logprobs,
                        void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- training: teacher-forced forward with a tape, hand-written backward, fused clamp + Adam ------------
+ * Replaces autograd through Captioner.forward_xe (:194-240) / forward_seq2seq (:242-288), and through the
+ * sampled forward_rl pass (models/decoder.py:86-88): REINFORCE re-scores the sampled tokens teacher-forced
+ * in ISC_MODE_RL, which is the same computation. ISC_PREC_BF16X3 only.
+ *   forward : prologue (+dropout masks) and n_steps decode steps feeding inputs[:, t]; writes
+ *             logprobs fp32 [B, n_steps, V] (the reference's return value), the pre-dropout fc embedding
+ *             (self.fc_feats) and cpt_feats (self.cpt_feats) when non-NULL, and the activation tape into
+ *             the workspace, which must stay untouched until the matching backward.
+ *   backward: incoming gradient either dense (dlogprobs [B, n_steps, V]) or as the fused masked-NLL /
+ *             REINFORCE form loss = sum_{b,t} coef[b,t] * (-logprobs[b,t,targets[b,t]]) (XECriterion
+ *             :427-440, RewardCriterion self_critical/utils.py:169-177; coef [B, n_steps], targets
+ *             int64 [B, ld_targets]); d_cpt_feats [B,H] is the gradient wrt cpt_feats (MSE domain-
+ *             alignment loss, train_xe.py:163) or NULL. Parameter gradients are ACCUMULATED (+=) into
+ *             *grads, laid out like the reference's tensors. */
+#define ISC_MODE_XE 0
+#define ISC_MODE_SEQ2SEQ 1
+#define ISC_MODE_RL 2
+typedef struct isc_grads {
+  float* word_embed; float* senti_label_embed;
+  float* fc_embed_w; float* fc_embed_b; float* cpt2fc_w; float* cpt2fc_b; float* att_embed_w; float* att_embed_b;
+  float* att_lstm_w_ih; float* att_lstm_w_hh; float* att_lstm_b_ih; float* att_lstm_b_hh;
+  float* att2att_w; float* att2att_b; float* senti2att_w; float* senti2att_b;
+  float* ca_h2att_w; float* ca_h2att_b; float* ca_alpha_w; float* ca_alpha_b;
+  float* sa_h2word_w; float* sa_h2word_b; float* sa_label2word_w; float* sa_label2word_b;
+  float* sa_alpha_w; float* sa_alpha_b;
+  float* g_h2att_w; float* g_h2att_b; float* g_cont2att_w; float* g_cont2att_b;
+  float* g_senti2att_w; float* g_senti2att_b; float* g_alpha_w; float* g_alpha_b;
+  float* lang_lstm_w_ih; float* lang_lstm_w_hh; float* lang_lstm_b_ih; float* lang_lstm_b_hh;
+  float* classifier_w; float* classifier_b;
+} isc_grads_t; /* same order as isc_weights_t */
+size_t isc_train_workspace_bytes(const isc_dims_t* dims, int precision, int B, int n_steps);
+int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision, int mode,
+                      const float* fc_feats, const float* att_feats, const int64_t* cpt_words, int n_cpt,
+                      const int64_t* senti_words, const int64_t* senti_labels, int B,
+                      const int64_t* inputs, int64_t ld_inputs, int n_steps, const isc_dropout_t* dropout,
+                      float* logprobs, float* fc_embedded, float* cpt_feats,
+                      void* workspace, size_t workspace_bytes, isc_stream_t stream);
+int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision, int mode,
+                       const float* fc_feats, const float* att_feats, const int64_t* cpt_words, int n_cpt,
+                       const int64_t* senti_words, const int64_t* senti_labels, int B,
+                       const int64_t* inputs, int64_t ld_inputs, int n_steps, const isc_dropout_t* dropout,
+                       const float* logprobs, const float* dlogprobs, const int64_t* targets,
+                       int64_t ld_targets, const float* coef, const float* d_cpt_feats,
+                       const isc_grads_t* grads, void* workspace, size_t workspace_bytes, isc_stream_t stream);
+/* Element-wise clamp to +-clip (train_xe.py:19-23; clip <= 0 disables) then torch.optim.Adam's update, fused over a
+ * flat fp32 buffer; grads are first multiplied by grad_scale (1 / world_size after a summing all-reduce). */
+int isc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float clip, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int step, float grad_scale, isc_stream_t stream);
 
 /* ---- dense contraction on its own (validation / profiling of the tensor-core kernel) -------
  * C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]), fp32 in/out; act 0 none, 1 ReLU, 2 tanh.
@@ -229,7 +294,8 @@ int isc_cider_ngram_counts(const int64_t* hyp, int32_t T, int32_t sos_id, int32_
 #define ISC_K_POINTWISE 4 /* embed/pack, gate mix, prologue gathers, plane split, fills */
 #define ISC_K_SELECT 5    /* log_softmax, greedy pick, beam expansion + merge */
 #define ISC_K_CIDER 6
-#define ISC_K_NUM 7
+#define ISC_K_TRAIN 7     /* backward-pass glue kernels, clamp + Adam */
+#define ISC_K_NUM 8
 uint64_t isc_launch_count(void);
 int isc_profile_enable(int on);
 int isc_profile_reset(void);

@@ -60,8 +60,19 @@ class Feats(C.Structure):
     _fields_ = [(f, C.c_void_p) for f in FEAT_FIELDS]
 
 
+class Dropout(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f in ("fc", "att", "sw", "sl", "out")] + [("scale", C.c_float)]
+
+
+class Grads(C.Structure):
+    _fields_ = [(f, C.c_void_p) for f, _ in WEIGHT_FIELDS]
+
+
+MODE_XE, MODE_SEQ2SEQ, MODE_RL = 0, 1, 2
+
 _vp, _i32, _i64, _sz, _u64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_uint64, C.c_double
 _PD, _PW, _PF = C.POINTER(Dims), C.POINTER(Weights), C.POINTER(Feats)
+_PDR, _PG, _f32 = C.POINTER(Dropout), C.POINTER(Grads), C.c_float
 
 # name -> (restype, argtypes); must list every symbol include/isc.h declares (tests/test_abi.py)
 SIGNATURES = {
@@ -72,17 +83,23 @@ SIGNATURES = {
     "isc_pack_weights": (C.c_int, [_PD, _PW, C.c_int, _vp, _sz, _vp]),
     "isc_prologue_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int]),
     "isc_prologue": (C.c_int, [_PD, _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _PF,
-                               _vp, _sz, _vp]),
+                               _vp, _sz, _vp, _PDR]),
     "isc_convert_features": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _i64, _vp]),
     "isc_hoist": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _PF, _vp, _sz, _vp]),
     "isc_decode_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int]),
     "isc_decode_step": (C.c_int, [_PD, _vp, C.c_int, _PF, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
                                   _vp, _vp, _vp, _vp, _sz, _vp]),
     "isc_decode_greedy": (C.c_int, [_PD, _vp, C.c_int, _PF, C.c_int, C.c_int, C.c_int, _vp, _u64, _vp, _vp, _vp,
-                                    _vp, _vp, _vp, _vp, _sz, _vp]),
+                                    _vp, _vp, _vp, _vp, _sz, _vp, _vp, _f32]),
     "isc_decode_beam": (C.c_int, [_PD, _vp, C.c_int, _PF, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp,
                                   _vp, _sz, _vp]),
     "isc_teacher_forced": (C.c_int, [_PD, _vp, C.c_int, _PF, C.c_int, C.c_int, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "isc_train_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int, C.c_int]),
+    "isc_train_forward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
+                                    _PDR, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "isc_train_backward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
+                                     _PDR, _vp, _vp, _vp, _i64, _vp, _vp, _PG, _vp, _sz, _vp]),
+    "isc_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int, _f32, _vp]),
     "isc_gemm_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "isc_gemm_tn": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
                               _vp, _sz, _vp]),
@@ -97,7 +114,7 @@ SIGNATURES = {
     "isc_profile_read": (C.c_int, [C.c_int, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_i64)]),
 }
 
-KERNEL_CLASSES = ["gemm_tc", "gemm_simt", "attention", "lstm", "pointwise", "select", "cider"]
+KERNEL_CLASSES = ["gemm_tc", "gemm_simt", "attention", "lstm", "pointwise", "select", "cider", "train"]
 
 _lib = None
 

@@ -66,6 +66,71 @@ class XECriterion(nn.Module):
         return nll.sum() / mask.sum()
 
 
+class _TeacherForced(torch.autograd.Function):
+    """Teacher-forced decode with hand-written backward (isc_train_forward / isc_train_backward).
+
+    forward(model, mode, call, *params) -> (logprobs [B,T,V], fc_embedded [B,512], cpt_feats [B,512]); ``params`` are the
+    model's parameters in _lib.WEIGHT_FIELDS order (passed so that autograd routes their gradients)."""
+
+    @staticmethod
+    def forward(ctx, model, mode, call, *params):
+        lib = _lib.load()
+        dev = model._device()
+        packed = model.pack_weights()
+        B, n_steps = call["inputs"].shape[0], call["inputs"].shape[1] - 1
+        d = model._dims(call["n_regions"], call["n_senti"])
+        nbytes = lib.isc_train_workspace_bytes(C.byref(d), model._prec, B, n_steps)
+        if nbytes == 0:
+            _lib.check(-1, "isc_train_workspace_bytes")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)  # holds the tape until backward
+        f32 = dict(dtype=torch.float32, device=dev)
+        logprobs = torch.empty(B, n_steps, model.vocab_size, **f32)
+        fc_emb = torch.zeros(B, 512, **f32)
+        cpt = torch.zeros(B, 512, **f32)
+        drop = model._dropout_struct(call["dropout"])
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_train_forward(
+                C.byref(d), _lib.ptr(packed), model._prec, mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
+                _lib.ptr(call["cpt"]), call["cpt"].shape[1] if call["cpt"] is not None else 0, _lib.ptr(call["sw"]),
+                _lib.ptr(call["labels"]), B, _lib.ptr(call["inputs"]), call["inputs"].shape[1], n_steps,
+                C.byref(drop) if call["dropout"] else None, _lib.ptr(logprobs), _lib.ptr(fc_emb),
+                _lib.ptr(cpt) if call["cpt"] is not None else None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                "isc_train_forward")
+        ctx.model, ctx.mode, ctx.call, ctx.ws, ctx.dims, ctx.packed = model, mode, call, ws, d, packed
+        ctx.save_for_backward(logprobs)
+        ctx.param_shapes = [p.shape for p in params]
+        ctx.mark_non_differentiable(fc_emb)
+        return logprobs, fc_emb, cpt
+
+    @staticmethod
+    def backward(ctx, dlogp, _dfc, dcpt):
+        lib = _lib.load()
+        model, call, d = ctx.model, ctx.call, ctx.dims
+        dev = model._device()
+        (logprobs,) = ctx.saved_tensors
+        B, n_steps = call["inputs"].shape[0], call["inputs"].shape[1] - 1
+        sizes = [int(torch.Size(sh).numel()) for sh in ctx.param_shapes]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, g, off = [], _lib.Grads(), 0
+        for (field, _), n, sh in zip(_lib.WEIGHT_FIELDS, sizes, ctx.param_shapes):
+            v = flat[off:off + n].view(sh)
+            views.append(v)
+            setattr(g, field, v.data_ptr())
+            off += n
+        dlogp = dlogp.contiguous() if dlogp is not None else None
+        dcpt = dcpt.contiguous() if (dcpt is not None and call["cpt"] is not None) else None
+        drop = model._dropout_struct(call["dropout"])
+        with torch.cuda.device(dev):
+            _lib.check(lib.isc_train_backward(
+                C.byref(d), _lib.ptr(ctx.packed), model._prec, ctx.mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
+                _lib.ptr(call["cpt"]), call["cpt"].shape[1] if call["cpt"] is not None else 0, _lib.ptr(call["sw"]),
+                _lib.ptr(call["labels"]), B, _lib.ptr(call["inputs"]), call["inputs"].shape[1], n_steps,
+                C.byref(drop) if call["dropout"] else None, _lib.ptr(logprobs), _lib.ptr(dlogp), None, 0, None,
+                _lib.ptr(dcpt), C.byref(g), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr(dev)), "isc_train_backward")
+        ctx.ws = None
+        return (None, None, None) + tuple(views)
+
+
 class Captioner(nn.Module):
     def __init__(self, idx2word, sentiment_categories, settings, precision: str = "bf16x3"):
         super().__init__()
@@ -107,6 +172,7 @@ class Captioner(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        self.dropout_override = None  # tests: dict of uint8 keep masks {fc, att, sw, sl, out, scale}
         self.use_cuda_graph = False  # beam_search: capture the device-side call once and replay it
         self._graphs = {}
         self._copy_stream = None
@@ -190,15 +256,62 @@ class Captioner(nn.Module):
                                                         x.numel(), _lib.stream_ptr(dev)), "isc_convert_features")
         return out
 
-    def _check_inference(self, what):
-        if self.training:
-            raise NotImplementedError(
-                "%s in training mode (dropout / scheduled sampling / autograd) is not built yet; "
-                "call .eval() — the B200 path currently covers inference-mode decoding only" % what)
+    # ------------------------------------------------------------------ training plumbing
+    def _dropout_masks(self, shapes, n_steps, B):
+        """uint8 keep masks for the tensors nn.Dropout touches in the reference (captioner.py:182, :200-214,
+        :250-262, :296-315). RNG is torch's (plumbing); tests inject masks through ``self.dropout_override``."""
+        p = float(self.settings["dropout_p"])
+        if self.dropout_override is not None:
+            return self.dropout_override
+        if not self.training or p <= 0.0:
+            return None
+        dev = self._device()
+        masks = {k: (torch.rand(sh, device=dev) >= p).to(torch.uint8) for k, sh in shapes.items()}
+        masks["out"] = (torch.rand(n_steps, B, 512, device=dev) >= p).to(torch.uint8)
+        masks["scale"] = 1.0 / (1.0 - p)
+        return masks
+
+    def _dropout_struct(self, masks):
+        d = _lib.Dropout()
+        if masks:
+            for k in ("fc", "att", "sw", "sl", "out"):
+                t = masks.get(k)
+                setattr(d, k, t.data_ptr() if t is not None else None)
+            d.scale = float(masks.get("scale", 1.0))
+        else:
+            d.scale = 1.0
+        return d
+
+    def _params_in_field_order(self):
+        sd = dict(self.named_parameters())
+        return [sd[name] for _, name in _lib.WEIGHT_FIELDS]
+
+    def _teacher_forced_train(self, mode, fc, att, cpt, sw, labels, inputs, ss_prob):
+        """Differentiable teacher forcing (autograd.Function over the C ABI)."""
+        if self._prec != _lib.PREC_BF16X3:
+            raise NotImplementedError("the backward pass runs in precision='bf16x3' only")
+        if ss_prob and ss_prob > 0.0 and self.training:
+            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not built yet")
+        dev = self._device()
+        B = inputs.shape[0]
+        n_steps = inputs.shape[1] - 1
+        L = att.shape[1] if att is not None else self.n_regions
+        S = (sw.shape[1] + 1) if sw is not None else (self.num_senti_words + 1)
+        shapes = {"fc": (B, 512), "sl": (B, 512)}
+        if att is not None:
+            shapes["att"] = (B, L, 512)
+        if sw is not None:
+            shapes["sw"] = (B, S, 512)
+        call = dict(fc=fc, att=att, cpt=cpt, sw=sw, labels=labels, inputs=inputs.long().contiguous(), n_regions=L, n_senti=S,
+                    dropout=self._dropout_masks(shapes, n_steps, B))
+        out, fc_emb, cpt_feats = _TeacherForced.apply(self, mode, call, *self._params_in_field_order())
+        self.cont_weights = self.senti_weights = self.cont_senti_weights = []
+        return out, fc_emb, (cpt_feats if cpt is not None else None), call
 
     def prologue(self, fc_feats=None, att_feats=None, cpt_words=None, senti_words=None, senti_labels=None,
-                 seq2seq=False):
-        """Step-invariant features (isc_prologue). Returns (dict of tensors, B)."""
+                 seq2seq=False, dropout=None):
+        """Step-invariant features (isc_prologue). Returns (dict of tensors, B). ``dropout`` is the keep-mask
+        dict of ``_dropout_masks`` (training-mode sampling pass) or None."""
         dev = self._device()
         lib = _lib.load()
         packed = self.pack_weights()
@@ -237,7 +350,8 @@ class Captioner(nn.Module):
                 _lib.ptr(fc_feats) if not seq2seq else None, _lib.ptr(att_feats) if not seq2seq else None,
                 _lib.ptr(cpt_words), cpt_words.shape[1] if cpt_words is not None else 0,
                 _lib.ptr(senti_words), _lib.ptr(senti_labels), B, 1 if seq2seq else 0, C.byref(feats),
-                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_prologue")
+                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
+                C.byref(self._dropout_struct(dropout)) if dropout else None), "isc_prologue")
         t["_dims"] = d
         return t, B
 
@@ -315,16 +429,38 @@ class Captioner(nn.Module):
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
         return out
 
+    def _needs_grad(self):
+        """True when the call has to build autograd history: train() mode, or eval() with gradients enabled like
+        the reference's modules — the latter only in bf16x3, the precision the backward pass exists in
+        (other precisions then return plain tensors; use torch.no_grad() for inference either way)."""
+        if self.training:
+            return True
+        return (self._prec == _lib.PREC_BF16X3 and torch.is_grad_enabled()
+                and any(p.requires_grad for p in self.parameters()))
+
     def forward_xe(self, fc_feats, att_feats, cpt_words, captions, senti_labels, ss_prob=0.0):
-        """Teacher-forced log-probs [bs, T-1, V] (captioner.py:194-240), inference semantics."""
-        self._check_inference("forward_xe")
+        """Teacher-forced log-probs [bs, T-1, V] (captioner.py:194-240). With gradients enabled (or in train()
+        mode) the result carries autograd history through the hand-written backward (isc_train_backward)."""
+        if self._needs_grad():
+            B = fc_feats.shape[0]
+            fc = fc_feats.reshape(B, -1).float().contiguous()
+            att = att_feats.reshape(B, -1, att_feats.shape[-1]).float().contiguous()
+            out, self.fc_feats, self.cpt_feats, _ = self._teacher_forced_train(
+                _lib.MODE_XE, fc, att, cpt_words.long().contiguous(), None, senti_labels.reshape(B).long().contiguous(),
+                captions, ss_prob)
+            return out
         t, B = self.prologue(fc_feats, att_feats, cpt_words, None, senti_labels)
         self.fc_feats, self.cpt_feats = t["fc"], t.get("cpt_feats")
         return self._teacher_forced(t, B, captions)
 
     def forward_seq2seq(self, senti_captions, cpt_words, senti_words, senti_labels, ss_prob=0.0):
-        """Sentiment-corpus teacher forcing (captioner.py:242-288), inference semantics."""
-        self._check_inference("forward_seq2seq")
+        """Sentiment-corpus teacher forcing (captioner.py:242-288)."""
+        if self._needs_grad():
+            B = senti_captions.shape[0]
+            out, _, _, _ = self._teacher_forced_train(
+                _lib.MODE_SEQ2SEQ, None, None, cpt_words.long().contiguous(), senti_words.reshape(B, -1).long().contiguous(),
+                senti_labels.reshape(B).long().contiguous(), senti_captions, ss_prob)
+            return out
         t, B = self.prologue(None, None, cpt_words, senti_words, senti_labels, seq2seq=True)
         return self._teacher_forced(t, B, senti_captions)
 
@@ -335,17 +471,22 @@ class Captioner(nn.Module):
         Sampling is Gumbel-max: argmax(logprobs + g). ``noise`` [T,B,V] supplies g explicitly (parity
         tests); otherwise g comes from a counter-based generator keyed by ``seed`` (drawn from torch's
         global generator when None, so torch.manual_seed makes it reproducible)."""
-        self._check_inference("forward_rl")
         dev = self._device()
         lib = _lib.load()
-        t, B = self.prologue(fc_feats, att_feats, cpt_words, senti_words, senti_labels)
+        with_grad = self._needs_grad() and torch.is_grad_enabled() and not sample_max
+        masks = None
+        if with_grad or (self.training and float(self.settings["dropout_p"]) > 0.0) or self.dropout_override is not None:
+            B0, L0 = fc_feats.shape[0], att_feats.reshape(fc_feats.shape[0], -1, att_feats.shape[-1]).shape[1]
+            masks = self._dropout_masks({"fc": (B0, 512), "sl": (B0, 512), "att": (B0, L0, 512),
+                                         "sw": (B0, senti_words.reshape(B0, -1).shape[1] + 1, 512)}, int(max_seq_len), B0)
+        t, B = self.prologue(fc_feats, att_feats, cpt_words, senti_words, senti_labels, dropout=masks)
         self.fc_feats, self.cpt_feats = t["fc"], t.get("cpt_feats")
         d = t["_dims"]
         T = int(max_seq_len)
         f32 = dict(dtype=torch.float32, device=dev)
         seq = torch.empty(B, T, dtype=torch.long, device=dev)
         lps = torch.empty(B, T, **f32)
-        masks = torch.empty(B, T, **f32)
+        seq_masks = torch.empty(B, T, **f32)
         L, S = d.n_regions, d.n_senti
         cw = sw = gw = None
         if self.collect_attention_weights:
@@ -367,17 +508,35 @@ class Captioner(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.isc_decode_greedy(
                 C.byref(d), _lib.ptr(self._packed), self._prec, C.byref(feats), B, T, mode, _lib.ptr(noise),
-                int(seed or 0), _lib.ptr(seq), _lib.ptr(lps), _lib.ptr(masks), _lib.ptr(cw), _lib.ptr(sw),
-                _lib.ptr(gw), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_decode_greedy")
+                int(seed or 0), _lib.ptr(seq), _lib.ptr(lps), _lib.ptr(seq_masks), _lib.ptr(cw), _lib.ptr(sw),
+                _lib.ptr(gw), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
+                _lib.ptr(masks["out"]) if masks and masks.get("out") is not None else None,
+                float(masks["scale"]) if masks else 1.0), "isc_decode_greedy")
+        masks_t = seq_masks
         if self.collect_attention_weights:
             # the reference's lists hold one entry per EXECUTED step (it breaks when every row is done)
-            steps = int(masks.sum(0).gt(0).sum().item())
+            steps = int(seq_masks.sum(0).gt(0).sum().item())
             self.cont_weights = cw[:, :steps].reshape(B, steps * L)
             self.senti_weights = sw[:, :steps].reshape(B, steps * S)
             self.cont_senti_weights = gw[:, :steps]
         else:
             self.cont_weights = self.senti_weights = self.cont_senti_weights = []
-        return seq, lps, masks
+        if with_grad:
+            # REINFORCE (models/decoder.py:86-88 runs this pass under autograd): re-score the sampled tokens teacher-forced
+            # with the same dropout masks — the same computation, now with the tape the backward needs
+            sos = torch.full((B, 1), self.sos_id, dtype=torch.long, device=dev)
+            inputs = torch.cat([sos, seq], dim=1)  # feeds [SOS, seq[:, :-1]]
+            saved, self.dropout_override = self.dropout_override, masks
+            try:
+                out, self.fc_feats, self.cpt_feats, _ = self._teacher_forced_train(
+                    _lib.MODE_RL, fc_feats.reshape(B, -1).float().contiguous(),
+                    att_feats.reshape(B, -1, att_feats.shape[-1]).float().contiguous(), cpt_words.long().contiguous(),
+                    senti_words.reshape(B, -1).long().contiguous(), senti_labels.reshape(B).long().contiguous(), inputs, 0.0)
+            finally:
+                self.dropout_override = saved
+            executed = seq_masks.sum(0, keepdim=True).gt(0).to(out.dtype)  # steps after the whole-batch stop never ran
+            lps = out.gather(2, seq.unsqueeze(2)).squeeze(2) * executed
+        return seq, lps, masks_t
 
     def beam_search(self, fc_feats, att_feats, senti_words=None, senti_labels=None, beam_size=3,
                     decoding_constraint=1, max_seq_len=16, host_chunk=256):

@@ -63,7 +63,8 @@ struct AttnParams {
 int launch_embed_pack(const long long* it, const int* parent, const float* h_in, int M, int V, const float* emb,
                       RowDest x1, RowDest x2, cudaStream_t stream);
 int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_prev, float* h_out, float* c_out,
-                          RowDest extra, int extra_col, int M, cudaStream_t stream);
+                          RowDest extra, int extra_col, int M, cudaStream_t stream, const unsigned char* mask = nullptr,
+                          float scale = 1.0f);
 int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode, cudaStream_t stream);
 int launch_gate_mix(const float* g3, const float* cs, const float* alpha, const float* alpha_b, RowDest ctx,
                     float* gate_w, long long ld_gate_w, int M, cudaStream_t stream);
@@ -130,5 +131,49 @@ int launch_greedy_init(long long* it, int* unfinished, int B, int sos_id, cudaSt
 // weights outputs must read as zero after the whole-batch early stop
 int launch_zero_if_stopped(float* p, long long row_stride, int row_len, int B, const int* alive_count, int t,
                            cudaStream_t stream);
+
+// ---- training / backward (train.cu) ---------------------------------------------------------------------
+struct AttnBwdParams {
+  int L = 0, S = 0;
+  const float* dcs = nullptr; long long ld_dcs = 0; int cont_col = 0, senti_col = 0;
+  const float* hproj = nullptr; long long ld_hproj = 0;
+  const float* pre_word = nullptr;
+  const float* att = nullptr; const float* ea_att = nullptr;
+  const float* sw = nullptr; const float* ea_sw = nullptr;
+  const float* cont_w = nullptr; const float* senti_w = nullptr;
+  const float* alpha_c = nullptr; const float* alpha_s = nullptr;
+  float* datt = nullptr; float* dp_att = nullptr; float* dsw = nullptr; float* dp_sw = nullptr;
+  RowDest dhproj;
+  float* dpre_word = nullptr;
+  float* dalpha_c = nullptr; float* dalpha_s = nullptr;
+};
+int launch_logsoftmax_bwd(const float* logp, long long ld_logp, const float* dlogp, long long ld_dlogp, const long long* target,
+                          long long ld_target, const float* coef, long long ld_coef, int M, int V, float* dlogits,
+                          long long ld_out, cudaStream_t s);
+int launch_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh_a, long long ld_a,
+                    const unsigned char* mask, float scale, const float* dh_b, long long ld_b, const float* dh_c,
+                    long long ld_c, float* dc_carry, float* dgates, RowDest planes, int M, cudaStream_t s);
+int launch_gate_bwd(const float* dctx, long long ld_dctx, const float* cs, const float* g3, const float* gate_w,
+                    const float* alpha, float* dcs, RowDest dpre3, int dpre3_col, float* dalpha, float* dalpha_b, int M,
+                    cudaStream_t s);
+int launch_attention_bwd(const AttnBwdParams& a, int M, cudaStream_t s);
+int launch_embed_bwd(const long long* ids, long long ld_ids, long long groups, long long ids_per_group, int prepend_pad,
+                     int pad_id, int skip_pad, int V, const float* emb, const float* g, long long ld_g,
+                     long long g_rows_per_group, const unsigned char* mask, float scale, float gscale, float* demb,
+                     cudaStream_t s);
+int launch_relu_mask_bwd(const float* a, long long ld_a, const float* b, long long ld_b, const float* gate, long long ld_gate,
+                         int gate_is_exp, const unsigned char* mask, long long ld_mask, float scale, long long rows, int cols,
+                         float* out, long long ld_out, RowDest planes, cudaStream_t s);
+int launch_apply_mask(float* x, long long ld, const unsigned char* mask, float scale, long long rows, int cols, RowDest planes,
+                      cudaStream_t s);
+int launch_colsum_add(const float* src, long long ld, long long rows, int cols, float* dst, float* dst2, cudaStream_t s);
+int launch_sum_steps(const float* src, int T, long long stride_t, long long n, float* dst, cudaStream_t s);
+int launch_add2d(float* dst, long long ld_dst, const float* src, long long ld_src, long long rows, int cols, cudaStream_t s);
+int launch_split_transpose(const float* src, long long ld_src, long long rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo,
+                           long long ld_dst, long long col0, cudaStream_t s);
+int launch_transpose_bf16(const __nv_bfloat16* src, long long ld_src, long long rows, int cols, __nv_bfloat16* dst,
+                          long long ld_dst, long long col0, cudaStream_t s);
+int launch_adam_clamp(float* p, const float* g, float* m, float* v, long long n, float clip, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float grad_scale, cudaStream_t s);
 
 }  // namespace isc

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(128) embed_pack_kernel(const long long* __rest
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) lstm_pointwise_kernel(const float* __restrict__ gates, const int* __restrict__ parent,
                                                              const float* __restrict__ c_prev, float* __restrict__ h_out,
-                                                             float* __restrict__ c_out, RowDest extra, int extra_col) {
+                                                             float* __restrict__ c_out, RowDest extra, int extra_col,
+                                                             const unsigned char* __restrict__ mask, float scale) {
   const int m = blockIdx.x;
   const int src = parent ? parent[m] : m;
   const int c = threadIdx.x * 4;
@@ -54,6 +55,10 @@ __global__ void __launch_bounds__(128) lstm_pointwise_kernel(const float* __rest
 #undef ISC_LSTM
   *reinterpret_cast<float4*>(c_out + (long long)m * H + c) = cn;
   *reinterpret_cast<float4*>(h_out + (long long)m * H + c) = hn;
+  if (mask) {  // dropout on the copy that feeds the next GEMM (captioner.py:182); the recurrent state stays intact
+    const uchar4 k = *reinterpret_cast<const uchar4*>(mask + (long long)m * H + c);
+    hn.x *= k.x ? scale : 0.f; hn.y *= k.y ? scale : 0.f; hn.z *= k.z ? scale : 0.f; hn.w *= k.w ? scale : 0.f;
+  }
   extra.store4(m, extra_col + c, hn);
 }
 
@@ -437,9 +442,9 @@ int launch_embed_pack(const long long* it, const int* parent, const float* h_in,
   return 0;
 }
 int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_prev, float* h_out, float* c_out,
-                          RowDest extra, int extra_col, int M, cudaStream_t stream) {
+                          RowDest extra, int extra_col, int M, cudaStream_t stream, const unsigned char* mask, float scale) {
   ProfScope ps(ISC_K_LSTM, (double)M * H * 4.0 * 8, stream);  // 4H gates + c in, h + c + h-copy out
-  lstm_pointwise_kernel<<<M, 128, 0, stream>>>(gates, parent, c_prev, h_out, c_out, extra, extra_col);
+  lstm_pointwise_kernel<<<M, 128, 0, stream>>>(gates, parent, c_prev, h_out, c_out, extra, extra_col, mask, scale);
   ISC_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,186 @@
+"""GPU parity of the training path: gradients of the hand-written backward (isc_train_backward, through the
+autograd.Function behind Captioner.forward_xe / forward_seq2seq / forward_rl) against torch autograd through the
+CPU oracle (a restatement of the reference's forward, pinned to reference-generated goldens). Same seeded
+weights and inputs; dropout either off (eval, like the reference's modules with gradients enabled) or with the
+SAME injected keep masks on both sides. Tolerance: 2e-3 of the tensor's largest gradient magnitude (bf16x3
+GEMMs are ~1e-5 relative; the atomics in the embedding / alpha reductions reorder fp32 sums)."""
+import numpy as np
+import pytest
+import torch
+
+from insenticap_model_b200 import _lib
+from insenticap_model_b200 import synthetic as syn
+from insenticap_model_b200.captioner import Captioner, XECriterion
+from oracle import captioner_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+V, B, T1 = 200, 6, 7  # captions have T1 tokens -> T1 - 1 decode steps
+
+
+def _model(seed=3):
+    m = Captioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS), precision="bf16x3")
+    sd = syn.synthetic_state_dict(V, seed)
+    m.load_state_dict(sd)
+    return m.cuda(), sd
+
+
+def _inputs(seed=11):
+    g = torch.Generator().manual_seed(seed)
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=seed)
+    caps = torch.randint(4, V, (B, T1), generator=g)
+    caps[:, 0] = 1
+    lengths = [T1 - 1, T1 - 1, T1 - 2, T1 - 3, 3, 2][:B]
+    for b, n in enumerate(lengths):  # EOS then PAD after the caption, like the dataloader's padding
+        caps[b, n] = 2
+        caps[b, n + 1:] = 0
+    return fc, att, cpts, sentis, labels, caps, lengths
+
+
+def _masks(mode, n_steps, p=0.5, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    keep = lambda *s: (torch.rand(*s, generator=g) >= p).to(torch.uint8)
+    m = {"fc": keep(B, 512), "sl": keep(B, 512), "out": keep(n_steps, B, 512), "scale": 1.0 / (1.0 - p)}
+    if mode != "seq2seq":
+        m["att"] = keep(B, 196, 512)
+    if mode != "xe":
+        m["sw"] = keep(B, 11, 512)
+    return m
+
+
+def _xe_loss(pred, target, lengths):
+    return XECriterion()(pred, target, lengths)
+
+
+def _oracle_grads(sd, loss_fn):
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss = loss_fn(p)
+    loss.backward()
+    return float(loss), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
+
+
+# ReLU-boundary noise: the prologue evaluates ~600k ReLU pre-activations (B*196*512 region units, B*11*512 sentiment-
+# word units); a handful sit within the GEMM rounding error (~1e-6) of zero, so the GPU and the CPU oracle switch
+# those units differently — exactly as fp32 CPU and fp32 CUDA runs of the reference would (verified with
+# tests/gpu_train_diag.py: every outlier row maps to a unit with |pre-activation| < 1e-5). One flipped unit moves
+# one row of the layer's weight gradient and what is upstream of it. For the tensors this can reach, the check is:
+# no error above 20 % of the tensor's largest gradient, and at most 1 % of the entries off by more than 1 %.
+RELU_BOUNDARY = ("att_embed.0.weight", "att_embed.0.bias", "att2att.0.weight", "att2att.0.bias", "senti2att.0.weight",
+                 "senti2att.0.bias", "word_embed.0.weight")
+
+
+def _compare(model, ref_grads, skip=()):
+    worst = []
+    for name, prm in model.named_parameters():
+        if name in skip:
+            continue
+        got = prm.grad.detach().cpu() if prm.grad is not None else torch.zeros_like(ref_grads[name])
+        ref = ref_grads[name]
+        scale = float(ref.abs().max())
+        diff = (got - ref).abs()
+        err = float(diff.max())
+        worst.append((err / (scale + 1e-12), name, err, scale))
+        if name in RELU_BOUNDARY:
+            assert err <= 0.2 * scale + 2e-7, "grad mismatch %s: max err %.3e, ref max %.3e" % (name, err, scale)
+            frac = float((diff > 1e-2 * scale + 2e-7).float().mean())
+            assert frac <= 0.01, "grad mismatch %s: %.2f %% of the entries are off by > 1 %%" % (name, 100 * frac)
+        else:
+            assert err <= 2e-3 * scale + 2e-7, "grad mismatch %s: max err %.3e, ref max %.3e" % (name, err, scale)
+    return max(worst)
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_xe_backward_matches_oracle_autograd(dropout):
+    m, sd = _model()
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    masks = _masks("xe", T1 - 1) if dropout else None
+    m.train(dropout)
+    m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()} if masks else None
+    m.zero_grad()
+    pred = m(fc.cuda(), att.cuda(), cpts.cuda(), caps.cuda(), labels.cuda(), 0.0, mode="xe")
+    loss = _xe_loss(pred, caps[:, 1:].cuda(), lengths) + torch.nn.functional.mse_loss(m.cpt_feats, m.fc_feats.detach())
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def ref_loss(p):
+        f = O.prologue(p, fc, att, cpts, None, labels, masks=masks)
+        lp = O.teacher_forced(p, f, caps, masks=masks)
+        return _xe_loss(lp, caps[:, 1:], lengths) + torch.nn.functional.mse_loss(f["cpt_feats"], f["fc_embedded"].detach())
+
+    ref, grads = _oracle_grads(sd, ref_loss)
+    assert abs(float(loss) - ref) <= 1e-4 * abs(ref), (float(loss), ref)
+    # xe mode leaves the sentiment attention and the gate without gradient: both sides give zeros there
+    _compare(m, grads)
+
+
+def test_seq2seq_backward_matches_oracle_autograd():
+    m, sd = _model()
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    masks = _masks("seq2seq", T1 - 1)
+    m.train(True)
+    m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()}
+    m.zero_grad()
+    pred = m(caps.cuda(), cpts.cuda(), sentis.cuda(), labels.cuda(), 0.0, mode="seq2seq")
+    loss = _xe_loss(pred, caps[:, 1:].cuda(), lengths)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def ref_loss(p):
+        f = O.prologue(p, None, None, cpts, sentis, labels, seq2seq=True, masks=masks)
+        return _xe_loss(O.teacher_forced(p, f, caps, masks=masks), caps[:, 1:], lengths)
+
+    ref, grads = _oracle_grads(sd, ref_loss)
+    assert abs(float(loss) - ref) <= 1e-4 * abs(ref)
+    _compare(m, grads)
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_rl_reinforce_backward_matches_oracle_autograd(dropout):
+    """forward_rl(sample_max=0) under autograd: sampled tokens (Gumbel noise injected), REINFORCE loss with fixed
+    rewards (RewardCriterion, self_critical/utils.py:169-177) + the domain-alignment MSE."""
+    m, sd = _model()
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    T = 6
+    masks = _masks("rl", T) if dropout else None
+    m.train(dropout)
+    m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()} if masks else None
+    m.zero_grad()
+    g = torch.Generator().manual_seed(9)
+    noise = -torch.log(-torch.log(torch.rand(T, B, V, generator=g).clamp_min(1e-9)))
+    rewards = torch.randn(B, T, generator=g)
+    seq, lps, smask = m(fc.cuda(), att.cuda(), cpts.cuda(), sentis.cuda(), labels.cuda(), T, 0, mode="rl", noise=noise)
+    loss = -(lps * smask * rewards.cuda()).sum() / smask.sum() + torch.nn.functional.mse_loss(m.cpt_feats, m.fc_feats.detach())
+    loss.backward()
+    torch.cuda.synchronize()
+    seq_c, smask_c = seq.cpu(), smask.cpu()
+
+    def ref_loss(p):
+        f = O.prologue(p, fc, att, cpts, sentis, labels, masks=masks)
+        inputs = torch.cat([torch.full((B, 1), 1, dtype=torch.long), seq_c], dim=1)
+        lp = O.teacher_forced(p, f, inputs, masks=masks)
+        executed = smask_c.sum(0, keepdim=True).gt(0).float()
+        chosen = lp.gather(2, seq_c.unsqueeze(2)).squeeze(2) * executed
+        return -(chosen * smask_c * rewards).sum() / smask_c.sum() + \
+            torch.nn.functional.mse_loss(f["cpt_feats"], f["fc_embedded"].detach())
+
+    ref, grads = _oracle_grads(sd, ref_loss)
+    assert abs(float(loss) - ref) <= 1e-4 * max(abs(ref), 1e-3), (float(loss), ref)
+    _compare(m, grads)
+
+
+def test_fused_clamp_adam_matches_torch():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * 0.3 for _ in range(3)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=4e-4, weight_decay=1e-5)
+    p, ma, va = p0.clone().cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    for step, gr in enumerate(grads, 1):
+        ref.grad = gr.clone().clamp_(-0.1, 0.1)  # train_xe.py:19-23 clip_gradient
+        opt.step()
+        _lib.check(lib.isc_adam_step(_lib.ptr(p), _lib.ptr(gr.cuda()), _lib.ptr(ma), _lib.ptr(va), n, 0.1, 4e-4, 0.9, 0.999, 1e-8,
+                                     1e-5, step, 1.0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
