@@ -1,0 +1,163 @@
+"""Data-parallel training of the captioner on the B200 path: the inner loops of the reference's
+train_xe.py:144-196 (XE epoch body) and models/decoder.py:52-176 (`Detector.forward`, the SCST iteration), with
+  * forward/backward through libisc_b200.so (Captioner.forward_xe / forward_seq2seq / forward_rl under autograd),
+  * the CIDEr-D reward computed on the device (reward.py) — sampled ids, greedy ids, rewards and the REINFORCE
+    loss never leave HBM (the reference round-trips through numpy, self_critical/utils.py:59-60, decoder.py:103),
+  * ONE collective per iteration: a summing all-reduce of the flat fp32 gradient (22.06 M elements at V = 10 000)
+    over torch.distributed (NCCL over NVLink on a B200 box, gloo in the CPU tests), then the reference's element-wise
+    clamp to +-grad_clip (train_xe.py:19-23) and Adam fused in one kernel over the flat buffers (isc_adam_step).
+The reference is single-device: data parallelism is new; images shard by rank with
+no other communication. Losses are per-batch means, so ranks must hold equal batch sizes for the average of
+gradients to equal the single-large-batch gradient.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib
+from .captioner import XECriterion
+from .reward import RewardCriterion, get_self_critical_reward
+
+
+def flatten_parameters(module: nn.Module):
+    """Re-home every parameter (and a matching .grad) as a view into one flat fp32 buffer each, in
+    named_parameters() order. Returns (flat_params, flat_grads). Works on any device."""
+    params = [p for _, p in module.named_parameters()]
+    n = sum(p.numel() for p in params)
+    dev = params[0].device
+    flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+    flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        k = p.numel()
+        flat_p[off:off + k].copy_(p.data.reshape(-1))
+        p.data = flat_p[off:off + k].view_as(p)
+        p.grad = flat_g[off:off + k].view_as(p)
+        off += k
+    return flat_p, flat_g
+
+
+def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> int:
+    """The path's one exchange step: sum the flat gradient over the ranks. Returns the world size (1 without an
+    initialised process group); the division by it is folded into the optimizer kernel (grad_scale)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return world
+
+
+class FusedClampAdam:
+    """clip_gradient(optimizer, grad_clip) + torch.optim.Adam.step() (train_xe.py:19-23, :191-192;
+    models/decoder.py:168-170) as one kernel over the flat parameter / gradient / moment buffers."""
+
+    def __init__(self, model, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, grad_clip=0.1, group=None):
+        self.model = model
+        self.lr, self.weight_decay, self.betas, self.eps, self.grad_clip = lr, weight_decay, betas, eps, grad_clip
+        self.group = group
+        self.flat_p, self.flat_g = flatten_parameters(model)
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.steps = 0
+        model._packed_key = None
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def _gather_grads(self):
+        """autograd accumulates into p.grad in place when it exists, so the views stay attached; parameters
+        that got no gradient keep their zeros."""
+        off = 0
+        for p in self.model.parameters():
+            k = p.numel()
+            if p.grad is None:
+                p.grad = self.flat_g[off:off + k].view_as(p)
+            elif p.grad.data_ptr() != self.flat_g[off:off + k].data_ptr():
+                self.flat_g[off:off + k].copy_(p.grad.reshape(-1))
+                p.grad = self.flat_g[off:off + k].view_as(p)
+            off += k
+
+    def step(self):
+        if not self.flat_p.is_cuda:
+            raise RuntimeError("FusedClampAdam.step runs on the GPU only (isc_adam_step); there is no CPU fallback")
+        self._gather_grads()
+        world = allreduce_gradients(self.flat_g, self.group)
+        self.steps += 1
+        lib = _lib.load()
+        with torch.cuda.device(self.flat_p.device):
+            _lib.check(lib.isc_adam_step(_lib.ptr(self.flat_p), _lib.ptr(self.flat_g), _lib.ptr(self.exp_avg),
+                                         _lib.ptr(self.exp_avg_sq), self.flat_p.numel(), float(self.grad_clip), float(self.lr),
+                                         float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+                                         self.steps, 1.0 / world, _lib.stream_ptr(self.flat_p.device)), "isc_adam_step")
+        self.model._packed_key = None  # parameters changed behind torch's version counters: repack on next use
+
+
+def xe_iteration(model, optim, batch, seq2seq_batch=None, ss_prob=0.0):
+    """One iteration of train_xe.py:150-192 on device tensors.
+    batch = (fc_feats, att_feats, captions, lengths, cpt_words, senti_labels); seq2seq_batch =
+    (captions, lengths, cpt_words, senti_words, senti_labels) or None. Returns the loss values (device scalars)."""
+    xe_crit, da_crit = XECriterion(), nn.MSELoss()
+    fc, att, caps, lengths, cpts, labels = batch
+    optim.zero_grad()
+    pred = model(fc, att, cpts, caps, labels, ss_prob, mode="xe")
+    xe_loss = xe_crit(pred, caps[:, 1:], lengths)
+    da_loss = da_crit(model.cpt_feats, model.fc_feats.detach())
+    all_loss = xe_loss + da_loss
+    out = {"xe_loss": xe_loss.detach(), "da_loss": da_loss.detach()}
+    if seq2seq_batch is not None:
+        s_caps, s_lengths, s_cpts, s_sentis, s_labels = seq2seq_batch
+        pred2 = model(s_caps, s_cpts, s_sentis, s_labels, ss_prob, mode="seq2seq")
+        s2s = xe_crit(pred2, s_caps[:, 1:], s_lengths)
+        all_loss = all_loss + s2s
+        out["seq2seq_loss"] = s2s.detach()
+    all_loss.backward()
+    optim.step()
+    out["all_loss"] = all_loss.detach()
+    return out
+
+
+def rl_iteration(model, optim, scorer, batch, max_seq_len=16, seq2seq_batch=None, samples_per_image=1, xe_ss_prob=0.0,
+                 seq_flag=1.0, extra_reward=None):
+    """One 'fact' iteration of Detector.forward (models/decoder.py:62-170) with the sentiment labels given (the
+    detector that predicts them is out of scope) and the classifier reward supplied by
+    ``extra_reward(sample, greedy) -> [B,T] tensor`` or omitted.
+    batch = (fns, fc_feats, att_feats, captions, lengths, cpt_words, senti_words, senti_labels, ground_truth).
+    ``samples_per_image`` tiles the batch (BASELINE cfg4: 5 samples per image; the reference draws 1)."""
+    fns, fc, att, caps, lengths, cpts, sentis, labels, ground_truth = batch
+    rl_crit, xe_crit, da_crit = RewardCriterion(), XECriterion(), nn.MSELoss()
+    optim.zero_grad()
+    R = int(samples_per_image)
+    rep = (lambda x: x.repeat_interleave(R, dim=0)) if R > 1 else (lambda x: x)
+    s_fns = [fn for fn in fns for _ in range(R)]
+    sample, sample_lp, seq_masks = model(rep(fc), rep(att), rep(cpts), rep(sentis), rep(labels), max_seq_len, 0, mode="rl")
+    da_loss = da_crit(model.cpt_feats, model.fc_feats.detach())
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        greedy, _, _ = model(fc, att, cpts, sentis, labels, max_seq_len, 1, mode="rl")
+    model.train(was_training)
+    rewards = get_self_critical_reward(sample, rep(greedy), s_fns, ground_truth, model.sos_id, model.eos_id, scorer,
+                                       as_tensor=True).float()
+    if extra_reward is not None:
+        rewards = rewards + extra_reward(sample, rep(greedy))
+    cap_loss = rl_crit(sample_lp, seq_masks, rewards)
+    out = {"fact_reward": rewards[:, 0].mean().detach(), "cap_loss": cap_loss.detach(), "da_loss": da_loss.detach()}
+    total = cap_loss + da_loss
+    if caps is not None:
+        pred = model(fc, att, cpts, caps, labels, xe_ss_prob, mode="xe")
+        xe_loss = xe_crit(pred, caps[:, 1:], lengths)
+        total = total + xe_loss
+        out["xe_loss"] = xe_loss.detach()
+    if seq2seq_batch is not None:
+        s_caps, s_lengths, s_cpts, s_sentis, s_labels = seq2seq_batch
+        pred2 = model(s_caps, s_cpts, s_sentis, s_labels, 0.0, mode="seq2seq")
+        s2s = seq_flag * xe_crit(pred2, s_caps[:, 1:], s_lengths)
+        total = total + s2s
+        out["seq2seq_loss"] = s2s.detach()
+    total.backward()
+    optim.step()
+    out["all_loss"] = total.detach()
+    return out

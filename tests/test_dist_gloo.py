@@ -63,3 +63,49 @@ def test_sharded_decode_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, True, (n, 4)), (1, True, (n, 4))]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Training exchange step: the flat-gradient all-reduce of insenticap_model_b200.train (world 2, gloo). The
+# clamp + Adam kernel that follows is CUDA-only; here a tiny linear model checks that the averaged flat gradient
+# equals the gradient of the single large batch (equal per-rank batch sizes, mean losses).
+def _train_worker(rank, world, port, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from insenticap_model_b200 import train as TR
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    ref.load_state_dict(net.state_dict())
+    flat_p, flat_g = TR.flatten_parameters(net)
+    ok = all(p.data_ptr() >= flat_p.data_ptr() for p in net.parameters())  # parameters are views of the flat buffer
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(8, 5, generator=g), torch.randn(8, 3, generator=g)
+    a, b = D.shard_range(8, rank, world)
+    torch.nn.functional.mse_loss(net(x[a:b]), y[a:b]).backward()
+    ok &= all(p.grad.data_ptr() >= flat_g.data_ptr() and p.grad.data_ptr() < flat_g.data_ptr() + flat_g.numel() * 4
+              for p in net.parameters())  # autograd accumulated in place into the flat gradient views
+    w = TR.allreduce_gradients(flat_g)
+    torch.nn.functional.mse_loss(ref(x), y).backward()
+    want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
+    ok &= w == world and torch.allclose(flat_g / w, want, atol=1e-6)
+    out_q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_world2_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

@@ -184,3 +184,81 @@ def test_fused_clamp_adam_matches_torch():
                                      1e-5, step, 1.0, _lib.stream_ptr()))
     torch.cuda.synchronize()
     np.testing.assert_allclose(p.cpu().numpy(), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_xe_iteration_updates_parameters_like_clip_plus_adam():
+    """train_xe.py:160-192 in one call: xe + domain-alignment + seq2seq losses, backward, clamp(0.1), Adam. The
+    losses match the oracle; the parameter update equals torch's clamp + Adam applied to the produced gradients
+    (flat views, fused kernel, repack of the kernel weights after the step); a second iteration lowers the loss."""
+    from insenticap_model_b200 import train as TR
+    m, sd = _model()
+    m.eval()  # dropout off: comparable with the oracle
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    optim = TR.FusedClampAdam(m, lr=4e-4, weight_decay=0.0, grad_clip=0.1)
+    before = {k: v.detach().clone() for k, v in m.named_parameters()}
+    batch = (fc.cuda(), att.cuda(), caps.cuda(), lengths, cpts.cuda(), labels.cuda())
+    s2s = (caps.cuda(), lengths, cpts.cuda(), sentis.cuda(), labels.cuda())
+    out = TR.xe_iteration(m, optim, batch, s2s)
+    torch.cuda.synchronize()
+
+    with torch.no_grad():
+        f = O.prologue(sd, fc, att, cpts, None, labels)
+        xe = _xe_loss(O.teacher_forced(sd, f, caps), caps[:, 1:], lengths)
+        da = torch.nn.functional.mse_loss(f["cpt_feats"], f["fc_embedded"])
+        f2 = O.prologue(sd, None, None, cpts, sentis, labels, seq2seq=True)
+        s2 = _xe_loss(O.teacher_forced(sd, f2, caps), caps[:, 1:], lengths)
+    assert abs(float(out["xe_loss"]) - float(xe)) < 1e-4 * float(xe)
+    assert abs(float(out["da_loss"]) - float(da)) < 1e-4 * float(da) + 1e-7
+    assert abs(float(out["seq2seq_loss"]) - float(s2)) < 1e-4 * float(s2)
+
+    shadow = {k: torch.nn.Parameter(v.cpu().clone()) for k, v in before.items()}
+    opt = torch.optim.Adam(list(shadow.values()), lr=4e-4)
+    for k, p in m.named_parameters():
+        shadow[k].grad = p.grad.detach().cpu().clone().clamp_(-0.1, 0.1)
+    opt.step()
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.detach().cpu().numpy(), shadow[k].detach().numpy(), rtol=0, atol=2e-7, err_msg=k)
+    out2 = TR.xe_iteration(m, optim, batch, s2s)
+    assert float(out2["all_loss"]) < float(out["all_loss"])
+
+
+def test_rl_iteration_device_reward_and_update():
+    """Detector.forward 'fact' iteration (models/decoder.py:62-170) with the labels given: sampled + greedy decode,
+    CIDEr-D reward on the device (== the CPU oracle's reward for the same captions), REINFORCE + DA + XE losses,
+    one optimizer step."""
+    from insenticap_model_b200 import reward as R
+    from insenticap_model_b200 import train as TR
+    from oracle import cider_oracle as CO
+    m, sd = _model()
+    m.train(True)
+    torch.manual_seed(0)
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    refs = syn.synthetic_references(B, V, 5, seed=3)
+    fns = ["img%d" % i for i in range(B)]
+    gts = {fn: refs[i] for i, fn in enumerate(fns)}
+    scorer = R.get_ciderd_scorer({"train": gts}, 1, 2, device="cuda")
+    optim = TR.FusedClampAdam(m, lr=4e-4, grad_clip=0.1)
+    before = optim.flat_p.clone()
+    captured = {}
+    orig = R.get_self_critical_reward
+
+    def spy(sample, greedy, *a, **k):
+        captured["sample"], captured["greedy"] = sample.cpu(), greedy.cpu()
+        captured["reward"] = orig(sample, greedy, *a, **k)
+        return captured["reward"]
+
+    TR.get_self_critical_reward = spy
+    try:
+        batch = (fns, fc.cuda(), att.cuda(), caps.cuda(), lengths, cpts.cuda(), sentis.cuda(), labels.cuda(), gts)
+        out = TR.rl_iteration(m, optim, scorer, batch, max_seq_len=8, samples_per_image=2)
+    finally:
+        TR.get_self_critical_reward = orig
+    torch.cuda.synchronize()
+    orc = CO.CiderOracle(refs, 1, 2)
+    rows = [refs[i] for i in range(B) for _ in range(2)]
+    want = orc.self_critical_reward(captured["sample"].tolist(), captured["greedy"].tolist(), rows)
+    np.testing.assert_allclose(captured["reward"].cpu().numpy(), want, atol=1e-9)
+    for k in ("cap_loss", "da_loss", "xe_loss", "all_loss"):
+        assert torch.isfinite(out[k]).all(), k
+    moved = (optim.flat_p - before).abs()
+    assert float(moved.max()) > 0 and float(moved.max()) <= 4e-4 * 1.01  # Adam's first step is at most lr per weight
