@@ -225,11 +225,21 @@ typedef struct isc_grads {
   float* lang_lstm_w_ih; float* lang_lstm_w_hh; float* lang_lstm_b_ih; float* lang_lstm_b_hh;
   float* classifier_w; float* classifier_b;
 } isc_grads_t; /* same order as isc_weights_t */
+/* Scheduled sampling (captioner.py:219-228): at steps t >= 1 a row with uniform[t,b] < prob is fed a word drawn
+ * from the previous step's distribution (Gumbel-max on the previous log-probs: noise [n_steps,B,V] if given, else
+ * a counter-based generator keyed by seed) instead of inputs[b,t]. NULL / prob 0: plain teacher forcing. */
+typedef struct isc_sched_sampling {
+  float prob;
+  const float* uniform; /* [n_steps, B] in [0,1) */
+  const float* noise;   /* [n_steps, B, V] Gumbel noise or NULL */
+  uint64_t seed;
+} isc_sched_sampling_t;
 size_t isc_train_workspace_bytes(const isc_dims_t* dims, int precision, int B, int n_steps);
 int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision, int mode,
                       const float* fc_feats, const float* att_feats, const int64_t* cpt_words, int n_cpt,
                       const int64_t* senti_words, const int64_t* senti_labels, int B,
                       const int64_t* inputs, int64_t ld_inputs, int n_steps, const isc_dropout_t* dropout,
+                      const isc_sched_sampling_t* sched_sampling,
                       float* logprobs, float* fc_embedded, float* cpt_feats,
                       void* workspace, size_t workspace_bytes, isc_stream_t stream);
 int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision, int mode,

@@ -68,6 +68,10 @@ class Grads(C.Structure):
     _fields_ = [(f, C.c_void_p) for f, _ in WEIGHT_FIELDS]
 
 
+class SchedSampling(C.Structure):
+    _fields_ = [("prob", C.c_float), ("uniform", C.c_void_p), ("noise", C.c_void_p), ("seed", C.c_uint64)]
+
+
 MODE_XE, MODE_SEQ2SEQ, MODE_RL = 0, 1, 2
 
 _vp, _i32, _i64, _sz, _u64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_uint64, C.c_double
@@ -96,7 +100,7 @@ SIGNATURES = {
     "isc_teacher_forced": (C.c_int, [_PD, _vp, C.c_int, _PF, C.c_int, C.c_int, _vp, _i64, _vp, _vp, _sz, _vp]),
     "isc_train_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int, C.c_int]),
     "isc_train_forward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
-                                    _PDR, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                    _PDR, C.POINTER(SchedSampling), _vp, _vp, _vp, _vp, _sz, _vp]),
     "isc_train_backward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
                                      _PDR, _vp, _vp, _vp, _i64, _vp, _vp, _PG, _vp, _sz, _vp]),
     "isc_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int, _f32, _vp]),

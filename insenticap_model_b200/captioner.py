@@ -93,9 +93,9 @@ class _TeacherForced(torch.autograd.Function):
                 C.byref(d), _lib.ptr(packed), model._prec, mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
                 _lib.ptr(call["cpt"]), call["cpt"].shape[1] if call["cpt"] is not None else 0, _lib.ptr(call["sw"]),
                 _lib.ptr(call["labels"]), B, _lib.ptr(call["inputs"]), call["inputs"].shape[1], n_steps,
-                C.byref(drop) if call["dropout"] else None, _lib.ptr(logprobs), _lib.ptr(fc_emb),
-                _lib.ptr(cpt) if call["cpt"] is not None else None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
-                "isc_train_forward")
+                C.byref(drop) if call["dropout"] else None, C.byref(call["ss"]) if call.get("ss") is not None else None,
+                _lib.ptr(logprobs), _lib.ptr(fc_emb), _lib.ptr(cpt) if call["cpt"] is not None else None, _lib.ptr(ws),
+                ws.numel(), _lib.stream_ptr(dev)), "isc_train_forward")
         ctx.model, ctx.mode, ctx.call, ctx.ws, ctx.dims, ctx.packed = model, mode, call, ws, d, packed
         ctx.save_for_backward(logprobs)
         ctx.param_shapes = [p.shape for p in params]
@@ -172,6 +172,7 @@ class Captioner(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        self.ss_override = None  # tests: {"uniform": [T,B], "noise": [T,B,V]} for scheduled sampling
         self.dropout_override = None  # tests: dict of uint8 keep masks {fc, att, sw, sl, out, scale}
         self.use_cuda_graph = False  # beam_search: capture the device-side call once and replay it
         self._graphs = {}
@@ -290,11 +291,17 @@ class Captioner(nn.Module):
         """Differentiable teacher forcing (autograd.Function over the C ABI)."""
         if self._prec != _lib.PREC_BF16X3:
             raise NotImplementedError("the backward pass runs in precision='bf16x3' only")
-        if ss_prob and ss_prob > 0.0 and self.training:
-            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not built yet")
         dev = self._device()
         B = inputs.shape[0]
         n_steps = inputs.shape[1] - 1
+        ss, ss_keep = None, None
+        if ss_prob and ss_prob > 0.0 and self.training:  # captioner.py:219: only in train() mode
+            o = self.ss_override or {}
+            uni = o["uniform"].to(dev).float().contiguous() if "uniform" in o else torch.rand(n_steps, B, device=dev)
+            noise = o["noise"].to(dev).float().contiguous() if "noise" in o else None
+            ss = _lib.SchedSampling(float(ss_prob), uni.data_ptr(), noise.data_ptr() if noise is not None else None,
+                                    int(torch.randint(0, 2 ** 62, (1,)).item()))
+            ss_keep = (uni, noise)
         L = att.shape[1] if att is not None else self.n_regions
         S = (sw.shape[1] + 1) if sw is not None else (self.num_senti_words + 1)
         shapes = {"fc": (B, 512), "sl": (B, 512)}
@@ -303,7 +310,7 @@ class Captioner(nn.Module):
         if sw is not None:
             shapes["sw"] = (B, S, 512)
         call = dict(fc=fc, att=att, cpt=cpt, sw=sw, labels=labels, inputs=inputs.long().contiguous(), n_regions=L, n_senti=S,
-                    dropout=self._dropout_masks(shapes, n_steps, B))
+                    dropout=self._dropout_masks(shapes, n_steps, B), ss=ss, ss_keep=ss_keep)
         out, fc_emb, cpt_feats = _TeacherForced.apply(self, mode, call, *self._params_in_field_order())
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
         return out, fc_emb, (cpt_feats if cpt is not None else None), call

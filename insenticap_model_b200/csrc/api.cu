@@ -729,7 +729,9 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
       if (fc_embedded) ISC_TRY(copy_block(fc_embedded, H, out->fc, H, B, H, c.s));
       if (drop && drop->fc) ISC_TRY(launch_apply_mask(out->fc, H, drop->fc, dscale, B, H, RowDest(), c.s));
     }
-    // att_embed + att2att (captioner.py:302-305), chunked over images so the operand planes stay small
+    // att_embed + att2att (captioner.py:302-305), chunked over images so the operand planes stay small (a chunk's
+    // planes fit the 126 MB L2). Running the fp32 -> bf16 plane split of chunk i+1 on a second stream beside the GEMMs
+    // of chunk i was measured and gains nothing: both are bound by the same L2/HBM traffic.
     for (int b0 = 0; b0 < B; b0 += w.chunk) {
       const int nb = (B - b0 < w.chunk) ? (B - b0) : w.chunk;
       const long long rows = (long long)nb * L;
@@ -1162,7 +1164,7 @@ struct TrainWs {
   void* pro_ws;
   size_t pro_bytes;
   float* cpt_mean;  // inside pro_ws
-  long long* it;
+  long long* it;  // [T][M] tokens actually fed (ground truth, or scheduled-sampling draws)
   // tape
   float *state_h, *state_c;  // [T+1][2][M][H]
   PM pX1, pX2, pcs, phL;     // [T*M][.]
@@ -1232,8 +1234,8 @@ TrainWs carve_train(const isc_dims_t& d, int precision, int B, int T, void* base
   w.pro_bytes = carve_prologue(d, precision, B, nullptr).total;
   w.pro_ws = b.take<uint8_t>(w.pro_bytes);
   w.cpt_mean = base ? carve_prologue(d, precision, B, w.pro_ws).tmp : nullptr;
-  w.it = b.take<long long>(m);
   const size_t tm = (size_t)T * m;
+  w.it = b.take<long long>(tm);
   w.state_h = b.take<float>((size_t)(T + 1) * 2 * m * H);
   w.state_c = b.take<float>((size_t)(T + 1) * 2 * m * H);
   pm(w.pX1, tm, 3 * H);
@@ -1390,8 +1392,8 @@ size_t isc_train_workspace_bytes(const isc_dims_t* dims, int precision, int B, i
 int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision, int mode, const float* fc_feats,
                       const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
                       const int64_t* senti_labels, int B, const int64_t* inputs, int64_t ld_inputs, int n_steps,
-                      const isc_dropout_t* dropout, float* logprobs, float* fc_embedded, float* cpt_feats, void* workspace,
-                      size_t workspace_bytes, isc_stream_t stream) {
+                      const isc_dropout_t* dropout, const isc_sched_sampling_t* ss, float* logprobs, float* fc_embedded,
+                      float* cpt_feats, void* workspace, size_t workspace_bytes, isc_stream_t stream) {
   ISC_TRY(check_device());
   ISC_TRY(check_dims(dims));
   ISC_REQUIRE(precision == ISC_PREC_BF16X3, "training runs in ISC_PREC_BF16X3 only");
@@ -1421,11 +1423,18 @@ int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision,
   ISC_CUDA(cudaMemsetAsync(w.state_c, 0, st, c.s));
   const long long V = dims->vocab, L = dims->n_regions, S = dims->n_senti;
   for (int t = 0; t < n_steps; ++t) {
-    ISC_CUDA(cudaMemcpy2DAsync(w.it, sizeof(long long), inputs + t, ld_inputs * sizeof(long long), sizeof(long long), B,
-                               cudaMemcpyDeviceToDevice, c.s));
+    long long* it_t = w.it + (size_t)t * B;
+    if (ss && ss->prob > 0.f && ss->uniform && t >= 1) {
+      ISC_TRY(launch_ss_select(logprobs + (long long)(t - 1) * V, (long long)n_steps * V,
+                               reinterpret_cast<const long long*>(inputs) + t, ld_inputs, ss->uniform + (size_t)t * B, ss->prob,
+                               ss->noise ? ss->noise + (size_t)t * B * V : nullptr, ss->seed, t, B, (int)V, it_t, c.s));
+    } else {
+      ISC_CUDA(cudaMemcpy2DAsync(it_t, sizeof(long long), inputs + t, ld_inputs * sizeof(long long), sizeof(long long), B,
+                                 cudaMemcpyDeviceToDevice, c.s));
+    }
     DecodeWs v = tape_view(w, t, B);
     StepIO io;
-    io.it = w.it;
+    io.it = it_t;
     io.parent = nullptr;
     io.h_in = w.state_h + (size_t)t * 2 * B * H;
     io.c_in = w.state_c + (size_t)t * 2 * B * H;
@@ -1613,8 +1622,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       // 9. d [h_lang_prev | xt | h_att_prev]
       ISC_TRY(pgemm(precision, op_of(w.pdg1), op_of(w.W1T), w.dX1[cur], 3 * H, M, 3 * H, G4, false, s));
       // 10. word embedding of this step's input tokens
-      ISC_TRY(launch_embed_bwd(reinterpret_cast<const long long*>(inputs) + t, ld_inputs, M, 1, 0, dims->pad_id, 1, (int)V, pk.emb,
-                               w.dX1[cur] + H, 3 * H, 1, nullptr, 1.f, 1.f, g->word_embed, s));
+      ISC_TRY(launch_embed_bwd(w.it + (size_t)t * M, 1, M, 1, 0, dims->pad_id, 1, (int)V, pk.emb, w.dX1[cur] + H, 3 * H, 1, nullptr,
+                               1.f, 1.f, g->word_embed, s));
     }
 
     // ---- weight gradients: one contraction over all T*B rows per matrix

@@ -134,8 +134,9 @@ inline int gemm(int precision, const Operand& A, const Operand& W, const Dest& C
 }
 
 // fp32 [rows, cols] -> bf16 hi (and lo = bf16(x - hi) when lo != null)
+// max_blocks > 0 caps the grid (used when the split shares the SMs with a persistent GEMM on another stream)
 int split_planes(const float* src, int64_t ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo,
-                 int64_t ld_dst, int64_t rows, int cols, cudaStream_t stream);
+                 int64_t ld_dst, int64_t rows, int cols, cudaStream_t stream, int max_blocks = 0);
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

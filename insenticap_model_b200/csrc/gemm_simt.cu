@@ -74,22 +74,39 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
 }
 
-__global__ void split_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ hi,
-                             __nv_bfloat16* __restrict__ lo, long long ld_dst, long long rows, int cols) {
+// 4 independent 16-byte loads in flight per thread: the kernel also runs with a deliberately small grid
+// (beside a persistent GEMM, see run_prologue) and must still cover the HBM latency
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ src, long long ld_src,
+                                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                    long long ld_dst, long long rows, int cols) {
   const int cols4 = cols >> 2;  // cols % 4 == 0 enforced by the host
-  long long total = rows * cols4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long r = i / cols4;
-    int c = (int)(i - r * cols4) * 4;
-    float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
-    __nv_bfloat16 h[4], l[4];
-    split_bf16(v.x, h[0], l[0]);
-    split_bf16(v.y, h[1], l[1]);
-    split_bf16(v.z, h[2], l[2]);
-    split_bf16(v.w, h[3], l[3]);
-    *reinterpret_cast<uint2*>(hi + r * ld_dst + c) = *reinterpret_cast<uint2*>(h);
-    if (lo) *reinterpret_cast<uint2*>(lo + r * ld_dst + c) = *reinterpret_cast<uint2*>(l);
+  const long long total = rows * cols4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 v[4];
+    long long r[4];
+    int c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) {
+        r[u] = i / cols4;
+        c[u] = (int)(i - r[u] * cols4) * 4;
+        v[u] = __ldg(reinterpret_cast<const float4*>(src + r[u] * ld_src + c[u]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride < total) {
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v[u].x, h[0], l[0]);
+        split_bf16(v[u].y, h[1], l[1]);
+        split_bf16(v[u].z, h[2], l[2]);
+        split_bf16(v[u].w, h[3], l[3]);
+        *reinterpret_cast<uint2*>(hi + r[u] * ld_dst + c[u]) = *reinterpret_cast<uint2*>(h);
+        if (lo) *reinterpret_cast<uint2*>(lo + r[u] * ld_dst + c[u]) = *reinterpret_cast<uint2*>(l);
+      }
+    }
   }
 }
 
@@ -109,13 +126,15 @@ int gemm_simt(const Operand& A, const Operand& W, const Dest& C, int M, int N, i
 }
 
 int split_planes(const float* src, int64_t ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t ld_dst, int64_t rows,
-                 int cols, cudaStream_t stream) {
+                 int cols, cudaStream_t stream, int max_blocks) {
   if (rows <= 0 || cols <= 0) return 0;
   ISC_REQUIRE(cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0,
               "split_planes: cols/ld must be multiples of 4 and src 16-byte aligned");
   long long total = rows * (cols / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  int blocks = (int)((total + 1023) / 1024);
+  if (blocks < 1) blocks = 1;
+  const int cap = max_blocks > 0 ? max_blocks : 148 * 8;
+  if (blocks > cap) blocks = cap;
   ProfScope ps(ISC_K_POINTWISE, (double)rows * cols * (4.0 + 2.0 + (lo ? 2.0 : 0.0)), stream);
   split_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, rows, cols);
   ISC_LAUNCH_CHECK();

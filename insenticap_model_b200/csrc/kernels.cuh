@@ -128,6 +128,9 @@ int launch_beam_init(long long* it, int* alive, int* len, double* score, int* pa
 int launch_beam_finalize(const int* tok, const int* len, const double* score, long long* tokens_out, double* scores_out,
                          int* lengths_out, int B, int K, int T, cudaStream_t stream);
 int launch_greedy_init(long long* it, int* unfinished, int B, int sos_id, cudaStream_t stream);
+int launch_ss_select(const float* logp_prev, long long ld_logp, const long long* truth, long long ld_truth,
+                     const float* uniform, float prob, const float* noise, unsigned long long seed, int t, int B, int V,
+                     long long* it, cudaStream_t stream);
 // weights outputs must read as zero after the whole-batch early stop
 int launch_zero_if_stopped(float* p, long long row_stride, int row_len, int B, const int* alive_count, int t,
                            cudaStream_t stream);

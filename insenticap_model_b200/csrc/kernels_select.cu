@@ -464,6 +464,37 @@ __global__ void __launch_bounds__(256) greedy_merge_kernel(GreedyParams p) {
   }
 }
 
+// Scheduled sampling (captioner.py:219-228): with probability ss_prob a row is fed a word drawn from the PREVIOUS
+// step's distribution instead of the ground-truth word. The draw is Gumbel-max on the previous log-probs (noise
+// injected or counter-based, like the sampled decode). One CTA per row.
+__global__ void __launch_bounds__(NT) ss_select_kernel(const float* __restrict__ logp_prev, long long ld_logp,
+                                                       const long long* __restrict__ truth, long long ld_truth,
+                                                       const float* __restrict__ uniform, float prob,
+                                                       const float* __restrict__ noise, unsigned long long seed, int t, int B,
+                                                       int V, long long* __restrict__ it) {
+  __shared__ float redv[NT / 32];
+  __shared__ int redi[NT / 32];
+  const int b = blockIdx.x;
+  if (!(uniform[b] < prob)) {
+    if (threadIdx.x == 0) it[b] = truth[(long long)b * ld_truth];
+    return;
+  }
+  const float* row = logp_prev + (long long)b * ld_logp;
+  float sv = -CUDART_INF_F;
+  int si = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += NT) {
+    const float g = noise ? noise[(long long)b * V + i]
+                          : gumbel_counter(seed, ((unsigned long long)t * B + b) * (unsigned long long)V + i);
+    const float s = row[i] + g;
+    if (s > sv) {
+      sv = s;
+      si = i;
+    }
+  }
+  block_argmax(sv, si, redv, redi);
+  if (threadIdx.x == 0) it[b] = si;
+}
+
 __global__ void beam_init_kernel(long long* it, int* alive, int* len, double* score, int* parent, int M, int K, int sos_id) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
@@ -539,6 +570,14 @@ int launch_beam_finalize(const int* tok, const int* len, const double* score, lo
   int M = B * K;
   ProfScope ps(ISC_K_SELECT, (double)M * T * 12.0, stream);
   beam_finalize_kernel<<<(M * T + 255) / 256, 256, 0, stream>>>(tok, len, score, tokens_out, scores_out, lengths_out, M, T);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_ss_select(const float* logp_prev, long long ld_logp, const long long* truth, long long ld_truth,
+                     const float* uniform, float prob, const float* noise, unsigned long long seed, int t, int B, int V,
+                     long long* it, cudaStream_t stream) {
+  ProfScope ps(ISC_K_SELECT, (double)B * V * 4.0 * (noise ? 2 : 1), stream);
+  ss_select_kernel<<<B, NT, 0, stream>>>(logp_prev, ld_logp, truth, ld_truth, uniform, prob, noise, seed, t, B, V, it);
   ISC_LAUNCH_CHECK();
   return 0;
 }

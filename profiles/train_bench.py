@@ -1,0 +1,89 @@
+"""Times the training iterations of BASELINE configs[2] / [3] on synthetic data (one process per GPU; torchrun for N > 1):
+  xe : train_xe.py:160-192  — xe + domain-alignment + seq2seq losses, backward, gradient all-reduce, clamp + Adam
+  rl : models/decoder.py:62-170 — sampled (x samples_per_image) + greedy decode, device CIDEr-D reward, REINFORCE + DA + XE
+Usage: python profiles/train_bench.py xe|rl [batch] [iters] [samples_per_image]
+Prints one JSON line on rank 0 (ms per iteration = max over ranks of CUDA-event time; rows/s over all ranks)."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from insenticap_model_b200 import reward as R  # noqa: E402
+from insenticap_model_b200 import synthetic as syn  # noqa: E402
+from insenticap_model_b200 import train as TR  # noqa: E402
+from insenticap_model_b200.captioner import Captioner  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "xe"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+iters = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+spi = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+V, T = 10000, 16
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+
+m = Captioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS), precision="bf16x3")
+m.load_state_dict(syn.synthetic_state_dict(V, 0))
+m = m.to(dev).train()
+optim = TR.FusedClampAdam(m, lr=4e-4, grad_clip=0.1)
+g = torch.Generator(device=dev).manual_seed(100 + rank)  # every rank holds its own images
+fc = torch.rand(B, 2048, device=dev, generator=g)
+att = torch.rand(B, 14, 14, 2048, device=dev, generator=g)
+cpts = torch.randint(4, V, (B, 5), device=dev, generator=g)
+sentis = torch.randint(4, V, (B, 10), device=dev, generator=g)
+labels = (torch.arange(B, device=dev) % 3).long()
+caps = torch.randint(4, V, (B, T + 1), device=dev, generator=g)
+caps[:, 0] = 1
+lengths = [T] * B
+s2s = (caps, lengths, cpts, sentis, labels)
+if what == "rl":
+    refs = syn.synthetic_references(B, V, 5, seed=3 + rank)
+    fns = ["img%d" % i for i in range(B)]
+    gts = {fn: refs[i] for i, fn in enumerate(fns)}
+    scorer = R.get_ciderd_scorer({"train": gts}, 1, 2, device=dev)
+    scorer.register_ground_truth(fns, gts, 1, 2)
+    batch = (fns, fc, att, caps, lengths, cpts, sentis, labels, gts)
+    step = lambda: TR.rl_iteration(m, optim, scorer, batch, max_seq_len=T, seq2seq_batch=s2s, samples_per_image=spi)
+    rows = B * (spi + 1)
+else:
+    batch = (fc, att, caps, lengths, cpts, labels)
+    step = lambda: TR.xe_iteration(m, optim, batch, s2s)
+    rows = B
+
+for _ in range(2):
+    out = step()
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    out = step()
+e1.record()
+torch.cuda.synchronize()
+ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+chk = optim.flat_p.double().sum().reshape(1)
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    in_sync = bool((hi - lo).abs().item() == 0.0)
+else:
+    in_sync = True
+if rank == 0:
+    print(json.dumps({"workload": what, "n_gpus": world, "batch_per_gpu": B, "samples_per_image": spi if what == "rl" else None,
+                      "ms_per_iteration": float(ms.item()), "rows_per_s": world * rows / (float(ms.item()) * 1e-3),
+                      "losses": {k: float(v) for k, v in out.items()}, "replicas_in_sync": in_sync,
+                      "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}), flush=True)
+if world > 1:
+    dist.destroy_process_group()

@@ -262,3 +262,36 @@ def test_rl_iteration_device_reward_and_update():
         assert torch.isfinite(out[k]).all(), k
     moved = (optim.flat_p - before).abs()
     assert float(moved.max()) > 0 and float(moved.max()) <= 4e-4 * 1.01  # Adam's first step is at most lr per weight
+
+
+def test_scheduled_sampling_matches_oracle():
+    """captioner.py:219-228 in train(): rows picked by the injected uniforms are fed the Gumbel-max draw from the
+    previous step's distribution (injected noise); log-probs and gradients match the oracle doing the same."""
+    m, sd = _model()
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    n = T1 - 1
+    g = torch.Generator().manual_seed(21)
+    ss = {"prob": 0.5, "uniform": torch.rand(n, B, generator=g),
+          "noise": -torch.log(-torch.log(torch.rand(n, B, V, generator=g).clamp_min(1e-9)))}
+    m.train(True)
+    m.dropout_override = {"scale": 1.0}  # train() mode without dropout
+    m.ss_override = {"uniform": ss["uniform"], "noise": ss["noise"]}
+    m.zero_grad()
+    pred = m(fc.cuda(), att.cuda(), cpts.cuda(), caps.cuda(), labels.cuda(), 0.5, mode="xe")
+    loss = _xe_loss(pred, caps[:, 1:].cuda(), lengths)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    def ref_loss(p):
+        f = O.prologue(p, fc, att, cpts, None, labels)
+        return _xe_loss(O.teacher_forced(p, f, caps, ss=ss), caps[:, 1:], lengths)
+
+    with torch.no_grad():
+        f = O.prologue(sd, fc, att, cpts, None, labels)
+        want = O.teacher_forced(sd, f, caps, ss=ss)
+        plain = O.teacher_forced(sd, f, caps)
+    assert not torch.allclose(want, plain)  # the draws really replaced ground-truth inputs
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-4)
+    ref, grads = _oracle_grads(sd, ref_loss)
+    assert abs(float(loss) - ref) <= 1e-4 * abs(ref)
+    _compare(m, grads)

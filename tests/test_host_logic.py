@@ -43,7 +43,7 @@ def test_no_cpu_fallback_and_mode_dispatch():
     m.train()  # the training path (tape + hand-written backward) is CUDA-only as well
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.forward_xe(fc, att, cpts, syn.synthetic_captions(2, 50), labels)
-    with pytest.raises(NotImplementedError):  # scheduled sampling is not built
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # scheduled sampling: same path, same rule
         m._teacher_forced_train(0, fc, att, cpts, None, labels, syn.synthetic_captions(2, 50), 0.25)
     with pytest.raises(ValueError):
         Captioner(syn.make_vocab(50), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS, rnn_hid_dim=256))
