@@ -251,6 +251,12 @@ def run_ours(args):
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": achieved / pk["hbm"], "traffic": None,
                 "note": "algorithmic bytes summed over %d launches / summed CUDA-event time; peak %s" % (d["launches"], pk["source"])}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.precision == "bf16x3" and B == 1024 and KB == 3:
+        tj = json.load(open(tpath))
+        if dom in tj:  # DRAM bytes per launch of this kernel class, from the committed ncu --set full captures
+            roof["traffic"] = tj[dom]["dram_bytes_per_launch"]
+            roof["traffic_note"] = "bytes per launch, dram read + write, " + tj["_source"]
     roof["avg_launch_us"] = 1e3 * d["ms"] / d["launches"]
     roof["share_of_kernel_time"] = d["ms"] / total_kernel_ms
     breakdown = {k: round(v["ms"] / args.steps, 4) for k, v in sorted(classes.items(), key=lambda kv: -kv[1]["ms"])}
