@@ -100,6 +100,12 @@ class _TeacherForced(torch.autograd.Function):
         ctx.save_for_backward(logprobs)
         ctx.param_shapes = [p.shape for p in params]
         ctx.mark_non_differentiable(fc_emb)
+        if call.get("fused") is not None:
+            # fused masked NLL / REINFORCE form: loss = sum coef[b,t] * (-logprobs[b,t,targets[b,t]]); the backward then
+            # builds d logits straight from (targets, coef) and never materialises a [B,T,V] gradient
+            targets, coef = call["fused"]
+            loss = -(logprobs.gather(2, targets.unsqueeze(2)).squeeze(2) * coef).sum()
+            return loss, fc_emb, cpt
         return logprobs, fc_emb, cpt
 
     @staticmethod
@@ -117,16 +123,27 @@ class _TeacherForced(torch.autograd.Function):
             views.append(v)
             setattr(g, field, v.data_ptr())
             off += n
-        dlogp = dlogp.contiguous() if dlogp is not None else None
+        targets = coef = None
+        if call.get("fused") is not None:
+            targets, coef = call["fused"]
+            coef = (coef * dlogp).contiguous() if dlogp is not None else None  # dlogp is d loss_out here (a scalar)
+            if coef is None:
+                targets = None
+            dlogp = None
+        else:
+            dlogp = dlogp.contiguous() if dlogp is not None else None
         dcpt = dcpt.contiguous() if (dcpt is not None and call["cpt"] is not None) else None
+        if dlogp is None and coef is None and dcpt is None:
+            return (None, None, None) + tuple(views)
         drop = model._dropout_struct(call["dropout"])
         with torch.cuda.device(dev):
             _lib.check(lib.isc_train_backward(
                 C.byref(d), _lib.ptr(ctx.packed), model._prec, ctx.mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
                 _lib.ptr(call["cpt"]), call["cpt"].shape[1] if call["cpt"] is not None else 0, _lib.ptr(call["sw"]),
                 _lib.ptr(call["labels"]), B, _lib.ptr(call["inputs"]), call["inputs"].shape[1], n_steps,
-                C.byref(drop) if call["dropout"] else None, _lib.ptr(logprobs), _lib.ptr(dlogp), None, 0, None,
-                _lib.ptr(dcpt), C.byref(g), _lib.ptr(ctx.ws), ctx.ws.numel(), _lib.stream_ptr(dev)), "isc_train_backward")
+                C.byref(drop) if call["dropout"] else None, _lib.ptr(logprobs), _lib.ptr(dlogp), _lib.ptr(targets),
+                targets.shape[1] if targets is not None else 0, _lib.ptr(coef), _lib.ptr(dcpt), C.byref(g), _lib.ptr(ctx.ws),
+                ctx.ws.numel(), _lib.stream_ptr(dev)), "isc_train_backward")
         ctx.ws = None
         return (None, None, None) + tuple(views)
 
@@ -287,8 +304,9 @@ class Captioner(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[name] for _, name in _lib.WEIGHT_FIELDS]
 
-    def _teacher_forced_train(self, mode, fc, att, cpt, sw, labels, inputs, ss_prob):
-        """Differentiable teacher forcing (autograd.Function over the C ABI)."""
+    def _teacher_forced_train(self, mode, fc, att, cpt, sw, labels, inputs, ss_prob, fused=None):
+        """Differentiable teacher forcing (autograd.Function over the C ABI). ``fused`` = (targets int64 [B,T],
+        coef fp32 [B,T]) makes the first result the scalar sum coef * (-logprobs[targets]) instead of the log-probs."""
         if self._prec != _lib.PREC_BF16X3:
             raise NotImplementedError("the backward pass runs in precision='bf16x3' only")
         dev = self._device()
@@ -310,7 +328,7 @@ class Captioner(nn.Module):
         if sw is not None:
             shapes["sw"] = (B, S, 512)
         call = dict(fc=fc, att=att, cpt=cpt, sw=sw, labels=labels, inputs=inputs.long().contiguous(), n_regions=L, n_senti=S,
-                    dropout=self._dropout_masks(shapes, n_steps, B), ss=ss, ss_keep=ss_keep)
+                    dropout=self._dropout_masks(shapes, n_steps, B), ss=ss, ss_keep=ss_keep, fused=fused)
         out, fc_emb, cpt_feats = _TeacherForced.apply(self, mode, call, *self._params_in_field_order())
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
         return out, fc_emb, (cpt_feats if cpt is not None else None), call
@@ -459,6 +477,34 @@ class Captioner(nn.Module):
         t, B = self.prologue(fc_feats, att_feats, cpt_words, None, senti_labels)
         self.fc_feats, self.cpt_feats = t["fc"], t.get("cpt_feats")
         return self._teacher_forced(t, B, captions)
+
+    @staticmethod
+    def _nll_coef(captions, lengths, dev):
+        """XECriterion's weights (captioner.py:431-440): mask[b,t] = t < lengths[b], normalised by its sum."""
+        n_steps = captions.shape[1] - 1
+        lens = torch.as_tensor(list(lengths), device=dev).unsqueeze(1)
+        mask = (torch.arange(n_steps, device=dev).unsqueeze(0) < lens).float()
+        return captions[:, 1:].long().contiguous(), (mask / mask.sum()).contiguous()
+
+    def xe_loss(self, fc_feats, att_feats, cpt_words, captions, senti_labels, lengths, ss_prob=0.0):
+        """``XECriterion()(self(..., mode='xe'), captions[:, 1:], lengths)`` with the loss fused into the backward
+        (no [B,T,V] gradient tensor). Sets fc_feats / cpt_feats like forward_xe."""
+        B = fc_feats.shape[0]
+        targets, coef = self._nll_coef(captions, lengths, self._device())
+        loss, self.fc_feats, self.cpt_feats, _ = self._teacher_forced_train(
+            _lib.MODE_XE, fc_feats.reshape(B, -1).float().contiguous(),
+            att_feats.reshape(B, -1, att_feats.shape[-1]).float().contiguous(), cpt_words.long().contiguous(), None,
+            senti_labels.reshape(B).long().contiguous(), captions, ss_prob, fused=(targets, coef))
+        return loss
+
+    def seq2seq_loss(self, senti_captions, cpt_words, senti_words, senti_labels, lengths, ss_prob=0.0):
+        """Fused-loss form of ``XECriterion()(self(..., mode='seq2seq'), senti_captions[:, 1:], lengths)``."""
+        B = senti_captions.shape[0]
+        targets, coef = self._nll_coef(senti_captions, lengths, self._device())
+        loss, _, _, _ = self._teacher_forced_train(
+            _lib.MODE_SEQ2SEQ, None, None, cpt_words.long().contiguous(), senti_words.reshape(B, -1).long().contiguous(),
+            senti_labels.reshape(B).long().contiguous(), senti_captions, ss_prob, fused=(targets, coef))
+        return loss
 
     def forward_seq2seq(self, senti_captions, cpt_words, senti_words, senti_labels, ss_prob=0.0):
         """Sentiment-corpus teacher forcing (captioner.py:242-288)."""

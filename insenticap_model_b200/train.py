@@ -95,22 +95,28 @@ class FusedClampAdam:
         self.model._packed_key = None  # parameters changed behind torch's version counters: repack on next use
 
 
-def xe_iteration(model, optim, batch, seq2seq_batch=None, ss_prob=0.0):
+def xe_iteration(model, optim, batch, seq2seq_batch=None, ss_prob=0.0, fused_loss=True):
     """One iteration of train_xe.py:150-192 on device tensors.
     batch = (fc_feats, att_feats, captions, lengths, cpt_words, senti_labels); seq2seq_batch =
-    (captions, lengths, cpt_words, senti_words, senti_labels) or None. Returns the loss values (device scalars)."""
+    (captions, lengths, cpt_words, senti_words, senti_labels) or None. Returns the loss values (device scalars).
+    ``fused_loss``: Captioner.xe_loss / seq2seq_loss (masked NLL folded into the backward) instead of materialising
+    the [B,T,V] log-probs' gradient; same value, same gradients."""
     xe_crit, da_crit = XECriterion(), nn.MSELoss()
     fc, att, caps, lengths, cpts, labels = batch
     optim.zero_grad()
-    pred = model(fc, att, cpts, caps, labels, ss_prob, mode="xe")
-    xe_loss = xe_crit(pred, caps[:, 1:], lengths)
+    if fused_loss:
+        xe_loss = model.xe_loss(fc, att, cpts, caps, labels, lengths, ss_prob)
+    else:
+        xe_loss = xe_crit(model(fc, att, cpts, caps, labels, ss_prob, mode="xe"), caps[:, 1:], lengths)
     da_loss = da_crit(model.cpt_feats, model.fc_feats.detach())
     all_loss = xe_loss + da_loss
     out = {"xe_loss": xe_loss.detach(), "da_loss": da_loss.detach()}
     if seq2seq_batch is not None:
         s_caps, s_lengths, s_cpts, s_sentis, s_labels = seq2seq_batch
-        pred2 = model(s_caps, s_cpts, s_sentis, s_labels, ss_prob, mode="seq2seq")
-        s2s = xe_crit(pred2, s_caps[:, 1:], s_lengths)
+        if fused_loss:
+            s2s = model.seq2seq_loss(s_caps, s_cpts, s_sentis, s_labels, s_lengths, ss_prob)
+        else:
+            s2s = xe_crit(model(s_caps, s_cpts, s_sentis, s_labels, ss_prob, mode="seq2seq"), s_caps[:, 1:], s_lengths)
         all_loss = all_loss + s2s
         out["seq2seq_loss"] = s2s.detach()
     all_loss.backward()

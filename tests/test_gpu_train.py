@@ -295,3 +295,28 @@ def test_scheduled_sampling_matches_oracle():
     ref, grads = _oracle_grads(sd, ref_loss)
     assert abs(float(loss) - ref) <= 1e-4 * abs(ref)
     _compare(m, grads)
+
+
+def test_fused_nll_equals_criterion_on_logprobs():
+    """Captioner.xe_loss / seq2seq_loss (loss folded into the backward: d logits built from targets + weights) give the
+    same value and the same 40 gradients as XECriterion on the materialised log-probs."""
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    grads = []
+    for fused in (False, True):
+        m, _ = _model()
+        m.eval()
+        m.zero_grad()
+        if fused:
+            loss = m.xe_loss(fc.cuda(), att.cuda(), cpts.cuda(), caps.cuda(), labels.cuda(), lengths) + \
+                m.seq2seq_loss(caps.cuda(), cpts.cuda(), sentis.cuda(), labels.cuda(), lengths)
+        else:
+            loss = _xe_loss(m(fc.cuda(), att.cuda(), cpts.cuda(), caps.cuda(), labels.cuda(), 0.0, mode="xe"), caps[:, 1:].cuda(),
+                            lengths) + \
+                _xe_loss(m(caps.cuda(), cpts.cuda(), sentis.cuda(), labels.cuda(), 0.0, mode="seq2seq"), caps[:, 1:].cuda(), lengths)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads.append((float(loss), {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[0][0])
+    for k in grads[0][1]:
+        a, b = grads[0][1][k], grads[1][1][k]
+        assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-9, k
