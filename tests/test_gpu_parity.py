@@ -331,3 +331,49 @@ def test_beam_graph_replay_and_host_pipeline_match_eager():
     torch.cuda.synchronize()
     for a, b in zip(host, ref):
         assert not a.is_cuda and torch.equal(a, b.cpu())
+
+
+@pytest.mark.parametrize("V,B,K,T_", [(1003, 1, 1, 3), (130, 5, 4, 9), (4097, 3, 2, 5), (257, 7, 3, 16), (1000, 2, 8, 6)])
+def test_ragged_shapes_against_oracle(V, B, K, T_):
+    """Edge shapes: single image / single beam, vocabularies that are not multiples of 4, 8 or 256 (ragged last logits
+    tile and record slice), row counts below one 128-row tile, beam sizes on both sides of the fused-selection
+    limit (K <= 4 fused in the GEMM epilogue, K = 8 through materialised logits), very short captions."""
+    m = model(V, 7, "bf16x3")
+    p = params(V, 7)
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=13)
+    with torch.no_grad():
+        tk, sc, ln = m.beam_search(*to_cuda(fc, att, sentis, labels), beam_size=K, max_seq_len=T_)
+        seq, lp, mask = m(*to_cuda(fc, att, cpts, sentis, labels), T_, 1, mode="rl")
+        f = O.prologue(p, fc, att, cpts, sentis, labels)
+        tk_o, sc_o, ln_o, margin = O.beam_search(p, f, B, K, 1, T_, return_margins=True)
+        seq_o, lp_o, mask_o, gm = O.decode_greedy(p, f, B, T_, return_margins=True)
+    assert tk.shape == (B, K, T_) and sc.shape == (B, K)
+    if margin > 1e-5:  # otherwise the oracle's own K-th / (K+1)-th candidates are a numerical tie
+        assert np.array_equal(tk.cpu().numpy(), tk_o.numpy())
+        assert np.array_equal(ln.cpu().numpy(), ln_o.numpy())
+        np.testing.assert_allclose(sc.cpu().numpy(), sc_o.numpy(), atol=2e-4)
+    bad, _ = greedy_mismatch_report(seq, seq_o, gm, 1e-5)
+    assert not bad, bad
+    same = (seq.cpu() == seq_o).all(1)
+    np.testing.assert_allclose(lp.cpu()[same].numpy(), lp_o[same].numpy(), **LP_TOL)
+
+
+def test_empty_and_invalid_arguments_fail_loudly():
+    """Error behaviour at the boundary: bad arguments come back as exceptions with the library's message, never as
+    a crash or a silent fallback."""
+    import ctypes as C
+    from insenticap_model_b200 import _lib
+    lib = _lib.load()
+    V = 130
+    m = model(V, 7, "bf16x3")
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(2, V, seed=13)
+    with pytest.raises(RuntimeError, match="beam|K"):
+        m.beam_search(*to_cuda(fc, att, sentis, labels), beam_size=9, max_seq_len=4)  # K <= 8
+    with pytest.raises(RuntimeError, match="T"):
+        m.beam_search(*to_cuda(fc, att, sentis, labels), beam_size=3, max_seq_len=65)  # T <= 64
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(fc, att, cpts, sentis, labels, 4, 1, mode="rl")  # host tensors on a decode entry point without a host path
+    d = m._dims()
+    assert lib.isc_decode_workspace_bytes(C.byref(d), 1, 0) == 0  # M = 0 -> no workspace, and the call refuses it
+    with pytest.raises(RuntimeError):
+        _lib.check(lib.isc_decode_beam(C.byref(d), None, 1, None, 0, 3, 4, 1, None, None, None, None, 0, None), "isc_decode_beam")
