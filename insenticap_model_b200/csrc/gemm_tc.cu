@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -37,15 +38,19 @@ constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one XOR-swizzled 32x32 fp
 
 // BN = 128 for the step GEMMs (M = 3072 rows: more, smaller tiles fill 148 SMs better), BN = 256 where there are many
 // tiles (vocabulary logits, prologue): 25 % less L2 -> smem traffic per flop, which is what bounds this kernel.
-template <int PASSES, int BN>
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile. Each CTA loads its 128 rows of A and
+// HALF of the B rows, and the pair's MMAs read both halves — per flop, half the B bytes cross L2 -> smem and the
+// smem port; the accumulator of each CTA (its 128 rows x BN columns) stays in its own TMEM.
+template <int PASSES, int BN, int CG = 1>
 struct Cfg {
   static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
   // K extent of one pipeline stage. 64 bf16 = one 128-byte swizzle row; the wide split-bf16 tile uses 32 (64-byte
   // swizzle) so that four 48 KiB stages fit instead of two 96 KiB ones — two stages cannot keep enough bytes in
   // flight to cover the L2 latency.
-  static constexpr int kBK = (PASSES == 3 && BN == 256) ? 32 : 64;
+  static constexpr int kBK = (PASSES == 3 && BN == 256 && CG == 1) ? 32 : 64;
+  static constexpr int kBRows = BN / CG;  // B rows this CTA loads
   static constexpr int kATileBytes = BM * kBK * 2;
-  static constexpr int kBTileBytes = BN * kBK * 2;
+  static constexpr int kBTileBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kPlanes * (kATileBytes + kBTileBytes);  // A_hi,(A_lo),B_hi,(B_lo)
   static constexpr int kStages = 192 * 1024 / kStageBytes;  // x3: 3 / 4 stages, bf16: 6 / 4
   static constexpr int kTmemCols = ACC_STAGES * BN;  // 256 / 512 columns (power of two)
@@ -111,6 +116,45 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// cta_group::2 variants: the load signals the LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared),
+// the MMA spans both CTAs of the pair, the commit arrives on the same barrier offset in both CTAs.
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  // arrive on `bar` of CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -183,12 +227,12 @@ __device__ __forceinline__ float act_ct(float v) {
   return v;
 }
 
-template <int PASSES, int BN, int ACT, int EPI>
+template <int PASSES, int BN, int ACT, int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const EpiParams ep) {
-  using C = Cfg<PASSES, BN>;
+  using C = Cfg<PASSES, BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_smem = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
@@ -204,8 +248,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   constexpr int BK = C::kBK;
   const int num_kb = (ep.K + BK - 1) / BK;
   const int tiles_n = (ep.N + BN - 1) / BN;
-  const int tiles_m = (ep.M + BM - 1) / BM;
+  const int tiles_m = (ep.M + CG * BM - 1) / (CG * BM);  // CG = 2: a tile is 256 rows, 128 per CTA of the pair
   const int num_tiles = tiles_m * tiles_n;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int walker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // the pair walks the tile list together
+  const int walkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
@@ -220,18 +267,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[s], CG * EPI_WARPS);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-wide; the same warp frees it at the end
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(C::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled into them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -239,29 +294,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================== TMA producer (one elected lane) =====================
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int tile = walker; tile < num_tiles; tile += walkers) {
+        const int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM;
+        const int n0 = (tile % tiles_n) * BN + cta_rank * C::kBRows;  // CG = 2: this CTA's half of the B rows
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
           uint8_t* st = smem + s * C::kStageBytes;
           uint8_t* stb = st + C::kPlanes * C::kATileBytes;
-          mbar_expect_tx(&full_bar[s], C::kStageBytes);
           const int k0 = kb * BK;
-          tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
-          if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
-          tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
-          if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          if (CG == 2) {
+            // both CTAs' bytes complete on the leader's barrier, which alone is armed and waited on
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kStageBytes);
+            tma_load_2d_pair(st, &map_a_hi, &full_bar[s], k0, m0);
+            if (PASSES == 3) tma_load_2d_pair(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
+            tma_load_2d_pair(stb, &map_b_hi, &full_bar[s], k0, n0);
+            if (PASSES == 3) tma_load_2d_pair(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          } else {
+            mbar_expect_tx(&full_bar[s], C::kStageBytes);
+            tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
+            if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
+            tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
+            if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    if (lane == 0 && cta_rank == 0) {  // CG = 2: the leader issues for the pair
+      constexpr uint32_t idesc = umma_idesc_bf16(CG * BM, BN);
       int it = 0, j = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
         const int as = j & 1;
         mbar_wait(&acc_empty[as], ((j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tcgen05_fence_after();
@@ -282,13 +347,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // +32 B per 16-element K step inside the 128 B swizzle atom
-              umma_bf16(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc, accumulate);
+              if (CG == 2)
+                umma_bf16_pair(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc, accumulate);
+              else
+                umma_bf16(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc, accumulate);
               accumulate = 1;
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once the MMAs above have read it
+          // frees the smem stage (in both CTAs of a pair) once the MMAs above have read it
+          if (CG == 2) umma_commit_pair(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full[as]);  // accumulator of this tile complete
+        // accumulator of this tile complete (signalled to the epilogue warps of both CTAs of a pair)
+        if (CG == 2) umma_commit_pair(&acc_full[as]);
+        else umma_commit(&acc_full[as]);
       }
     }
   } else if (EPI == EPI_LOGITS) {
@@ -301,9 +373,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const LogitsSelect& sel = ep.sel;
     constexpr float kLog2e = 1.4426950408889634f;
     int j = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+    for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
       const int tn = tile % tiles_n;
-      const int m0 = (tile / tiles_n) * BM, n_base = tn * BN + half * SLICE;
+      const int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM, n_base = tn * BN + half * SLICE;
       const int as = j & 1;
       const int row = m0 + quarter * 32 + lane;
       for (int i = lane; i < SLICE; i += 32) bias_s[i] = (ep.bias && n_base + i < ep.N) ? __ldg(ep.bias + n_base + i) : 0.f;
@@ -353,11 +425,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
-      // the accumulator stage is drained: release it to the MMA warp before the stores
+      // the accumulator stage is drained: release it to the (leader's) MMA warp before the stores
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+        if (CG == 2) mbar_arrive_cta(&acc_empty[as], 0);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
       }
       if (row < ep.M) {
         float4* r4 = reinterpret_cast<float4*>(sel.rec + ((long long)row * sel.np + (tn * 2 + half)) * SEL_REC);
@@ -385,8 +458,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const bool madd_vec = ep.addmat && ((reinterpret_cast<uintptr_t>(ep.addmat) & 15) == 0) && ((ep.ld_addmat & 3) == 0);
     const bool bias_vec = ep.bias && ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     int j = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
+      const int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM, n0 = (tile % tiles_n) * BN;
       const int as = j & 1;
       const int row0 = m0 + quarter * 32 + r_off;  // this lane's rows: row0 + 4*i, i = 0..7
       int nvalid = (ep.M - row0 + 3) >> 2;
@@ -464,20 +537,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         __syncwarp();  // staging tile is reused by the next chunk
       }
-      // release the accumulator stage to the MMA warp
+      // release the accumulator stage to the (leader's) MMA warp
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+        if (CG == 2) mbar_arrive_cta(&acc_empty[as], 0);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
       }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // no CTA of the pair leaves while the other may still signal into its smem
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    if (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
   }
 }
 
@@ -542,24 +620,42 @@ struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int PASSES, int BN, int ACT, int EPI>
+template <int PASSES, int BN, int ACT, int EPI, int CG>
 static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStream_t stream) {
-  ISC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<PASSES, BN, ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg<PASSES, BN>::kSmemBytes));
-  gemm_tc_kernel<PASSES, BN, ACT, EPI><<<grid, NUM_THREADS, Cfg<PASSES, BN>::kSmemBytes, stream>>>(m.a_hi, m.a_lo, m.b_hi,
-                                                                                                 m.b_lo, ep);
+  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG>;
+  constexpr int smem = Cfg<PASSES, BN, CG>::kSmemBytes;
+  ISC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    ISC_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, m.b_hi, m.b_lo, ep));
+  } else {
+    kern<<<grid, NUM_THREADS, smem, stream>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, ep);
+  }
   ISC_LAUNCH_CHECK();
   return 0;
 }
 
-template <int PASSES, int BN>
+template <int PASSES, int BN, int CG>
 static int make_maps(Maps& m, const Operand& A, const Operand& W, int M, int N, int K) {
-  constexpr int BK = Cfg<PASSES, BN>::kBK;
+  using C = Cfg<PASSES, BN, CG>;
+  constexpr int BK = C::kBK;
   ISC_TRY(make_map(&m.a_hi, A.hi, M, K, A.ldp, BM, BK));
-  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, BN, BK));
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, C::kBRows, BK));
   if (PASSES == 3) {
     ISC_TRY(make_map(&m.a_lo, A.lo, M, K, A.ldp, BM, BK));
-    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, BN, BK));
+    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, C::kBRows, BK));
   } else {
     m.a_lo = m.a_hi;
     m.b_lo = m.b_hi;
@@ -567,18 +663,19 @@ static int make_maps(Maps& m, const Operand& A, const Operand& W, int M, int N, 
   return 0;
 }
 
-template <int BN>
+// persistent grid: one CTA (CG = 2: one CTA pair) per SM (pair) walks the tile list
+template <int BN, int CG>
 static int persistent_grid(int M, int N) {
-  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
-  const int sms = num_sms();
-  return tiles < sms ? tiles : sms;  // one CTA per SM walks the tile list
+  const int tiles = ((N + BN - 1) / BN) * ((M + CG * BM - 1) / (CG * BM));
+  const int slots = num_sms() / CG;
+  return CG * (tiles < slots ? tiles : slots);
 }
 
-template <int PASSES, int BN>
+template <int PASSES, int BN, int CG>
 static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int N, int K, const Epilogue& e,
                   cudaStream_t stream) {
   Maps m;
-  ISC_TRY((make_maps<PASSES, BN>(m, A, W, M, N, K)));
+  ISC_TRY((make_maps<PASSES, BN, CG>(m, A, W, M, N, K)));
   EpiParams ep;
   ep.bias = e.bias;
   ep.rowadd = e.rowadd;
@@ -595,22 +692,22 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.M = M;
   ep.N = N;
   ep.K = K;
-  const int grid = persistent_grid<BN>(M, N);
+  const int grid = persistent_grid<BN, CG>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
   switch (e.act) {
-    case ACT_RELU: return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD>(m, ep, grid, stream);
-    case ACT_TANH: return launch_kernel<PASSES, BN, ACT_TANH, EPI_STD>(m, ep, grid, stream);
-    case ACT_EXPNEG2_RELU: return launch_kernel<PASSES, BN, ACT_EXPNEG2_RELU, EPI_STD>(m, ep, grid, stream);
-    default: return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD>(m, ep, grid, stream);
+    case ACT_RELU: return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG>(m, ep, grid, stream);
+    case ACT_TANH: return launch_kernel<PASSES, BN, ACT_TANH, EPI_STD, CG>(m, ep, grid, stream);
+    case ACT_EXPNEG2_RELU: return launch_kernel<PASSES, BN, ACT_EXPNEG2_RELU, EPI_STD, CG>(m, ep, grid, stream);
+    default: return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, CG>(m, ep, grid, stream);
   }
 }
 
-template <int PASSES>
+template <int PASSES, int CG>
 static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K, const float* bias,
                          const LogitsSelect& sel, cudaStream_t stream) {
   constexpr int BN = 256;
   Maps m;
-  ISC_TRY((make_maps<PASSES, BN>(m, A, W, M, N, K)));
+  ISC_TRY((make_maps<PASSES, BN, CG>(m, A, W, M, N, K)));
   EpiParams ep;
   memset(&ep, 0, sizeof(ep));
   ep.bias = bias;
@@ -619,9 +716,25 @@ static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K
   ep.N = N;
   ep.K = K;
   ep.sel = sel;
-  const int grid = persistent_grid<BN>(M, N);
+  const int grid = persistent_grid<BN, CG>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
-  return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS>(m, ep, grid, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS, CG>(m, ep, grid, stream);
+}
+
+// CTA pairs pay off on large GEMMs only (measured: 8192^3 1.41 -> 1.57 PFLOP/s x3-equivalent, logits-shaped 85 -> 75 us,
+// no change on the M = 3072 step GEMMs, which are bound by wave quantisation and fill/drain, not by operand traffic).
+static bool pair_pays(int M, int N, bool wide) {
+  const long long pair_tiles = (long long)((M + 2 * BM - 1) / (2 * BM)) * ((N + (wide ? 255 : 127)) / (wide ? 256 : 128));
+  return pair_tiles >= 3LL * (num_sms() / 2);
+}
+// ISC_GEMM_PAIR=0 forces single-CTA tiles, =1 forces CTA pairs wherever M spans more than one 128-row tile
+static int pair_mode() {
+  static int mode = -2;
+  if (mode == -2) {
+    const char* e = getenv("ISC_GEMM_PAIR");
+    mode = e ? atoi(e) : -1;
+  }
+  return mode;
 }
 
 // 128x256 tiles move 25 % fewer operand bytes per flop (a tile costs ~1.5x a 128x128 one for 2x the work) but
@@ -642,11 +755,14 @@ int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc: K=%d must be a positive multiple of 8", K);
   ISC_REQUIRE(A.hi && W.hi, "gemm_tc: bf16 hi planes missing");
   const bool wide = tc::use_wide_tiles(M, N);
+  const bool pair = M > tc::BM && (tc::pair_mode() == 1 || (tc::pair_mode() < 0 && tc::pair_pays(M, N, wide)));
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc: bf16 lo planes missing for the 3-pass mode");
-    return wide ? tc::launch<3, 256>(A, W, C, M, N, K, ep, stream) : tc::launch<3, 128>(A, W, C, M, N, K, ep, stream);
+    if (pair) return wide ? tc::launch<3, 256, 2>(A, W, C, M, N, K, ep, stream) : tc::launch<3, 128, 2>(A, W, C, M, N, K, ep, stream);
+    return wide ? tc::launch<3, 256, 1>(A, W, C, M, N, K, ep, stream) : tc::launch<3, 128, 1>(A, W, C, M, N, K, ep, stream);
   }
-  return wide ? tc::launch<1, 256>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128>(A, W, C, M, N, K, ep, stream);
+  if (pair) return wide ? tc::launch<1, 256, 2>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 2>(A, W, C, M, N, K, ep, stream);
+  return wide ? tc::launch<1, 256, 1>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 1>(A, W, C, M, N, K, ep, stream);
 }
 
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
@@ -654,11 +770,12 @@ int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int 
   if (M <= 0 || N <= 0) return 0;
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_logits: K=%d must be a positive multiple of 8", K);
   ISC_REQUIRE(A.hi && W.hi && sel.rec && sel.np == logits_slices(N), "gemm_tc_logits: planes / records missing");
+  const bool pair = tc::pair_mode() == 1 && M > tc::BM;
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc_logits: bf16 lo planes missing for the 3-pass mode");
-    return tc::launch_logits<3>(A, W, M, N, K, bias, sel, stream);
+    return pair ? tc::launch_logits<3, 2>(A, W, M, N, K, bias, sel, stream) : tc::launch_logits<3, 1>(A, W, M, N, K, bias, sel, stream);
   }
-  return tc::launch_logits<1>(A, W, M, N, K, bias, sel, stream);
+  return pair ? tc::launch_logits<1, 2>(A, W, M, N, K, bias, sel, stream) : tc::launch_logits<1, 1>(A, W, M, N, K, bias, sel, stream);
 }
 
 }  // namespace isc
