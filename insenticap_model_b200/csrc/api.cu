@@ -218,6 +218,7 @@ struct Planes {
 };
 struct DecodeWs {
   float *X1, *X2, *gates, *gates2, *hproj, *cs, *g3, *logits;  // gates2 == gates unless a tape keeps both
+  bool tape;  // training: the gate pre-activations must be kept, so the LSTM cell is not fused into the GEMM
   Planes pX1, pX2, pcs, phL;
   float* state_h[2];
   float* state_c[2];
@@ -259,6 +260,7 @@ DecodeWs carve_decode(const isc_dims_t& d, int precision, int M, void* base) {
   planes(w.pX2, m * 3 * H);
   w.gates = b.take<float>(m * G4);
   w.gates2 = w.gates;
+  w.tape = false;
   w.hproj = b.take<float>(m * 3 * H);
   w.cs = b.take<float>(m * 2 * H);
   planes(w.pcs, m * 2 * H);
@@ -381,8 +383,21 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
   RowDest x2 = rowdest(w.X2, 3 * H, w.pX2, 3 * H);
   ISC_TRY(launch_embed_pack(io.it, io.parent, io.h_in, M, c.d.vocab, pk.emb, x1, x2, c.s));
 
+  const bool fuse_lstm = c.precision != ISC_PREC_FP32 && !w.tape;  // LSTM cell inside the gate GEMM's epilogue
+  const int passes = c.precision == ISC_PREC_BF16X3 ? 3 : 1;
   // attention LSTM
-  {
+  if (fuse_lstm) {
+    LstmEpilogue le;
+    le.parent = io.parent;
+    le.c_prev = io.c_in;
+    le.h_out = io.h_out;
+    le.c_out = io.c_out;
+    le.x_hi = w.pX2.hi;  // h_att is the middle third of the language LSTM's operand
+    le.x_lo = w.pX2.lo;
+    le.ldx = 3 * H;
+    le.x_col = H;
+    ISC_TRY(gemm_tc_lstm(operand(nullptr, 0, w.pX1, 3 * H), pk.W1.op(), M, 3 * H, passes, nullptr, f.pre_gates, G4, R, le, c.s));
+  } else {
     Epilogue ep;
     ep.rowadd = f.pre_gates;
     ep.ld_rowadd = G4;
@@ -449,7 +464,20 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     ISC_TRY(launch_gate_mix(w.g3, w.cs, pk.alpha_g, pk.alpha_g_b, x2, io.gate_w, io.ld_gate_w, M, c.s));
   }
   // language LSTM
-  {
+  if (fuse_lstm) {
+    LstmEpilogue le;
+    le.parent = io.parent;
+    le.c_prev = io.c_in + m * H;
+    le.h_out = io.h_out + m * H;
+    le.c_out = io.c_out + m * H;
+    le.x_hi = w.phL.hi;  // h_lang (after dropout, if any) is the classifier's operand
+    le.x_lo = w.phL.lo;
+    le.ldx = H;
+    le.x_col = 0;
+    le.mask = io.out_mask;
+    le.scale = io.drop_scale;
+    ISC_TRY(gemm_tc_lstm(operand(nullptr, 0, w.pX2, 3 * H), pk.W4.op(), M, 3 * H, passes, pk.b4, nullptr, 0, 1, le, c.s));
+  } else {
     Epilogue ep;
     ep.bias = pk.b4;
     Dest dst;
@@ -1371,6 +1399,7 @@ DecodeWs tape_view(const TrainWs& w, int t, int B) {
   v.pX2 = pl(w.pX2, 3 * H);
   v.pcs = pl(w.pcs, 2 * H);
   v.phL = pl(w.phL, H);
+  v.tape = true;
   v.gates = w.gates1 + r0 * G4;
   v.gates2 = w.gates2 + r0 * G4;
   v.hproj = w.hproj + r0 * 3 * H;

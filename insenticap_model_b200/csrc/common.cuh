@@ -123,6 +123,25 @@ int gemm_simt(const Operand& A, const Operand& W, const Dest& C, int M, int N, i
               const Epilogue& ep, cudaStream_t stream);
 int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, int passes,
             const Epilogue& ep, cudaStream_t stream);
+// LSTM cell fused into the gate GEMM's epilogue (nn.LSTMCell, gate order i,f,g,o): the [M,4H] pre-activations are
+// never written. The B tile of a 128-column output tile is loaded as 8 boxes of 16 weight rows —
+// [i f g o] of hidden units 32t..32t+15, then [i f g o] of units 32t+16..32t+31 — so the thread that owns a row and
+// 64 accumulator columns holds all four gates of 16 units. The weight matrix keeps the reference's row order.
+struct LstmEpilogue {
+  const int* parent = nullptr;   // [M] row of the previous state this row continues from (beam reorder), or null
+  const float* c_prev = nullptr; // [*, H]
+  float* h_out = nullptr;        // [M, H]
+  float* c_out = nullptr;        // [M, H]
+  __nv_bfloat16* x_hi = nullptr; // h also goes, as bf16 planes, into the next GEMM's operand [M, ldx] at column x_col
+  __nv_bfloat16* x_lo = nullptr;
+  long long ldx = 0;
+  int x_col = 0;
+  const unsigned char* mask = nullptr;  // dropout keep mask [M, H] on that copy only (captioner.py:182), or null
+  float scale = 1.0f;
+};
+int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,
+                 int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream);
+
 // tensor-core GEMM whose epilogue emits LogitsSelect records instead of C (bias added; N = vocabulary)
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
                    const LogitsSelect& sel, cudaStream_t stream);

@@ -57,7 +57,7 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-enum { EPI_STD = 0, EPI_LOGITS = 1 };
+enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2 };
 
 struct EpiParams {
   const float* bias;
@@ -75,6 +75,8 @@ struct EpiParams {
   int M, N, K;
   // EPI_LOGITS: per (row, 128-column slice) online-softmax partials + top candidates instead of the logits
   LogitsSelect sel;
+  // EPI_LSTM: the LSTM cell applied to the four gate pre-activations of each hidden unit
+  LstmEpilogue lstm;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -311,6 +313,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (PASSES == 3) tma_load_2d_pair(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
             tma_load_2d_pair(stb, &map_b_hi, &full_bar[s], k0, n0);
             if (PASSES == 3) tma_load_2d_pair(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+          } else if (EPI == EPI_LSTM) {
+            // gate-interleaved B tile: box q = 16 weight rows of gate (q & 3) for the unit half (q >> 2) of this tile
+            mbar_expect_tx(&full_bar[s], C::kStageBytes);
+            tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
+            if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
+            const int u0 = (tile % tiles_n) * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int wrow = (q & 3) * (ep.N >> 2) + u0 + (q >> 2) * 16;
+              tma_load_2d(stb + q * 16 * BK * 2, &map_b_hi, &full_bar[s], k0, wrow);
+              if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes + q * 16 * BK * 2, &map_b_lo, &full_bar[s], k0, wrow);
+            }
           } else {
             mbar_expect_tx(&full_bar[s], C::kStageBytes);
             tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
@@ -443,6 +457,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
       __syncwarp();  // bias slice is rewritten for the next tile
+    }
+  } else if (EPI == EPI_LSTM) {
+    // ===================== epilogue: LSTM cell on the gate pre-activations (tile columns = [i f g o] x 16 units, twice) =====
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int half = ew >> 2;      // which 16 of the tile's 32 hidden units
+    const LstmEpilogue& L = ep.lstm;
+    const int HH = ep.N >> 2;      // hidden size
+    int j = 0;
+    for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
+      const int m0 = (tile / tiles_n) * BM;
+      const int u0 = (tile % tiles_n) * 32 + half * 16;  // first hidden unit of this thread
+      const int as = j & 1;
+      const long long row = m0 + quarter * 32 + lane;
+      const bool live = row < ep.M;
+      const long long src = (live && L.parent) ? L.parent[row] : row;
+      float cp[16];
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(L.c_prev + src * HH + u0) + q);
+          cp[4 * q] = t.x; cp[4 * q + 1] = t.y; cp[4 * q + 2] = t.z; cp[4 * q + 3] = t.w;
+        }
+      }
+      const float* radd = ep.rowadd ? ep.rowadd + (long long)((unsigned)row / (unsigned)ep.rows_per_group) * ep.ld_rowadd : nullptr;
+      mbar_wait(&acc_full[as], (j >> 1) & 1);
+      tcgen05_fence_after();
+      float vif[32], vgo[32];  // [i(16) | f(16)], [g(16) | o(16)]
+      const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * 64;
+      tmem_ld32(tcol, vif);
+      tmem_ld32(tcol + 32, vgo);
+      // the accumulator stage is drained: release it to the MMA warp before the math and the stores
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+      if (live) {
+        // same association as the unfused path: (acc + bias) + rowadd, then nn.LSTMCell's pointwise math
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float* v = (g < 2 ? vif : vgo) + (g & 1) * 16;
+          const int col = g * HH + u0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (ep.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + q);
+              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            }
+            if (radd) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(radd + col) + q);
+              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+          }
+        }
+        float hn[16], cn[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          cn[u] = sigmoid_accurate(vif[16 + u]) * cp[u] + sigmoid_accurate(vif[u]) * tanhf(vgo[u]);
+          hn[u] = sigmoid_accurate(vgo[16 + u]) * tanhf(cn[u]);
+        }
+        float4* co = reinterpret_cast<float4*>(L.c_out + row * HH + u0);
+        float4* ho = reinterpret_cast<float4*>(L.h_out + row * HH + u0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          co[q] = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+          ho[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+        }
+        if (L.x_hi) {
+          if (L.mask) {
+            const uint4 k = __ldg(reinterpret_cast<const uint4*>(L.mask + row * HH + u0));
+            const unsigned char* kb = reinterpret_cast<const unsigned char*>(&k);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) hn[u] *= kb[u] ? L.scale : 0.f;
+          }
+          __align__(16) __nv_bfloat16 hh[16], ll[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) split_bf16(hn[u], hh[u], ll[u]);
+          uint4* dh = reinterpret_cast<uint4*>(L.x_hi + row * L.ldx + L.x_col + u0);
+          dh[0] = reinterpret_cast<const uint4*>(hh)[0];
+          dh[1] = reinterpret_cast<const uint4*>(hh)[1];
+          if (L.x_lo) {
+            uint4* dl = reinterpret_cast<uint4*>(L.x_lo + row * L.ldx + L.x_col + u0);
+            dl[0] = reinterpret_cast<const uint4*>(ll)[0];
+            dl[1] = reinterpret_cast<const uint4*>(ll)[1];
+          }
+        }
+      }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> global =====================
@@ -721,6 +821,37 @@ static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS, CG>(m, ep, grid, stream);
 }
 
+template <int PASSES>
+static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const float* bias, const float* rowadd,
+                       int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream) {
+  constexpr int BN = 128;
+  using C = Cfg<PASSES, BN, 1>;
+  const int N = 4 * H;
+  Maps m;
+  ISC_TRY(make_map(&m.a_hi, A.hi, M, K, A.ldp, BM, C::kBK));
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, 16, C::kBK));  // 16-row boxes: see the EPI_LSTM producer
+  if (PASSES == 3) {
+    ISC_TRY(make_map(&m.a_lo, A.lo, M, K, A.ldp, BM, C::kBK));
+    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, 16, C::kBK));
+  } else {
+    m.a_lo = m.a_hi;
+    m.b_lo = m.b_hi;
+  }
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias;
+  ep.rowadd = rowadd;
+  ep.ld_rowadd = ld_rowadd;
+  ep.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  ep.M = M;
+  ep.N = N;
+  ep.K = K;
+  ep.lstm = lstm;
+  const int grid = persistent_grid<BN, 1>(M, N);
+  ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_LSTM, 1>(m, ep, grid, stream);
+}
+
 // CTA pairs pay off on large GEMMs only (measured: 8192^3 1.41 -> 1.57 PFLOP/s x3-equivalent, logits-shaped 85 -> 75 us,
 // no change on the M = 3072 step GEMMs, which are bound by wave quantisation and fill/drain, not by operand traffic).
 static bool pair_pays(int M, int N, bool wide) {
@@ -763,6 +894,23 @@ int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int
   }
   if (pair) return wide ? tc::launch<1, 256, 2>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 2>(A, W, C, M, N, K, ep, stream);
   return wide ? tc::launch<1, 256, 1>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 1>(A, W, C, M, N, K, ep, stream);
+}
+
+int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,
+                 int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_lstm: K=%d must be a positive multiple of 8", K);
+  ISC_REQUIRE(A.hi && W.hi && lstm.c_prev && lstm.h_out && lstm.c_out, "gemm_tc_lstm: planes / state buffers missing");
+  ISC_REQUIRE(!lstm.x_hi || ((lstm.ldx % 8) == 0 && (lstm.x_col % 8) == 0 && (reinterpret_cast<uintptr_t>(lstm.x_hi) & 15) == 0),
+              "gemm_tc_lstm: operand planes must be 16-byte aligned");
+  ISC_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm_tc_lstm: bias must be 16-byte aligned");
+  ISC_REQUIRE(!rowadd || ((reinterpret_cast<uintptr_t>(rowadd) & 15) == 0 && (ld_rowadd & 3) == 0),
+              "gemm_tc_lstm: rowadd must be 16-byte aligned");
+  if (passes == 3) {
+    ISC_REQUIRE(A.lo && W.lo, "gemm_tc_lstm: bf16 lo planes missing for the 3-pass mode");
+    return tc::launch_lstm<3>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+  }
+  return tc::launch_lstm<1>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
 }
 
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,

@@ -149,6 +149,7 @@ __device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kCh
 // One warp scores items l = warp, warp + n_warps, ...  The item's 512-wide row is staged gmem -> smem with
 // cp.async (no registers held across the long SFU-bound scoring of the previous row): a 2-slot ring per warp.
 // Every lane reads back exactly the 16-byte chunks it copied itself, so no cross-lane barrier is needed.
+constexpr int kRing = 2;  // staging slots per warp in score_rows (3 was measured: the smem costs a CTA per SM, 2.83 -> 3.09 ms)
 template <typename FeatT, int TANH_MODE, int RT>
 __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
                                            const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
@@ -171,14 +172,17 @@ __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // kRing slots, kRing - 1 rows in flight per warp
   prefetch(warp, 0);
+  if (kRing > 2) prefetch(warp + n_warps, 1);
   int it = 0;
   for (int l = warp; l < n_items; l += n_warps, ++it) {
-    prefetch(l + n_warps, (it + 1) & 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    prefetch(l + (kRing - 1) * n_warps, (it + kRing - 1) % kRing);
+    if (kRing > 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 1;" ::: "memory");
     float pv[L::kChunks][L::kWidth];
 #pragma unroll
-    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it & 1) * H, lane, i, pv[i]);
+    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it % kRing) * H, lane, i, pv[i]);
     score_one<FeatT, TANH_MODE, RT>(pv, al, l, n_items, R, q_smem, score_smem, lane);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -313,9 +317,9 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   const FeatT* p_att = reinterpret_cast<const FeatT*>(p.p_att);
   if (att)
     score_rows<FeatT, TANH_MODE, RT>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c,
-                                     reinterpret_cast<FeatT*>(ring_base + warp * 2 * H), warp, lane, 8);
+                                     reinterpret_cast<FeatT*>(ring_base + warp * kRing * H), warp, lane, 8);
   if (p.sw)
-    score_rows<float, TANH_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring_base + warp * 2 * H,
+    score_rows<float, TANH_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring_base + warp * kRing * H,
                                      warp, lane, 8);
   __syncthreads();
   if (att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
@@ -344,7 +348,7 @@ int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode,
   ISC_REQUIRE(p.R >= 1 && p.R <= 8, "attention: rows per image %d not in 1..8", p.R);
   ISC_REQUIRE((bf16_feats && tanh_mode == 2) || (!bf16_feats && tanh_mode != 2), "attention: feature dtype / tanh mode mismatch");
   const int Lp = (p.L + 3) & ~3, Sp = (p.S + 3) & ~3;
-  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp + 8 * 2 * H);
+  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp + 8 * kRing * H);
   // algorithmic HBM bytes: both feature tensors of every image once per launch (shared by its R rows),
   // sentiment-word features, the R query rows in and the R context rows out
   const double feat_b = bf16_feats ? 2.0 : 4.0;

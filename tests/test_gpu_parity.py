@@ -30,7 +30,8 @@ def _cfg1():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 @pytest.mark.parametrize("shape", [(300, 200, 136), (128, 128, 64), (1, 10000, 512), (640, 512, 2048), (3072, 2048, 1536),
-                                   (3072, 1536, 512), (18816, 512, 64)])  # the last two take the 128x256-tile kernel
+                                   (3072, 1536, 512), (18816, 512, 64),  # these two take the 128x256-tile kernel
+                                   (8192, 4096, 128)])  # large enough for CTA pairs (cta_group::2) by default
 def test_gemm(precision, shape):
     import ctypes as C
     from insenticap_model_b200 import _lib
@@ -58,6 +59,20 @@ def test_gemm(precision, shape):
         ref = [ref, ref.clamp(min=0), ref.tanh()][act]
         err = (out.cpu().double() - ref).abs()
         assert bool((err <= tol).all()), (precision, shape, act, err.max().item(), (err / tol).max().item())
+
+
+def test_gemm_and_decode_with_cta_pairs_forced():
+    """ISC_GEMM_PAIR=1 routes every multi-tile GEMM through the cta_group::2 kernel (cluster of 2, 256-row tiles):
+    the GEMM shapes and the golden beam / greedy decodes must hold there too (run in a subprocess: the switch is
+    read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
+                        "test_gemm and not pairs or cfg1_matches or ragged"], cwd=root, capture_output=True, text=True,
+                       env=dict(os.environ, ISC_GEMM_PAIR="1"), timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 @pytest.mark.parametrize("precision", EXACT)
