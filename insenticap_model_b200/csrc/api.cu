@@ -1198,16 +1198,17 @@ struct TrainWs {
   PM pX1, pX2, pcs, phL;     // [T*M][.]
   float *gates1, *gates2, *hproj, *cs, *g3, *gate_w, *cont_w, *senti_w;
   // backward scratch
-  float* dlogits;  // [M][Vp]
-  PM pdlog;        // [M][Vp]
+  float* dlogits;  // [T*M][Vp], step-major
+  PM pdlog;        // [T*M][Vp]
   PM dlogT;        // [V][TMp]
+  float* dh_all;   // [T*M][H] d h_lang through the classifier, all steps
   float* dh_tmp;   // [M][H]
   float* dX1[2];   // [M][3H]
   float* dX2[2];
-  float *dg1, *dg2;  // [M][4H]
+  float *dg1, *dg2;  // [T*M][4H]: all steps (bias colsums and transposed planes are taken once, after the loop)
   PM pdg1, pdg2;
   PM dg1T, dg2T;  // [4H][TMp]
-  float* dhproj;  // [M][3H]
+  float* dhproj;  // [T*M][3H], all steps
   PM pdhproj;
   PM dhprojT;  // [3H][TMp]
   float* dcs;  // [M][2H]
@@ -1278,21 +1279,22 @@ TrainWs carve_train(const isc_dims_t& d, int precision, int B, int T, void* base
   w.gate_w = b.take<float>(tm);
   w.cont_w = b.take<float>(tm * L);
   w.senti_w = b.take<float>(tm * S);
-  w.dlogits = b.take<float>(m * w.Vp);
-  pm(w.pdlog, m, w.Vp);
+  w.dlogits = b.take<float>((size_t)T * m * w.Vp);
+  pm(w.pdlog, (size_t)T * m, w.Vp);
+  w.dh_all = b.take<float>((size_t)T * m * H);
   pm(w.dlogT, V, w.TMp);
   w.dh_tmp = b.take<float>(m * H);
   for (int i = 0; i < 2; ++i) {
     w.dX1[i] = b.take<float>(m * 3 * H);
     w.dX2[i] = b.take<float>(m * 3 * H);
   }
-  w.dg1 = b.take<float>(m * G4);
-  w.dg2 = b.take<float>(m * G4);
+  w.dg1 = b.take<float>((size_t)T * m * G4);
+  w.dg2 = b.take<float>((size_t)T * m * G4);
   pm(w.pdg1, m, G4);
   pm(w.pdg2, m, G4);
   pm(w.dg1T, G4, w.TMp);
   pm(w.dg2T, G4, w.TMp);
-  w.dhproj = b.take<float>(m * 3 * H);
+  w.dhproj = b.take<float>((size_t)T * m * 3 * H);
   pm(w.pdhproj, m, 3 * H);
   pm(w.dhprojT, 3 * H, w.TMp);
   w.dcs = b.take<float>(m * 2 * H);
@@ -1551,10 +1553,10 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     ISC_CUDA(zf(w.dp_sw, (size_t)M * S * H));
     ISC_CUDA(zf(w.dpre_word, (size_t)M * H));
     ISC_CUDA(zf(w.dpre_gates, (size_t)M * G4));
-    ISC_CUDA(zf(w.dhproj, (size_t)M * 3 * H));
-    ISC_CUDA(zf(w.dlogits, (size_t)M * w.Vp));
+    ISC_CUDA(zf(w.dhproj, (size_t)TM * 3 * H));
+    if (w.Vp != V) ISC_CUDA(zf(w.dlogits, (size_t)TM * w.Vp));  // pad columns must read as zero
     ISC_TRY(zero_pm(w.pdhproj, M, s));
-    ISC_TRY(zero_pm(w.pdlog, M, s));
+
     ISC_TRY(zero_pm(w.dlogT, V, s));
     ISC_TRY(zero_pm(w.dg1T, G4, s));
     ISC_TRY(zero_pm(w.dg2T, G4, s));
@@ -1564,6 +1566,15 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     ISC_TRY(zero_pm(w.csT, 2 * H, s));
     ISC_TRY(zero_pm(w.hLT, H, s));
 
+    // ---- classifier backward for ALL steps at once (none of it depends on the recurrence): d logits from the
+    // log-softmax backward, their planes (operand of d h_lang = d logits . W5) and transposed planes (operand of dW5)
+    ISC_TRY(launch_logsoftmax_bwd(logprobs, dlogprobs, reinterpret_cast<const long long*>(targets), ld_targets, coef, T, M, (int)V,
+                                  w.dlogits, w.Vp, s));
+    ISC_TRY(split_planes(w.dlogits, w.Vp, w.pdlog.hi, w.pdlog.lo, w.Vp, TM, (int)w.Vp, s));
+    ISC_TRY(to_T(w.dlogits, w.Vp, TM, (int)V, w.dlogT, 0, s));
+    if (g->classifier_b) ISC_TRY(launch_colsum_add(w.dlogits, w.Vp, TM, (int)V, g->classifier_b, nullptr, s));
+    ISC_TRY(pgemm(precision, op_of(w.pdlog), op_of(w.W5T), w.dh_all, H, (int)TM, H, (int)w.Vp, false, s));
+
     // which slice of the h projections is live: [cont h2att | senti h2word | gate h2att]
     const int hp0 = tm.att ? 0 : H, hpn = (tm.att && tm.sw) ? 3 * H : H;
 
@@ -1572,21 +1583,13 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       const long long r0 = (long long)t * M;
       const float* h_prev_c = w.state_c + (size_t)t * 2 * M * H;
       const float* c_new = w.state_c + (size_t)(t + 1) * 2 * M * H;
-      // 1. log_softmax backward -> d logits (fp32, planes, transposed planes), classifier bias grad
-      ISC_TRY(launch_logsoftmax_bwd(logprobs + t * V, (long long)T * V, dlogprobs ? dlogprobs + t * V : nullptr, (long long)T * V,
-                                    reinterpret_cast<const long long*>(targets) + (targets ? t : 0), ld_targets,
-                                    coef ? coef + t : nullptr, T, M, (int)V, w.dlogits, w.Vp, s));
-      ISC_TRY(split_planes(w.dlogits, w.Vp, w.pdlog.hi, w.pdlog.lo, w.Vp, M, (int)w.Vp, s));  // pad columns stay zero
-      ISC_TRY(to_T(w.dlogits, w.Vp, M, (int)V, w.dlogT, r0, s));
-      if (g->classifier_b) ISC_TRY(launch_colsum_add(w.dlogits, w.Vp, M, (int)V, g->classifier_b, nullptr, s));
-      // 2. d h_lang (through the classifier)
-      ISC_TRY(pgemm(precision, op_of(w.pdlog), op_of(w.W5T), w.dh_tmp, H, M, H, (int)w.Vp, false, s));
+      float* dg1 = w.dg1 + r0 * G4;        // this step's slices of the all-steps gradient matrices
+      float* dg2 = w.dg2 + r0 * G4;
+      float* dhproj = w.dhproj + r0 * 3 * H;
       // 3. language LSTM backward
-      ISC_TRY(launch_lstm_bwd(w.gates2 + r0 * G4, h_prev_c + (size_t)M * H, c_new + (size_t)M * H, w.dh_tmp, H,
+      ISC_TRY(launch_lstm_bwd(w.gates2 + r0 * G4, h_prev_c + (size_t)M * H, c_new + (size_t)M * H, w.dh_all + r0 * H, H,
                               (dropout && dropout->out) ? dropout->out + (size_t)t * M * H : nullptr, dscale, w.dX1[nxt], 3 * H,
-                              w.dX2[nxt] + 2 * H, 3 * H, w.dc_lang, w.dg2, rd_of(nullptr, 0, w.pdg2), M, s));
-      ISC_TRY(to_T(w.dg2, G4, M, G4, w.dg2T, r0, s));
-      ISC_TRY(launch_colsum_add(w.dg2, G4, M, G4, g->lang_lstm_b_ih, g->lang_lstm_b_hh, s));
+                              w.dX2[nxt] + 2 * H, 3 * H, w.dc_lang, dg2, rd_of(nullptr, 0, w.pdg2), M, s));
       // 4. d [ctx | h_att | h_lang_prev]
       ISC_TRY(pgemm(precision, op_of(w.pdg2), op_of(w.W4T), w.dX2[cur], 3 * H, M, 3 * H, G4, false, s));
       // 5. gate
@@ -1595,7 +1598,7 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       int cont_col = 0, senti_col = 0;
       if (tm.att && tm.sw) {
         ISC_TRY(launch_gate_bwd(w.dX2[cur], 3 * H, w.cs + r0 * 2 * H, w.g3 + r0 * H, w.gate_w + r0, pk.alpha_g, w.dcs,
-                                rd_of(w.dhproj, 3 * H, w.pdhproj), 2 * H, g->g_alpha_w, g->g_alpha_b, M, s));
+                                rd_of(dhproj, 3 * H, w.pdhproj), 2 * H, g->g_alpha_w, g->g_alpha_b, M, s));
         ISC_TRY(pgemm(precision, op_of(w.pdhproj, 0, 2 * H), op_of(w.W3T), w.dcs, 2 * H, M, 2 * H, H, true, s));
         dcs = w.dcs;
         ld_dcs = 2 * H;
@@ -1631,29 +1634,33 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
         ab.dalpha_s = g->sa_alpha_w;
         ab.dpre_word = w.dpre_word;
       }
-      ab.dhproj = rd_of(w.dhproj, 3 * H, w.pdhproj);
+      ab.dhproj = rd_of(dhproj, 3 * H, w.pdhproj);
       ISC_TRY(launch_attention_bwd(ab, M, s));
-      ISC_TRY(to_T(w.dhproj + hp0, 3 * H, M, hpn, rows_from(w.dhprojT, hp0), r0, s));
-      if (tm.att) ISC_TRY(launch_colsum_add(w.dhproj, 3 * H, M, H, g->ca_h2att_b, nullptr, s));
-      if (tm.sw) ISC_TRY(launch_colsum_add(w.dhproj + H, 3 * H, M, H, g->sa_h2word_b, nullptr, s));
-      if (tm.att && tm.sw) {
-        ISC_TRY(launch_colsum_add(w.dhproj + 2 * H, 3 * H, M, H, g->g_h2att_b, g->g_cont2att_b, s));
-        ISC_TRY(launch_colsum_add(w.dhproj + 2 * H, 3 * H, M, H, g->g_senti2att_b, nullptr, s));
-      }
       // 7. d h_att through the projections
       ISC_TRY(pgemm(precision, op_of(w.pdhproj, 0, hp0), op_of(w.W2T, 0, hp0), w.dh_tmp, H, M, H, hpn, false, s));
       // 8. attention LSTM backward
       ISC_TRY(launch_lstm_bwd(w.gates1 + r0 * G4, h_prev_c, c_new, w.dh_tmp, H, nullptr, 1.f, w.dX2[cur] + H, 3 * H,
-                              w.dX1[nxt] + 2 * H, 3 * H, w.dc_att, w.dg1, rd_of(nullptr, 0, w.pdg1), M, s));
-      ISC_TRY(to_T(w.dg1, G4, M, G4, w.dg1T, r0, s));
-      ISC_TRY(launch_colsum_add(w.dg1, G4, M, G4, g->att_lstm_b_ih, g->att_lstm_b_hh, s));
-      ISC_TRY(launch_add2d(w.dpre_gates, G4, w.dg1, G4, M, G4, s));
+                              w.dX1[nxt] + 2 * H, 3 * H, w.dc_att, dg1, rd_of(nullptr, 0, w.pdg1), M, s));
       // 9. d [h_lang_prev | xt | h_att_prev]
       ISC_TRY(pgemm(precision, op_of(w.pdg1), op_of(w.W1T), w.dX1[cur], 3 * H, M, 3 * H, G4, false, s));
       // 10. word embedding of this step's input tokens
       ISC_TRY(launch_embed_bwd(w.it + (size_t)t * M, 1, M, 1, 0, dims->pad_id, 1, (int)V, pk.emb, w.dX1[cur] + H, 3 * H, 1, nullptr,
                                1.f, 1.f, g->word_embed, s));
     }
+
+    // ---- bias gradients and transposed planes of the all-steps gradient matrices, once
+    ISC_TRY(launch_colsum_add(w.dg2, G4, TM, G4, g->lang_lstm_b_ih, g->lang_lstm_b_hh, s));
+    ISC_TRY(launch_colsum_add(w.dg1, G4, TM, G4, g->att_lstm_b_ih, g->att_lstm_b_hh, s));
+    ISC_TRY(to_T(w.dg2, G4, TM, G4, w.dg2T, 0, s));
+    ISC_TRY(to_T(w.dg1, G4, TM, G4, w.dg1T, 0, s));
+    ISC_TRY(to_T(w.dhproj + hp0, 3 * H, TM, hpn, rows_from(w.dhprojT, hp0), 0, s));
+    if (tm.att) ISC_TRY(launch_colsum_add(w.dhproj, 3 * H, TM, H, g->ca_h2att_b, nullptr, s));
+    if (tm.sw) ISC_TRY(launch_colsum_add(w.dhproj + H, 3 * H, TM, H, g->sa_h2word_b, nullptr, s));
+    if (tm.att && tm.sw) {
+      ISC_TRY(launch_colsum_add(w.dhproj + 2 * H, 3 * H, TM, H, g->g_h2att_b, g->g_cont2att_b, s));
+      ISC_TRY(launch_colsum_add(w.dhproj + 2 * H, 3 * H, TM, H, g->g_senti2att_b, nullptr, s));
+    }
+    ISC_TRY(launch_sum_steps(w.dg1, T, (long long)M * G4, (long long)M * G4, w.dpre_gates, s));  // hoisted pre_gates: sum over steps
 
     // ---- weight gradients: one contraction over all T*B rows per matrix
     ISC_TRY(planes_T(w.pX1, TM, 3 * H, w.X1T, s));

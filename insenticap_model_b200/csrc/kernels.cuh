@@ -150,9 +150,8 @@ struct AttnBwdParams {
   float* dpre_word = nullptr;
   float* dalpha_c = nullptr; float* dalpha_s = nullptr;
 };
-int launch_logsoftmax_bwd(const float* logp, long long ld_logp, const float* dlogp, long long ld_dlogp, const long long* target,
-                          long long ld_target, const float* coef, long long ld_coef, int M, int V, float* dlogits,
-                          long long ld_out, cudaStream_t s);
+int launch_logsoftmax_bwd(const float* logp, const float* dlogp, const long long* target, long long ld_target,
+                          const float* coef, int T, int M, int V, float* dlogits, long long ld_out, cudaStream_t s);
 int launch_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh_a, long long ld_a,
                     const unsigned char* mask, float scale, const float* dh_b, long long ld_b, const float* dh_c,
                     long long ld_c, float* dc_carry, float* dgates, RowDest planes, int M, cudaStream_t s);

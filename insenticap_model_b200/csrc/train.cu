@@ -15,15 +15,18 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // Dense form: dlogp row given. Fused-loss form (dlogp == null): the loss is sum coef[m] * (-logp[m, target[m]]), so
 // d logp is -coef at the target and the row sum is -coef.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __restrict__ logp, long long ld_logp,
-                                                             const float* __restrict__ dlogp, long long ld_dlogp,
+// Input rows live in the [B, T, V] tensors (row b * T + t); output row blockIdx.x = t * M + b (step-major, the order of
+// the tape), so one launch covers every step and the classifier's backward GEMMs contract over all T * B rows at once.
+__global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __restrict__ logp, const float* __restrict__ dlogp,
                                                              const long long* __restrict__ target, long long ld_target,
-                                                             const float* __restrict__ coef, long long ld_coef, int V,
+                                                             const float* __restrict__ coef, int T, int M, int V,
                                                              float* __restrict__ dlogits, long long ld_out) {
   __shared__ float red[8];
-  const long long m = blockIdx.x;
+  const int t = blockIdx.x / M, b = blockIdx.x - t * M;
+  const long long m = (long long)b * T + t;  // row in the [B, T, .] inputs
+  const long long ld_logp = V, ld_dlogp = V, ld_coef = 1;
   const float* lp = logp + m * ld_logp;
-  float* out = dlogits + m * ld_out;
+  float* out = dlogits + (long long)blockIdx.x * ld_out;
   float s = 0.f;
   int tgt = -1;
   float cf = 0.f;
@@ -37,7 +40,7 @@ __global__ void __launch_bounds__(256) logsoftmax_bwd_kernel(const float* __rest
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i];
   } else {
-    tgt = (int)target[m * ld_target];
+    tgt = (int)target[(long long)b * ld_target + t];
     cf = coef[m * ld_coef];
     s = -cf;
   }
@@ -383,23 +386,25 @@ __global__ void apply_mask_kernel(float* __restrict__ x, long long ld, const uns
   }
 }
 
-// dst[c] += sum_r src[r, c]; one block per 32 columns, 8 row-lanes
+// dst[c] += sum_r src[r, c]; a block sums 32 columns x up to 512 rows (8 row-lanes) and adds its partial atomically
 __global__ void __launch_bounds__(256) colsum_add_kernel(const float* __restrict__ src, long long ld, long long rows, int cols,
                                                          float* __restrict__ dst, float* __restrict__ dst2) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int ry = threadIdx.x >> 5;
+  const long long r_begin = (long long)blockIdx.y * 512;
+  const long long r_end = r_begin + 512 < rows ? r_begin + 512 : rows;
   float s = 0.f;
   if (c < cols)
-    for (long long r = ry; r < rows; r += 8) s += src[r * ld + c];
+    for (long long r = r_begin + ry; r < r_end; r += 8) s += src[r * ld + c];
   red[ry][threadIdx.x & 31] = s;
   __syncthreads();
   if (ry == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x & 31];
-    dst[c] += t;
-    if (dst2) dst2[c] += t;
+    atomicAdd(dst + c, t);
+    if (dst2) atomicAdd(dst2 + c, t);
   }
 }
 
@@ -503,11 +508,10 @@ int grid_for(long long n, int per_block = 256) {
 }  // namespace
 
 // ------------------------------------------------------------------ host launchers
-int launch_logsoftmax_bwd(const float* logp, long long ld_logp, const float* dlogp, long long ld_dlogp, const long long* target,
-                          long long ld_target, const float* coef, long long ld_coef, int M, int V, float* dlogits,
-                          long long ld_out, cudaStream_t s) {
-  ProfScope ps(ISC_K_TRAIN, (double)M * V * 4.0 * (dlogp ? 4 : 2), s);
-  logsoftmax_bwd_kernel<<<M, 256, 0, s>>>(logp, ld_logp, dlogp, ld_dlogp, target, ld_target, coef, ld_coef, V, dlogits, ld_out);
+int launch_logsoftmax_bwd(const float* logp, const float* dlogp, const long long* target, long long ld_target,
+                          const float* coef, int T, int M, int V, float* dlogits, long long ld_out, cudaStream_t s) {
+  ProfScope ps(ISC_K_TRAIN, (double)T * M * V * 4.0 * (dlogp ? 4 : 2), s);
+  logsoftmax_bwd_kernel<<<T * M, 256, 0, s>>>(logp, dlogp, target, ld_target, coef, T, M, V, dlogits, ld_out);
   ISC_LAUNCH_CHECK();
   return 0;
 }
@@ -583,7 +587,8 @@ int launch_apply_mask(float* x, long long ld, const unsigned char* mask, float s
 int launch_colsum_add(const float* src, long long ld, long long rows, int cols, float* dst, float* dst2, cudaStream_t s) {
   if (rows <= 0 || cols <= 0) return 0;
   ProfScope ps(ISC_K_TRAIN, (double)rows * cols * 4.0, s);
-  colsum_add_kernel<<<(cols + 31) / 32, 256, 0, s>>>(src, ld, rows, cols, dst, dst2);
+  dim3 grid((cols + 31) / 32, (unsigned)((rows + 511) / 512));
+  colsum_add_kernel<<<grid, 256, 0, s>>>(src, ld, rows, cols, dst, dst2);
   ISC_LAUNCH_CHECK();
   return 0;
 }

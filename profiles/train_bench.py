@@ -85,5 +85,25 @@ if rank == 0:
                       "ms_per_iteration": float(ms.item()), "rows_per_s": world * rows / (float(ms.item()) * 1e-3),
                       "losses": {k: float(v) for k, v in out.items()}, "replicas_in_sync": in_sync,
                       "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}), flush=True)
+# per-kernel-class device time of one more iteration (CUDA events around every launch of the library)
+if rank == 0 and os.environ.get("ISC_TRAIN_PROFILE"):
+    import ctypes as C
+    from insenticap_model_b200 import _lib
+    lib = _lib.load()
+    lib.isc_profile_reset()
+    lib.isc_profile_enable(1)
+    n0 = lib.isc_launch_count()
+    e0.record()
+    step()
+    e1.record()
+    torch.cuda.synchronize()
+    lib.isc_profile_enable(0)
+    out = {}
+    for i, name in enumerate(_lib.KERNEL_CLASSES):
+        tm, wk, n = C.c_double(), C.c_double(), C.c_int64()
+        lib.isc_profile_read(i, C.byref(tm), C.byref(wk), C.byref(n))
+        if n.value:
+            out[name] = {"ms": round(tm.value, 3), "launches": n.value}
+    print(json.dumps({"profiled_iteration_ms": e0.elapsed_time(e1), "library_launches": lib.isc_launch_count() - n0, "classes": out}))
 if world > 1:
     dist.destroy_process_group()
