@@ -232,7 +232,7 @@ struct DecodeWs {
   int* alive[2];
   float* fcsl;
   Planes pfcsl;
-  float* rec;  // LogitsSelect records of the fused logits epilogue [M][np][SEL_REC] (tensor-core precisions)
+  float* rec;  // LogitsSelect records of the fused logits epilogue [M][np][sel_rec(8)] (tensor-core precisions)
   int np;
   float* cand_lp;
   int* cand_word;
@@ -285,7 +285,7 @@ DecodeWs carve_decode(const isc_dims_t& d, int precision, int M, void* base) {
   w.fcsl = b.take<float>(m * 2 * H);
   planes(w.pfcsl, m * 2 * H);
   w.np = logits_slices(d.vocab);
-  w.rec = tc ? b.take<float>(m * w.np * SEL_REC) : nullptr;
+  w.rec = tc ? b.take<float>(m * w.np * sel_rec(SEL_K_MAX)) : nullptr;
   w.cand_lp = b.take<float>(m * 8);
   w.cand_word = b.take<int>(m * 8);
   w.cand_count = b.take<int>(m);
@@ -993,12 +993,14 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
   ISC_CUDA(cudaMemsetAsync(w.tok[0], 0, (size_t)M * T * sizeof(int), c.s));
   ISC_CUDA(cudaMemsetAsync(w.ticket, 0, (size_t)B * sizeof(int), c.s));
   ISC_TRY(launch_beam_init(w.it, w.alive[0], w.len[0], w.score[0], w.parent, B, K, dims->sos_id, c.s));
-  const bool fused = precision != ISC_PREC_FP32 && K <= SEL_K;  // masks + top-K inside the logits GEMM epilogue
+  const bool fused = precision != ISC_PREC_FP32;  // masks + top-K inside the logits GEMM epilogue
+  const int k_sel = K <= 4 ? 4 : 8;               // candidates kept per 128-column slice
   for (int t = 0; t < T; ++t) {
     StepIO io;
     if (fused) {
       io.sel.rec = w.rec;
       io.sel.np = w.np;
+      io.sel.k_sel = k_sel;
       io.sel.last = w.it;
       io.sel.constraint = decoding_constraint ? 1 : 0;
       io.sel.mask_special = dims->pad_id != dims->eos_id;
@@ -1020,6 +1022,7 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
     bp.ld = w.ld_logits;
     bp.rec = io.sel.rec;
     bp.np = io.sel.np;
+    bp.k_sel = k_sel;
     bp.B = B;
     bp.K = K;
     bp.V = dims->vocab;

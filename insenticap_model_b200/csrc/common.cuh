@@ -89,16 +89,18 @@ struct Epilogue {
 
 // Fused vocabulary-logit epilogue of the tensor-core GEMM: the [M,V] logits are never written. Every epilogue
 // thread owns one row and one 128-column slice of a 128x256 tile and emits one record
-//   {slice max, sum exp(x - max), -, -, v[SEL_K], idx[SEL_K]}     (SEL_REC floats)
-// with the SEL_K largest UNMASKED logits of the slice (value desc, column asc). A small merge kernel turns the
+//   {slice max, sum exp(x - max), -, -, v[k_sel], idx[k_sel]}     (sel_rec(k_sel) floats)
+// with the k_sel largest UNMASKED logits of the slice (value desc, column asc). A small merge kernel turns the
 // np = 2 * ceil(V / 256) records of a row into its log-softmax normaliser and its top-K (kernels_select.cu).
 // Masks follow Captioner.sample (captioner.py:394-399): PAD/SOS/UNK when pad != eos, the previous word when
 // decoding_constraint is set.
-constexpr int SEL_K = 4;
-constexpr int SEL_REC = 4 + 2 * SEL_K;
+// Two record widths: 4 candidates per slice (beams up to 4, greedy) or 8 (beams 5..8).
+constexpr int SEL_K_MAX = 8;
+__host__ __device__ constexpr int sel_rec(int ks) { return 4 + 2 * ks; }  // floats per record
 struct LogitsSelect {
-  float* rec = nullptr;             // [M][np][SEL_REC]
+  float* rec = nullptr;             // [M][np][sel_rec(k_sel)]
   int np = 0;
+  int k_sel = 4;                    // 4 or 8
   const long long* last = nullptr;  // [M] previous word per row, or null
   int constraint = 0, mask_special = 0, pad_id = 0, sos_id = 0, unk_id = 0;
 };

@@ -57,7 +57,7 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2 };
+enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2, EPI_LOGITS8 = 3 };  // EPI_LOGITS8: 8 candidates per slice
 
 struct EpiParams {
   const float* bias;
@@ -377,7 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         else umma_commit(&acc_full[as]);
       }
     }
-  } else if (EPI == EPI_LOGITS) {
+  } else if (EPI == EPI_LOGITS || EPI == EPI_LOGITS8) {
+    constexpr int SEL_K = EPI == EPI_LOGITS8 ? 8 : 4;
+    constexpr int SEL_REC = sel_rec(SEL_K);
     // ===================== epilogue: softmax partials + top candidates per (row, 128-column slice) =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
@@ -818,6 +820,7 @@ static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K
   ep.sel = sel;
   const int grid = persistent_grid<BN, CG>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  if (sel.k_sel == 8) return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS8, CG>(m, ep, grid, stream);
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS, CG>(m, ep, grid, stream);
 }
 
@@ -917,7 +920,8 @@ int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int 
                    const LogitsSelect& sel, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_logits: K=%d must be a positive multiple of 8", K);
-  ISC_REQUIRE(A.hi && W.hi && sel.rec && sel.np == logits_slices(N), "gemm_tc_logits: planes / records missing");
+  ISC_REQUIRE(A.hi && W.hi && sel.rec && sel.np == logits_slices(N) && (sel.k_sel == 4 || sel.k_sel == 8),
+              "gemm_tc_logits: planes / records missing");
   const bool pair = tc::pair_mode() == 1 && M > tc::BM;
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc_logits: bf16 lo planes missing for the 3-pass mode");

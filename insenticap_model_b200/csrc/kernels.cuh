@@ -88,7 +88,7 @@ struct GreedyParams {
   long long* it = nullptr;        // [B] next input token (written)
   int* unfinished = nullptr;      // [B] (read/write)
   int* alive_count = nullptr;     // [T] number of unfinished rows after step t
-  const float* rec = nullptr;     // fused argmax path (sample_mode 0): [B][np][SEL_REC], logits is null then
+  const float* rec = nullptr;     // fused argmax path (sample_mode 0): [B][np][sel_rec(4)], logits is null then
   int np = 0;
   long long* seq = nullptr;       // [B,T]
   float* seq_logprobs = nullptr;  // [B,T]
@@ -115,8 +115,8 @@ struct BeamParams {
   int* parent = nullptr;    // [B*K] absolute state row each new beam continues from (written)
   // scratch: per-row candidates published by the row CTAs, per-image ticket counter (zeroed once)
   // fused path: records written by the logits GEMM epilogue (common.cuh LogitsSelect); logits is null then
-  const float* rec = nullptr;  // [B*K][np][SEL_REC]
-  int np = 0;
+  const float* rec = nullptr;  // [B*K][np][sel_rec(k_sel)]
+  int np = 0, k_sel = 4;
   float* cand_lp = nullptr;  // [B*K, 8]
   int* cand_word = nullptr;  // [B*K, 8]
   int* cand_count = nullptr; // [B*K]

@@ -231,8 +231,10 @@ __device__ __forceinline__ void beam_pool(const BeamParams& p, int b) {
 // ---- merge of the LogitsSelect records written by the logits GEMM epilogue (common.cuh) --------------------
 // One warp reduces the np records of a row to the row max, log(sum exp) and the row's K <= SEL_K best unmasked
 // logits (value desc, column asc). Results are broadcast to every lane.
+template <int SEL_K>
 __device__ __forceinline__ void merge_row(const float* __restrict__ rec, int np, int K, int lane, float& mx_out,
                                           float& lse_out, float (&out_v)[SEL_K], int (&out_i)[SEL_K]) {
+  constexpr int SEL_REC = sel_rec(SEL_K);
   float mx = -CUDART_INF_F;
   for (int pi = lane; pi < np; pi += 32) mx = fmaxf(mx, __ldcg(rec + (long long)pi * SEL_REC));
   mx = warp_max(mx);
@@ -412,7 +414,9 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
 
 // Fused path: the logits GEMM already produced per-slice partials; one CTA per image (4 warps, a warp per row)
 // merges them and pools the image's beams.
+template <int SEL_K>
 __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
+  constexpr int SEL_REC = sel_rec(SEL_K);
   const int b = blockIdx.x, K = p.K, t = p.t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int kk = warp; kk < K; kk += 4) {
@@ -422,7 +426,7 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
     if (alive && !finished) {
       float mx, lse, v[SEL_K];
       int w[SEL_K];
-      merge_row(p.rec + (long long)m * p.np * SEL_REC, p.np, K, lane, mx, lse, v, w);
+      merge_row<SEL_K>(p.rec + (long long)m * p.np * SEL_REC, p.np, K, lane, mx, lse, v, w);
       if (lane == 0) {
         int cnt = 0;
 #pragma unroll
@@ -448,9 +452,10 @@ __global__ void __launch_bounds__(256) greedy_merge_kernel(GreedyParams p) {
   const int t = p.t;
   if (b >= p.B) return;
   if (t > 0 && p.alive_count[t - 1] == 0) return;  // whole-batch early stop (captioner.py:343-344)
+  constexpr int SEL_K = 4, SEL_REC = sel_rec(4);
   float mx, lse, v[SEL_K];
   int w[SEL_K];
-  merge_row(p.rec + (long long)b * p.np * SEL_REC, p.np, 1, lane, mx, lse, v, w);
+  merge_row<SEL_K>(p.rec + (long long)b * p.np * SEL_REC, p.np, 1, lane, mx, lse, v, w);
   if (lane == 0) {
     const int unf = p.unfinished[b];
     const long long tok = unf ? w[0] : 0;  // finished rows emit PAD (captioner.py:338)
@@ -532,7 +537,7 @@ int launch_log_softmax(float* x, long long ld, int M, int V, cudaStream_t stream
 int launch_greedy_select(const GreedyParams& p, cudaStream_t stream) {
   if (p.rec) {
     ISC_REQUIRE(p.sample_mode == 0, "fused greedy pick only serves sample_max = 1");
-    ProfScope ps(ISC_K_SELECT, (double)p.B * p.np * SEL_REC * 4.0, stream);
+    ProfScope ps(ISC_K_SELECT, (double)p.B * p.np * sel_rec(4) * 4.0, stream);
     greedy_merge_kernel<<<(p.B + 7) / 8, 256, 0, stream>>>(p);
     ISC_LAUNCH_CHECK();
     return 0;
@@ -546,9 +551,11 @@ int launch_beam_select(const BeamParams& p, cudaStream_t stream) {
   ISC_REQUIRE(p.K >= 1 && p.K <= KMAX, "beam size %d not in 1..%d", p.K, KMAX);
   ISC_REQUIRE(p.cand_lp && p.cand_word && p.cand_count && p.ticket, "beam_select: scratch buffers missing");
   if (p.rec) {
-    ISC_REQUIRE(p.K <= SEL_K, "fused beam merge serves beam sizes up to %d", SEL_K);
-    ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.np * SEL_REC * 4.0, stream);
-    beam_merge_kernel<<<p.B, 128, 0, stream>>>(p);
+    ISC_REQUIRE(p.K <= p.k_sel && (p.k_sel == 4 || p.k_sel == 8), "fused beam merge: beam size %d exceeds the %d candidates per slice",
+                p.K, p.k_sel);
+    ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.np * sel_rec(p.k_sel) * 4.0, stream);
+    if (p.k_sel == 8) beam_merge_kernel<8><<<p.B, 128, 0, stream>>>(p);
+    else beam_merge_kernel<4><<<p.B, 128, 0, stream>>>(p);
     ISC_LAUNCH_CHECK();
     return 0;
   }
