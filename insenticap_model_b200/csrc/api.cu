@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -760,6 +761,7 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
     // att_embed + att2att (captioner.py:302-305), chunked over images so the operand planes stay small (a chunk's
     // planes fit the 126 MB L2). Running the fp32 -> bf16 plane split of chunk i+1 on a second stream beside the GEMMs
     // of chunk i was measured and gains nothing: both are bound by the same L2/HBM traffic.
+    static const bool fused_split = getenv("ISC_PROLOGUE_SPLIT_KERNEL") == nullptr;  // set to use the separate split pass
     for (int b0 = 0; b0 < B; b0 += w.chunk) {
       const int nb = (B - b0 < w.chunk) ? (B - b0) : w.chunk;
       const long long rows = (long long)nb * L;
@@ -767,7 +769,6 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
       Planes praw;
       praw.hi = w.raw_hi;
       praw.lo = w.raw_lo;
-      if (tc) ISC_TRY(split_planes(raw, D, w.raw_hi, w.raw_lo, D, rows, D, c.s));
       Epilogue ep;
       ep.bias = pk.batt;
       ep.act = ACT_RELU;
@@ -788,7 +789,13 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
           patt.lo = w.att_lo;
         }
       }
-      ISC_TRY(gemm(precision, operand(raw, D, praw, D), pk.Watt.op(), dst, (int)rows, H, D, ep, c.s));
+      if (tc && fused_split) {
+        // the fp32 region features go straight into the GEMM: its converter warps split them in shared memory
+        ISC_TRY(gemm_tc_af32(raw, D, pk.Watt.op(), dst, (int)rows, H, D, precision == ISC_PREC_BF16X3 ? 3 : 1, ep, c.s));
+      } else {
+        if (tc) ISC_TRY(split_planes(raw, D, w.raw_hi, w.raw_lo, D, rows, D, c.s));
+        ISC_TRY(gemm(precision, operand(raw, D, praw, D), pk.Watt.op(), dst, (int)rows, H, D, ep, c.s));
+      }
       if (drop && drop->att) {
         ISC_REQUIRE(dst.f32 != nullptr, "dropout needs fp32 features (ISC_PREC_FP32 / ISC_PREC_BF16X3)");
         ISC_TRY(launch_apply_mask(dst.f32, H, drop->att + (long long)b0 * L * H, dscale, rows, H, rowdest(nullptr, 0, patt, H),

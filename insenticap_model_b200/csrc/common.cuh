@@ -144,6 +144,11 @@ struct LstmEpilogue {
 int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,
                  int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream);
 
+// tensor-core GEMM whose A operand is fp32 in HBM: TMA brings fp32 tiles into a staging ring and four converter warps
+// split them into the bf16 hi/lo operand tiles in shared memory (no plane-split pass over HBM). 128x256 tiles.
+int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, int M, int N, int K, int passes,
+                 const Epilogue& ep, cudaStream_t stream);
+
 // tensor-core GEMM whose epilogue emits LogitsSelect records instead of C (bias added; N = vocabulary)
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
                    const LogitsSelect& sel, cudaStream_t stream);

@@ -41,20 +41,26 @@ constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one XOR-swizzled 32x32 fp
 // CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BN tile. Each CTA loads its 128 rows of A and
 // HALF of the B rows, and the pair's MMAs read both halves — per flop, half the B bytes cross L2 -> smem and the
 // smem port; the accumulator of each CTA (its 128 rows x BN columns) stays in its own TMEM.
-template <int PASSES, int BN, int CG = 1>
+// AF = 1: the A operand arrives as fp32 (TMA into a staging ring) and four extra warps split it into the bf16 hi/lo
+// operand tiles in shared memory — no separate plane-split pass over HBM (used for the raw region features).
+template <int PASSES, int BN, int CG = 1, int AF = 0>
 struct Cfg {
   static constexpr int kPlanes = PASSES == 3 ? 2 : 1;
   // K extent of one pipeline stage. 64 bf16 = one 128-byte swizzle row; the wide split-bf16 tile uses 32 (64-byte
   // swizzle) so that four 48 KiB stages fit instead of two 96 KiB ones — two stages cannot keep enough bytes in
   // flight to cover the L2 latency.
-  static constexpr int kBK = (PASSES == 3 && BN == 256 && CG == 1) ? 32 : 64;
+  static constexpr int kBK = (AF || (PASSES == 3 && BN == 256 && CG == 1)) ? 32 : 64;
   static constexpr int kBRows = BN / CG;  // B rows this CTA loads
   static constexpr int kATileBytes = BM * kBK * 2;
   static constexpr int kBTileBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kPlanes * (kATileBytes + kBTileBytes);  // A_hi,(A_lo),B_hi,(B_lo)
-  static constexpr int kStages = 192 * 1024 / kStageBytes;  // x3: 3 / 4 stages, bf16: 6 / 4
+  static constexpr int kStgBytes = AF ? BM * kBK * 4 : 0;  // one fp32 A tile (128 rows x 128 B)
+  static constexpr int kStgSlots = 2;
+  static constexpr int kStages = (192 * 1024 - kStgSlots * kStgBytes) / kStageBytes;  // x3: 3 / 4 stages, bf16: 6 / 4
   static constexpr int kTmemCols = ACC_STAGES * BN;  // 256 / 512 columns (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStgSlots * kStgBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kThreads = NUM_THREADS + (AF ? 128 : 0);
 };
 
 enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2, EPI_LOGITS8 = 3 };  // EPI_LOGITS8: 8 candidates per slice
@@ -229,21 +235,24 @@ __device__ __forceinline__ float act_ct(float v) {
   return v;
 }
 
-template <int PASSES, int BN, int ACT, int EPI, int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int PASSES, int BN, int ACT, int EPI, int CG, int AF>
+__global__ void __launch_bounds__(NUM_THREADS + (AF ? 128 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const EpiParams ep) {
-  using C = Cfg<PASSES, BN, CG>;
+  using C = Cfg<PASSES, BN, CG, AF>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_smem = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes + EPI_BYTES);
-  uint64_t* full_bar = bars;                           // [kStages] TMA -> MMA
-  uint64_t* empty_bar = bars + C::kStages;             // [kStages] MMA -> TMA
+  uint8_t* stg = smem + C::kStages * C::kStageBytes;  // AF: fp32 A staging ring (map_a_hi is the fp32 map then)
+  float* epi_smem = reinterpret_cast<float*>(stg + C::kStgSlots * C::kStgBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_smem) + EPI_BYTES);
+  uint64_t* full_bar = bars;                           // [kStages] TMA (+ converters) -> MMA
+  uint64_t* empty_bar = bars + C::kStages;             // [kStages] MMA -> TMA (+ converters)
   uint64_t* acc_full = bars + 2 * C::kStages;          // [ACC_STAGES] MMA -> epilogue
   uint64_t* acc_empty = acc_full + ACC_STAGES;         // [ACC_STAGES] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
+  uint64_t* stg_full = acc_empty + ACC_STAGES;         // [kStgSlots] TMA -> converters
+  uint64_t* stg_empty = stg_full + C::kStgSlots;       // [kStgSlots] converters -> TMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_empty + C::kStgSlots);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -264,8 +273,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
     }
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], AF ? 5 : 1);  // AF: the producer's arrive (B bytes) + one arrive per converter warp (A tiles)
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < C::kStgSlots; ++s) {
+      mbar_init(&stg_full[s], 1);
+      mbar_init(&stg_empty[s], 4);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -306,7 +319,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint8_t* st = smem + s * C::kStageBytes;
           uint8_t* stb = st + C::kPlanes * C::kATileBytes;
           const int k0 = kb * BK;
-          if (CG == 2) {
+          if (AF) {
+            // B planes straight into the stage; the fp32 A tile into the staging ring for the converter warps
+            mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
+            tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
+            if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+            const int slot = it & 1;
+            mbar_wait(&stg_empty[slot], ((it >> 1) & 1) ^ 1);
+            mbar_expect_tx(&stg_full[slot], C::kStgBytes);
+            tma_load_2d(stg + slot * C::kStgBytes, &map_a_hi, &stg_full[slot], k0, m0);
+          } else if (CG == 2) {
             // both CTAs' bytes complete on the leader's barrier, which alone is armed and waited on
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kStageBytes);
             tma_load_2d_pair(st, &map_a_hi, &full_bar[s], k0, m0);
@@ -375,6 +397,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // accumulator of this tile complete (signalled to the epilogue warps of both CTAs of a pair)
         if (CG == 2) umma_commit_pair(&acc_full[as]);
         else umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (AF && warp >= 2 + EPI_WARPS) {
+    // ===================== converters: fp32 A tile (staging) -> bf16 hi/lo operand tiles of the stage =====================
+    // thread r owns row r: 32 floats = 128 B in the 128B-swizzled staging tile -> 2 x 64 B in the 64B-swizzled operand tiles
+    const int r = threadIdx.x - (2 + EPI_WARPS) * 32;
+    int it = 0;
+    for (int tile = walker; tile < num_tiles; tile += walkers) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        const int slot = it & 1;
+        mbar_wait(&stg_full[slot], (it >> 1) & 1);
+        const uint8_t* src = stg + slot * C::kStgBytes + r * 128;
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 t = *reinterpret_cast<const float4*>(src + ((c ^ (r & 7)) << 4));
+          v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+        }
+        __align__(16) __nv_bfloat16 hh[32], ll[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) split_bf16(v[i], hh[i], ll[i]);
+        mbar_wait(&empty_bar[s], ph ^ 1);  // the MMAs that read this stage's previous contents are done
+        uint8_t* dh = smem + s * C::kStageBytes + r * 64;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int pos = (c ^ ((r >> 1) & 3)) << 4;
+          *reinterpret_cast<uint4*>(dh + pos) = reinterpret_cast<const uint4*>(hh)[c];
+          if (PASSES == 3) *reinterpret_cast<uint4*>(dh + C::kATileBytes + pos) = reinterpret_cast<const uint4*>(ll)[c];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&stg_empty[slot])) : "memory");
+        }
       }
     }
   } else if (EPI == EPI_LOGITS || EPI == EPI_LOGITS8) {
@@ -722,10 +781,37 @@ struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int PASSES, int BN, int ACT, int EPI, int CG>
+// fp32 matrix [rows, cols] -> 2D map, box 32 floats (one 128-byte swizzle row) x 128 rows
+static int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable from the driver");
+    return ISC_ERR_DEVICE;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 4) % 16 != 0) {
+    set_error("gemm_tc: fp32 operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    return ISC_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, static_cast<cuuint32_t>(BM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d (rows %lld cols %lld ld %lld)", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return ISC_ERR_ARG;
+  }
+  return 0;
+}
+
+template <int PASSES, int BN, int ACT, int EPI, int CG, int AF = 0>
 static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG>;
-  constexpr int smem = Cfg<PASSES, BN, CG>::kSmemBytes;
+  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG, AF>;
+  constexpr int smem = Cfg<PASSES, BN, CG, AF>::kSmemBytes;
+  constexpr int NUM_THREADS = Cfg<PASSES, BN, CG, AF>::kThreads;
   ISC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (CG == 2) {
     cudaLaunchConfig_t cfg;
@@ -824,6 +910,41 @@ static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS, CG>(m, ep, grid, stream);
 }
 
+// A given as fp32 (split into operand planes inside the kernel), 128x256 tiles
+template <int PASSES>
+static int launch_af32(const float* A, int64_t lda, const Operand& W, const Dest& Cd, int M, int N, int K, const Epilogue& e,
+                       cudaStream_t stream) {
+  constexpr int BN = 256;
+  using C = Cfg<PASSES, BN, 1, 1>;
+  Maps m;
+  ISC_TRY(make_map_f32(&m.a_hi, A, M, K, lda));
+  m.a_lo = m.a_hi;
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, BN, C::kBK));
+  if (PASSES == 3) ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, BN, C::kBK));
+  else m.b_lo = m.b_hi;
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = e.bias;
+  ep.rowadd = e.rowadd;
+  ep.ld_rowadd = e.ld_rowadd;
+  ep.rows_per_group = e.rows_per_group > 0 ? e.rows_per_group : 1;
+  ep.addmat = e.addmat;
+  ep.ld_addmat = e.ld_addmat;
+  ep.act = e.act;
+  ep.c = Cd.f32;
+  ep.ldc = Cd.ld;
+  ep.hi = Cd.hi;
+  ep.lo = Cd.lo;
+  ep.ldp = Cd.ldp;
+  ep.M = M;
+  ep.N = N;
+  ep.K = K;
+  const int grid = persistent_grid<BN, 1>(M, N);
+  ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, 1>(m, ep, grid, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, 1, 1>(m, ep, grid, stream);
+}
+
 template <int PASSES>
 static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const float* bias, const float* rowadd,
                        int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream) {
@@ -897,6 +1018,18 @@ int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int
   }
   if (pair) return wide ? tc::launch<1, 256, 2>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 2>(A, W, C, M, N, K, ep, stream);
   return wide ? tc::launch<1, 256, 1>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 1>(A, W, C, M, N, K, ep, stream);
+}
+
+int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, int M, int N, int K, int passes,
+                 const Epilogue& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_af32: K=%d must be a positive multiple of 8", K);
+  ISC_REQUIRE(A && W.hi && (ep.act == ACT_RELU || ep.act == ACT_NONE), "gemm_tc_af32: operands missing / unsupported activation");
+  if (passes == 3) {
+    ISC_REQUIRE(W.lo, "gemm_tc_af32: bf16 lo plane missing for the 3-pass mode");
+    return tc::launch_af32<3>(A, lda, W, C, M, N, K, ep, stream);
+  }
+  return tc::launch_af32<1>(A, lda, W, C, M, N, K, ep, stream);
 }
 
 int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,
