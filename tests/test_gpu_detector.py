@@ -1,0 +1,83 @@
+"""The drop-in Detector (models/decoder.py:21-192) on the B200 captioner: one 'fact' and one 'senti' RL iteration with
+stand-in sentiment models that have the reference modules' interfaces, plus Detector.sample."""
+import pytest
+import torch
+import torch.nn as nn
+
+from insenticap_model_b200 import synthetic as syn
+from insenticap_model_b200.detector import Detector
+
+pytestmark = pytest.mark.gpu
+V, B, T = 300, 6, 8
+
+
+class _StubSentiDetector(nn.Module):
+    """sample(att_feats, threshold) -> (labels, senti_features, sentiment names, scores) like SentimentDetector.sample."""
+
+    def __init__(self, cats):
+        super().__init__()
+        self.cats = cats
+
+    def sample(self, features, senti_threshold=0):
+        n = features.shape[0]
+        labels = (torch.arange(n, device=features.device) % 3).long()
+        return labels, None, [self.cats[int(i)] for i in labels], torch.ones(n, device=features.device)
+
+
+class _StubSentCls(nn.Module):
+    """forward(seqs, lengths) -> (pred [B,3], per-word weights [B, max(lengths)]) like SentenceSentimentClassifier."""
+
+    def __init__(self):
+        super().__init__()
+        self.emb = nn.Embedding(V, 3)
+
+    def forward(self, seqs, lengths):
+        lens = torch.as_tensor([max(int(x), 1) for x in lengths], device=seqs.device)
+        max_len = int(lens.max())
+        mask = (torch.arange(max_len, device=seqs.device).unsqueeze(0) < lens.unsqueeze(1)).float()
+        e = self.emb(seqs[:, :max_len]) * mask.unsqueeze(-1)
+        return e.sum(1), mask / lens.unsqueeze(1)
+
+
+def _detector():
+    torch.manual_seed(0)
+    d = Detector(syn.make_vocab(V), T, syn.SENTIMENT_CATEGORIES, {"cap_lr": 4e-4}, dict(syn.DEFAULT_SETTINGS),
+                 senti_detector=_StubSentiDetector(syn.SENTIMENT_CATEGORIES), sent_senti_cls=_StubSentCls())
+    d.captioner.load_state_dict(syn.synthetic_state_dict(V, 1))
+    return d.cuda()
+
+
+def _batches():
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=5)
+    g = torch.Generator().manual_seed(6)
+    caps = torch.randint(4, V, (B, T + 1), generator=g)
+    caps[:, 0] = 1
+    lengths = [T] * B
+    refs = syn.synthetic_references(B, V, 5, seed=3)
+    fns = ["img%d" % i for i in range(B)]
+    gts = {fn: refs[i] for i, fn in enumerate(fns)}
+    fact = [(fns, fc, att, (caps, lengths), cpts, sentis, gts)]
+    senti = [(fns, fc, att, cpts, sentis, labels)]
+    scs = [((caps, lengths), cpts, sentis, labels)]
+    return fact, senti, scs, gts
+
+
+def test_detector_fact_and_senti_iterations_and_sample():
+    d = _detector()
+    fact, senti, scs, gts = _batches()
+    d.set_ciderd_scorer({"train": gts})
+    before = {k: v.detach().clone() for k, v in d.captioner.named_parameters()}
+    out = d((fact, scs), "fact", training=True)
+    assert set(out) == {"da_loss", "fact_reward", "cls_reward", "all_rewards", "cap_loss", "xe_loss", "seq2seq_loss"}
+    assert all(torch.isfinite(torch.tensor(v)) for v in out.values())
+    moved = max(float((p.detach() - before[k]).abs().max()) for k, p in d.captioner.named_parameters())
+    assert 0 < moved <= 4e-4 * 1.01  # one clamp + Adam step
+    out2 = d((senti, scs), "senti", training=True)
+    assert "fact_reward" not in out2 and "xe_loss" not in out2 and "seq2seq_loss" in out2
+    snap = {k: v.detach().clone() for k, v in d.captioner.named_parameters()}
+    out3 = d((fact, scs), "fact", training=False)  # evaluation: no optimizer step, no seq2seq pass
+    assert "seq2seq_loss" not in out3
+    assert all(torch.equal(p.detach(), snap[k]) for k, p in d.captioner.named_parameters())
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(1, V, seed=9)
+    caps, sentiments = d.sample(fc[0].cuda(), att[0].cuda(), sentis[0].cuda(), beam_size=3)
+    assert len(caps) == 3 and isinstance(caps[0], str) and sentiments == ["positive"]
