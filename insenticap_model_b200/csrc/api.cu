@@ -172,6 +172,30 @@ int isc_pack_weights(const isc_dims_t* dims, const isc_weights_t* w, int precisi
   ISC_TRY(add_vec(p.alpha_g_b, w->g_alpha_b, nullptr, 1, s));
   const Mat* mats[] = {&p.W1, &p.Wpre, &p.W2, &p.W3, &p.W4, &p.W5, &p.Wfc, &p.Watt, &p.Wa2a, &p.Ws2a, &p.Wcpt, &p.Wl2w};
   for (const Mat* m : mats) ISC_TRY(finish_mat(*m, precision, s));
+  if (precision != ISC_PREC_FP32) {
+    // W1b = [h_lang_prev | h_att_prev] columns; xt_gates = ReLU(E) . W_ih[:, 2H:3H]^T through the tensor-core GEMM
+    ISC_TRY(copy_block(p.W1b.f32, 2 * H, w->att_lstm_w_ih, 3 * H, G4, H, s));
+    ISC_TRY(copy_block(p.W1b.f32 + H, 2 * H, w->att_lstm_w_hh, H, G4, H, s));
+    ISC_TRY(finish_mat(p.W1b, precision, s));
+    ISC_TRY(launch_embed_rows(nullptr, V, 1, 0, 0, V, p.emb, [&] {
+      RowDest r;
+      r.hi = p.erelu_hi;
+      r.lo = p.erelu_lo;
+      r.ldp = H;
+      return r;
+    }(), s));
+    Operand a, wx;
+    a.hi = p.erelu_hi;
+    a.lo = p.erelu_lo;
+    a.ldp = H;
+    wx.hi = p.W1.hi + H;  // the xt columns of W1 = [h_lang | xt | h_att]
+    wx.lo = p.W1.lo ? p.W1.lo + H : nullptr;
+    wx.ldp = 3 * H;
+    Dest d;
+    d.f32 = p.xt_gates;
+    d.ld = G4;
+    ISC_TRY(gemm_tc(a, wx, d, V, G4, H, precision == ISC_PREC_BF16X3 ? 3 : 1, Epilogue(), s));
+  }
   return 0;
 }
 

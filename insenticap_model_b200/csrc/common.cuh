@@ -140,6 +140,10 @@ struct LstmEpilogue {
   int x_col = 0;
   const unsigned char* mask = nullptr;  // dropout keep mask [M, H] on that copy only (captioner.py:182), or null
   float scale = 1.0f;
+  // optional gathered addend: gates[row] += gather_tab[clamp(gather_idx[row]), :]  ([gather_rows, 4H] fp32)
+  const float* gather_tab = nullptr;
+  const long long* gather_idx = nullptr;
+  int gather_rows = 0;
 };
 int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,
                  int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream);

@@ -86,6 +86,12 @@ struct Mat {
 
 struct Packed {
   Mat W1, Wpre, W2, W3, W4, W5, Wfc, Watt, Wa2a, Ws2a, Wcpt, Wl2w;
+  // decode-only shortcut for the attention LSTM's word term: xt_gates[v] = W_ih[:, 2H:3H] . ReLU(E[v]) for every word
+  // (tensor-core precisions). The gate GEMM then contracts over [h_lang_prev | h_att_prev] only (W1b, K = 2H) and its
+  // fused LSTM epilogue adds the row xt_gates[it] — a third of that GEMM's flops becomes an 8 KB gather per row.
+  Mat W1b;           // [4H, 2H] = W1 columns [h_lang_prev | h_att_prev]
+  float* xt_gates;   // [V, 4H]
+  bf16 *erelu_hi, *erelu_lo;  // [V, H] planes of ReLU(E), operand of the GEMM that builds xt_gates
   float *b1, *b2, *b3, *b4, *b5, *bfc, *batt, *ba2a, *bs2a, *bcpt, *bl2w;
   float *emb, *lab_emb, *alpha_c, *alpha_s, *alpha_g, *alpha_g_b;
   size_t total = 0;
@@ -110,6 +116,14 @@ Packed carve_packed(const isc_dims_t& d, int precision, void* base) {
   mat(p.W3, H, 2 * H);
   mat(p.W4, G4, 3 * H);
   mat(p.W5, V, H);
+  p.xt_gates = nullptr;
+  p.erelu_hi = p.erelu_lo = nullptr;
+  if (precision != ISC_PREC_FP32) {
+    mat(p.W1b, G4, 2 * H);
+    p.xt_gates = b.take<float>((size_t)V * G4);
+    p.erelu_hi = b.take<bf16>((size_t)V * H);
+    if (precision == ISC_PREC_BF16X3) p.erelu_lo = b.take<bf16>((size_t)V * H);
+  }
   mat(p.Wfc, H, D);
   mat(p.Watt, H, D);
   mat(p.Wa2a, H, H);
@@ -326,12 +340,13 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
   const bool rl = has_att && has_sw;
   const long long m = M;
 
-  RowDest x1 = rowdest(w.X1, 3 * H, w.pX1, 3 * H);
-  RowDest x2 = rowdest(w.X2, 3 * H, w.pX2, 3 * H);
-  ISC_TRY(launch_embed_pack(io.it, io.parent, io.h_in, M, c.d.vocab, pk.emb, x1, x2, c.s));
-
   const bool fuse_lstm = c.precision != ISC_PREC_FP32 && !w.tape;  // LSTM cell inside the gate GEMM's epilogue
   const int passes = c.precision == ISC_PREC_BF16X3 ? 3 : 1;
+  RowDest x1 = rowdest(w.X1, 3 * H, w.pX1, 3 * H);
+  RowDest x2 = rowdest(w.X2, 3 * H, w.pX2, 3 * H);
+  // fused path: X1 = [h_lang_prev | h_att_prev] only, the word term comes from the xt_gates table in the epilogue
+  ISC_TRY(launch_embed_pack(io.it, io.parent, io.h_in, M, c.d.vocab, fuse_lstm ? nullptr : pk.emb, x1, x2, c.s));
+
   // attention LSTM
   if (fuse_lstm) {
     LstmEpilogue le;
@@ -343,7 +358,10 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     le.x_lo = w.pX2.lo;
     le.ldx = 3 * H;
     le.x_col = H;
-    ISC_TRY(gemm_tc_lstm(operand(nullptr, 0, w.pX1, 3 * H), pk.W1.op(), M, 3 * H, passes, nullptr, f.pre_gates, G4, R, le, c.s));
+    le.gather_tab = pk.xt_gates;
+    le.gather_idx = io.it;
+    le.gather_rows = c.d.vocab;
+    ISC_TRY(gemm_tc_lstm(operand(nullptr, 0, w.pX1, 3 * H), pk.W1b.op(), M, 2 * H, passes, nullptr, f.pre_gates, G4, R, le, c.s));
   } else {
     Epilogue ep;
     ep.rowadd = f.pre_gates;

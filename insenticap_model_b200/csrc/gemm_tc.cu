@@ -543,6 +543,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
       const float* radd = ep.rowadd ? ep.rowadd + (long long)((unsigned)row / (unsigned)ep.rows_per_group) * ep.ld_rowadd : nullptr;
+      const float* gat = nullptr;
+      if (live && L.gather_tab) {
+        long long tok = L.gather_idx[row];
+        tok = tok < 0 ? 0 : (tok >= L.gather_rows ? L.gather_rows - 1 : tok);
+        gat = L.gather_tab + tok * ep.N;
+      }
       mbar_wait(&acc_full[as], (j >> 1) & 1);
       tcgen05_fence_after();
       float vif[32], vgo[32];  // [i(16) | f(16)], [g(16) | o(16)]
@@ -567,6 +573,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
             if (radd) {
               const float4 t = __ldg(reinterpret_cast<const float4*>(radd + col) + q);
+              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+            }
+            if (gat) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(gat + col) + q);
               v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
             }
           }

@@ -23,11 +23,15 @@ __global__ void __launch_bounds__(128) embed_pack_kernel(const long long* __rest
   const int c = threadIdx.x * 4;
   float4 hl = *reinterpret_cast<const float4*>(h_in + (1 * M + src) * H + c);
   float4 ha = *reinterpret_cast<const float4*>(h_in + (0 * M + src) * H + c);
-  float4 e = *reinterpret_cast<const float4*>(emb + tok * H + c);
-  e.x = fmaxf(e.x, 0.f); e.y = fmaxf(e.y, 0.f); e.z = fmaxf(e.z, 0.f); e.w = fmaxf(e.w, 0.f);
   x1.store4(m, c, hl);
-  x1.store4(m, H + c, e);
-  x1.store4(m, 2 * H + c, ha);
+  if (emb) {
+    float4 e = *reinterpret_cast<const float4*>(emb + tok * H + c);
+    e.x = fmaxf(e.x, 0.f); e.y = fmaxf(e.y, 0.f); e.z = fmaxf(e.z, 0.f); e.w = fmaxf(e.w, 0.f);
+    x1.store4(m, H + c, e);
+    x1.store4(m, 2 * H + c, ha);
+  } else {  // the word term is added from the xt_gates table by the gate GEMM's epilogue: X1 = [h_lang_prev | h_att_prev]
+    x1.store4(m, H + c, ha);
+  }
   x2.store4(m, 2 * H + c, hl);
 }
 
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(128) gate_mix_kernel(const float* __restrict__
 // --------------------------------------------------------------------------------------------
 // Prologue gathers: ReLU(E[id]) rows; concept mean; senti-word rows with the prepended PAD.
 // --------------------------------------------------------------------------------------------
-// out[row] = ReLU(emb[ids[row]]);  ids == null -> row's id comes from `fixed_id`
+// out[row] = ReLU(emb[ids[row]]);  ids == null -> out[row] = ReLU(emb[row]) (the whole table)
 __global__ void __launch_bounds__(128) embed_rows_kernel(const long long* __restrict__ ids, long long n_per_group,
                                                          int prepend_pad, int pad_id, int V, const float* __restrict__ emb,
                                                          RowDest dst) {
@@ -406,7 +410,7 @@ __global__ void __launch_bounds__(128) embed_rows_kernel(const long long* __rest
   const long long per = n_per_group + prepend_pad;
   const long long grp = row / per;
   const long long j = row - grp * per;
-  long long tok = (prepend_pad && j == 0) ? pad_id : ids[grp * n_per_group + (j - prepend_pad)];
+  long long tok = (prepend_pad && j == 0) ? pad_id : (ids ? ids[grp * n_per_group + (j - prepend_pad)] : row);
   tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
   const int c = threadIdx.x * 4;
   float4 e = *reinterpret_cast<const float4*>(emb + tok * H + c);
