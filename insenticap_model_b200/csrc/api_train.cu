@@ -68,6 +68,7 @@ struct TrainWs {
   float* dcs;  // [M][2H]
   float *dc_att, *dc_lang;
   float *datt, *dp_att, *dsw, *dp_sw, *dpre_word, *dpre_gates;
+  float *de_c, *de_s, *dctx_c, *dctx_s;  // per-step softmax gradients [T*M][L|S] and d ctx [T*M][H] (deferred attention backward)
   PM X1T, X2T, csT, hLT;  // [.][TMp]
   PM W1T, W2T, W3T, W4T, W5T, WpreT, Wl2wT, Wa2aT, Ws2aT, WcptT;
   // end phase
@@ -158,6 +159,10 @@ TrainWs carve_train(const isc_dims_t& d, int precision, int B, int T, void* base
   w.dp_att = b.take<float>(m * L * H);
   w.dsw = b.take<float>(m * S * H);
   w.dp_sw = b.take<float>(m * S * H);
+  w.de_c = b.take<float>(tm * L);
+  w.de_s = b.take<float>(tm * S);
+  w.dctx_c = b.take<float>(tm * H);
+  w.dctx_s = b.take<float>(tm * H);
   w.dpre_word = b.take<float>(m * H);
   w.dpre_gates = b.take<float>(m * G4);
   pm(w.X1T, 3 * H, w.TMp);
@@ -401,10 +406,6 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     }
     ISC_CUDA(zf(w.dc_att, (size_t)M * H));
     ISC_CUDA(zf(w.dc_lang, (size_t)M * H));
-    ISC_CUDA(zf(w.datt, (size_t)M * L * H));
-    ISC_CUDA(zf(w.dp_att, (size_t)M * L * H));
-    ISC_CUDA(zf(w.dsw, (size_t)M * S * H));
-    ISC_CUDA(zf(w.dp_sw, (size_t)M * S * H));
     ISC_CUDA(zf(w.dpre_word, (size_t)M * H));
     ISC_CUDA(zf(w.dpre_gates, (size_t)M * G4));
     ISC_CUDA(zf(w.dhproj, (size_t)TM * 3 * H));
@@ -473,8 +474,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
         ab.att = static_cast<const float*>(f.att);
         ab.ea_att = static_cast<const float*>(f.p_att);
         ab.cont_w = w.cont_w + r0 * L;
-        ab.datt = w.datt;
-        ab.dp_att = w.dp_att;
+        ab.de_c = w.de_c + r0 * L;      // deferred: d att / d p_att are built once, after the loop
+        ab.dctx_c = w.dctx_c + r0 * H;
         ab.alpha_c = pk.alpha_c;
         ab.dalpha_c = g->ca_alpha_w;
       }
@@ -482,8 +483,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
         ab.sw = f.sw;
         ab.ea_sw = f.p_sw;
         ab.senti_w = w.senti_w + r0 * S;
-        ab.dsw = w.dsw;
-        ab.dp_sw = w.dp_sw;
+        ab.de_s = w.de_s + r0 * S;
+        ab.dctx_s_out = w.dctx_s + r0 * H;
         ab.alpha_s = pk.alpha_s;
         ab.dalpha_s = g->sa_alpha_w;
         ab.dpre_word = w.dpre_word;
@@ -501,6 +502,14 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       ISC_TRY(launch_embed_bwd(w.it + (size_t)t * M, 1, M, 1, 0, dims->pad_id, 1, (int)V, pk.emb, w.dX1[cur] + H, 3 * H, 1, nullptr,
                                1.f, 1.f, g->word_embed, s));
     }
+
+    // ---- attention feature gradients for all steps in one pass per image
+    if (tm.att)
+      ISC_TRY(launch_attention_bwd_final(T, M, B, (int)L, static_cast<const float*>(f.p_att), w.cont_w, w.de_c, w.dctx_c, w.hproj,
+                                         3 * H, 0, nullptr, pk.alpha_c, w.datt, w.dp_att, s));
+    if (tm.sw)
+      ISC_TRY(launch_attention_bwd_final(T, M, B, (int)S, f.p_sw, w.senti_w, w.de_s, w.dctx_s, w.hproj, 3 * H, H, f.pre_word,
+                                         pk.alpha_s, w.dsw, w.dp_sw, s));
 
     // ---- bias gradients and transposed planes of the all-steps gradient matrices, once
     ISC_TRY(launch_colsum_add(w.dg2, G4, TM, G4, g->lang_lstm_b_ih, g->lang_lstm_b_hh, s));

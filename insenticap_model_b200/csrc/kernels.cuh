@@ -149,7 +149,13 @@ struct AttnBwdParams {
   RowDest dhproj;
   float* dpre_word = nullptr;
   float* dalpha_c = nullptr; float* dalpha_s = nullptr;
+  // deferred accumulation (datt == null): this step's softmax gradients and d ctx are kept for launch_attention_bwd_final
+  float* de_c = nullptr; float* de_s = nullptr;            // [M,L], [M,S]
+  float* dctx_c = nullptr; float* dctx_s_out = nullptr;    // [M,H]
 };
+int launch_attention_bwd_final(int T, int M, int B, int n_items, const float* ea, const float* w_all, const float* de_all,
+                               const float* dctx_all, const float* hproj, long long ld_hproj, int q_col, const float* pre_word,
+                               const float* alpha, float* dfeat, float* dp, cudaStream_t s);
 int launch_logsoftmax_bwd(const float* logp, const float* dlogp, const long long* target, long long ld_target,
                           const float* coef, int T, int M, int V, float* dlogits, long long ld_out, cudaStream_t s);
 int launch_lstm_bwd(const float* gates, const float* c_prev, const float* c_new, const float* dh_a, long long ld_a,

@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(128) gate_bwd_kernel(const float* __restrict__
 __device__ void attn_bwd_part(const float* __restrict__ feat, const float* __restrict__ ea, int n_items,
                               const float* __restrict__ w_saved, const float* dctx_s, const float* eb_s,
                               const float* alpha_s, float* dw_s, float* red_s /*[8][2][H]*/, float* dfeat, float* dp,
-                              float* dq_out /*smem [H]*/, float* dalpha_g /*global [H]*/) {
+                              float* dq_out /*smem [H]*/, float* dalpha_g /*global [H]*/, float* de_out /*[n_items] or null*/) {
+  // dfeat / dp == null: deferred accumulation — this step only leaves de_l (and the caller d ctx) behind, and
+  // attention_bwd_final_kernel builds d feat / d p for all steps in one pass instead of a read-modify-write per step
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // phase 1: dw_l and d feat_l
   for (int l = warp; l < n_items; l += 8) {
@@ -181,10 +183,12 @@ __device__ void attn_bwd_part(const float* __restrict__ feat, const float* __res
       const float4 f = *reinterpret_cast<const float4*>(feat + (long long)l * H + c);
       const float4 d = *reinterpret_cast<const float4*>(dctx_s + c);
       acc += f.x * d.x + f.y * d.y + f.z * d.z + f.w * d.w;
-      float4* dst = reinterpret_cast<float4*>(dfeat + (long long)l * H + c);
-      float4 o = *dst;
-      o.x += wl * d.x; o.y += wl * d.y; o.z += wl * d.z; o.w += wl * d.w;
-      *dst = o;
+      if (dfeat) {
+        float4* dst = reinterpret_cast<float4*>(dfeat + (long long)l * H + c);
+        float4 o = *dst;
+        o.x += wl * d.x; o.y += wl * d.y; o.z += wl * d.z; o.w += wl * d.w;
+        *dst = o;
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) dw_s[l] = acc;
@@ -194,7 +198,11 @@ __device__ void attn_bwd_part(const float* __restrict__ feat, const float* __res
   float sdw = 0.f;
   for (int l = 0; l < n_items; ++l) sdw += w_saved[l] * dw_s[l];
   __syncthreads();
-  for (int l = threadIdx.x; l < n_items; l += 256) dw_s[l] = w_saved[l] * (dw_s[l] - sdw);  // de_l
+  for (int l = threadIdx.x; l < n_items; l += 256) {
+    const float de = w_saved[l] * (dw_s[l] - sdw);  // de_l
+    dw_s[l] = de;
+    if (de_out) de_out[l] = de;
+  }
   __syncthreads();
   // phase 3: through the tanh
   float dq[16], da[16];
@@ -219,10 +227,12 @@ __device__ void attn_bwd_part(const float* __restrict__ feat, const float* __res
         dq[i * 4 + j] += dpre[j];
         da[i * 4 + j] += de * t[j];
       }
-      float4* dst = reinterpret_cast<float4*>(dp + (long long)l * H + c);
-      float4 o = *dst;
-      o.x += dpre[0]; o.y += dpre[1]; o.z += dpre[2]; o.w += dpre[3];
-      *dst = o;
+      if (dp) {
+        float4* dst = reinterpret_cast<float4*>(dp + (long long)l * H + c);
+        float4 o = *dst;
+        o.x += dpre[0]; o.y += dpre[1]; o.z += dpre[2]; o.w += dpre[3];
+        *dst = o;
+      }
     }
   }
 #pragma unroll
@@ -259,6 +269,9 @@ struct AttnBwd {
   RowDest dhproj;                                               // [M,3H]: cols 0..H-1 <- dq_c, H..2H-1 <- dq_s
   float* dpre_word;                                             // [B,H] += dq_s
   float* dalpha_c; float* dalpha_s;                             // [H] +=
+  // deferred mode (datt == null): this step's softmax gradients and d ctx, for attention_bwd_final_kernel
+  float* de_c; float* de_s;                                     // [M,L], [M,S]
+  float* dctx_c; float* dctx_s_out;                             // [M,H] each
 };
 __global__ void __launch_bounds__(256) attention_bwd_kernel(AttnBwd p) {
   extern __shared__ __align__(16) float sm[];
@@ -277,8 +290,11 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(AttnBwd p) {
       alpha_s[c] = p.alpha_c[c];
     }
     __syncthreads();
+    if (p.dctx_c)
+      for (int c = threadIdx.x; c < H; c += 256) p.dctx_c[m * H + c] = dctx_s[c];
     attn_bwd_part(p.att + m * p.L * H, p.ea_att + m * p.L * H, p.L, p.cont_w + m * p.L, dctx_s, eb_s, alpha_s, dw_s, red_s,
-                  p.datt + m * p.L * H, p.dp_att + m * p.L * H, dq_s, p.dalpha_c);
+                  p.datt ? p.datt + m * p.L * H : nullptr, p.datt ? p.dp_att + m * p.L * H : nullptr, dq_s, p.dalpha_c,
+                  p.de_c ? p.de_c + m * p.L : nullptr);
     for (int c = threadIdx.x * 4; c < H; c += 1024) p.dhproj.store4(m, c, *reinterpret_cast<float4*>(dq_s + c));
     __syncthreads();
   }
@@ -289,8 +305,11 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(AttnBwd p) {
       alpha_s[c] = p.alpha_s[c];
     }
     __syncthreads();
+    if (p.dctx_s_out)
+      for (int c = threadIdx.x; c < H; c += 256) p.dctx_s_out[m * H + c] = dctx_s[c];
     attn_bwd_part(p.sw + m * p.S * H, p.ea_sw + m * p.S * H, p.S, p.senti_w + m * p.S, dctx_s, eb_s, alpha_s, dw_s, red_s,
-                  p.dsw + m * p.S * H, p.dp_sw + m * p.S * H, dq_s, p.dalpha_s);
+                  p.dsw ? p.dsw + m * p.S * H : nullptr, p.dsw ? p.dp_sw + m * p.S * H : nullptr, dq_s, p.dalpha_s,
+                  p.de_s ? p.de_s + m * p.S : nullptr);
     for (int c = threadIdx.x * 4; c < H; c += 1024) {
       const float4 v = *reinterpret_cast<float4*>(dq_s + c);
       p.dhproj.store4(m, H + c, v);
@@ -300,6 +319,82 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(AttnBwd p) {
         o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
         *d = o;
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Deferred accumulation of the attention feature gradients over all T steps, one pass per image:
+//   d feat[l, j] = sum_t w[t, l] dctx[t, j]
+//   d p[l, j]    = sum_t de[t, l] alpha_j (1 - tanh^2(p[l, j] + q[t, j]))
+// (plain stores: no zero-init, no per-step read-modify-write of the [B, L, H] accumulators).
+// ---------------------------------------------------------------------------------------------------------
+struct AttnBwdFinal {
+  int T, M, n_items;
+  const float* ea;        // [B, n, H] exp(-2 p)
+  const float* w_all;     // [T, M, n] softmax weights
+  const float* de_all;    // [T, M, n]
+  const float* dctx_all;  // [T, M, H]
+  const float* hproj;     // [T, M, ld_hproj] queries; column q_col
+  long long ld_hproj;
+  int q_col;
+  const float* pre_word;  // [B, H] added to the query (sentiment attention) or null
+  const float* alpha;     // [H]
+  float* dfeat;           // [B, n, H]
+  float* dp;              // [B, n, H]
+};
+__global__ void __launch_bounds__(256) attention_bwd_final_kernel(AttnBwdFinal p) {
+  extern __shared__ __align__(16) float sm[];
+  float* dctx_s = sm;                 // [T][H]
+  float* eb_s = dctx_s + p.T * H;     // [T][H]
+  float* alpha_s = eb_s + p.T * H;    // [H]
+  const long long b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.T * H; i += 256) {
+    const int t = i / H, c = i - t * H;
+    const long long row = (long long)t * p.M + b;
+    dctx_s[i] = p.dctx_all[row * H + c];
+    eb_s[i] = exp_neg2(p.hproj[row * p.ld_hproj + p.q_col + c] + (p.pre_word ? p.pre_word[b * H + c] : 0.f));
+  }
+  for (int i = threadIdx.x; i < H; i += 256) alpha_s[i] = p.alpha[i];
+  __syncthreads();
+  for (int l = warp; l < p.n_items; l += 8) {
+    float af[16], ap[16], e[16], al[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 128 + lane * 4;
+      const float4 e4 = *reinterpret_cast<const float4*>(p.ea + (b * p.n_items + l) * H + c);
+      const float4 a4 = *reinterpret_cast<const float4*>(alpha_s + c);
+      e[4 * i] = e4.x; e[4 * i + 1] = e4.y; e[4 * i + 2] = e4.z; e[4 * i + 3] = e4.w;
+      al[4 * i] = a4.x; al[4 * i + 1] = a4.y; al[4 * i + 2] = a4.z; al[4 * i + 3] = a4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) af[i] = ap[i] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      const long long row = (long long)t * p.M + b;
+      const float w = p.w_all[row * p.n_items + l];
+      const float de = p.de_all[row * p.n_items + l];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = i * 128 + lane * 4;
+        const float4 d4 = *reinterpret_cast<const float4*>(dctx_s + t * H + c);
+        const float4 b4 = *reinterpret_cast<const float4*>(eb_s + t * H + c);
+        float tt[4];
+        tanh2_eprod(e[4 * i], e[4 * i + 1], b4.x, b4.y, tt[0], tt[1]);
+        tanh2_eprod(e[4 * i + 2], e[4 * i + 3], b4.z, b4.w, tt[2], tt[3]);
+        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          af[4 * i + j] = fmaf(w, dd[j], af[4 * i + j]);
+          ap[4 * i + j] = fmaf(de * al[4 * i + j], 1.f - tt[j] * tt[j], ap[4 * i + j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = i * 128 + lane * 4;
+      *reinterpret_cast<float4*>(p.dfeat + (b * p.n_items + l) * H + c) = make_float4(af[4 * i], af[4 * i + 1], af[4 * i + 2], af[4 * i + 3]);
+      *reinterpret_cast<float4*>(p.dp + (b * p.n_items + l) * H + c) = make_float4(ap[4 * i], ap[4 * i + 1], ap[4 * i + 2], ap[4 * i + 3]);
     }
   }
 }
@@ -545,12 +640,27 @@ int launch_attention_bwd(const AttnBwdParams& a, int M, cudaStream_t s) {
   p.cont_w = a.cont_w; p.senti_w = a.senti_w; p.alpha_c = a.alpha_c; p.alpha_s = a.alpha_s;
   p.datt = a.datt; p.dp_att = a.dp_att; p.dsw = a.dsw; p.dp_sw = a.dp_sw;
   p.dhproj = a.dhproj; p.dpre_word = a.dpre_word; p.dalpha_c = a.dalpha_c; p.dalpha_s = a.dalpha_s;
+  p.de_c = a.de_c; p.de_s = a.de_s; p.dctx_c = a.dctx_c; p.dctx_s_out = a.dctx_s_out;
   const int nmax = ((a.L > a.S ? a.L : a.S) + 3) & ~3;
   const size_t smem = sizeof(float) * (4 * H + nmax + 16 * H);
   ISC_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const double bytes = (double)M * ((a.att ? 6.0 * a.L * H * 4.0 : 0.0) + (a.sw ? 6.0 * a.S * H * 4.0 : 0.0));
   ProfScope ps(ISC_K_TRAIN, bytes, s);
   attention_bwd_kernel<<<M, 256, smem, s>>>(p);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_attention_bwd_final(int T, int M, int B, int n_items, const float* ea, const float* w_all, const float* de_all,
+                               const float* dctx_all, const float* hproj, long long ld_hproj, int q_col, const float* pre_word,
+                               const float* alpha, float* dfeat, float* dp, cudaStream_t s) {
+  AttnBwdFinal p;
+  p.T = T; p.M = M; p.n_items = n_items; p.ea = ea; p.w_all = w_all; p.de_all = de_all; p.dctx_all = dctx_all;
+  p.hproj = hproj; p.ld_hproj = ld_hproj; p.q_col = q_col; p.pre_word = pre_word; p.alpha = alpha; p.dfeat = dfeat; p.dp = dp;
+  const size_t smem = sizeof(float) * ((size_t)2 * T * H + H);
+  ISC_REQUIRE(smem <= 200 * 1024, "attention_bwd_final: %d steps do not fit shared memory", T);
+  ISC_CUDA(cudaFuncSetAttribute(attention_bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProfScope ps(ISC_K_TRAIN, (double)B * n_items * H * 4.0 * 3, s);
+  attention_bwd_final_kernel<<<B, 256, smem, s>>>(p);
   ISC_LAUNCH_CHECK();
   return 0;
 }
