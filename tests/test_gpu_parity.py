@@ -348,11 +348,12 @@ def test_beam_graph_replay_and_host_pipeline_match_eager():
         assert not a.is_cuda and torch.equal(a, b.cpu())
 
 
-@pytest.mark.parametrize("V,B,K,T_", [(1003, 1, 1, 3), (130, 5, 4, 9), (4097, 3, 2, 5), (257, 7, 3, 16), (1000, 2, 8, 6)])
+@pytest.mark.parametrize("V,B,K,T_", [(1003, 1, 1, 3), (130, 5, 4, 9), (4097, 3, 2, 5), (257, 7, 3, 16), (1000, 2, 8, 6),
+                                      (130, 2, 3, 40)])
 def test_ragged_shapes_against_oracle(V, B, K, T_):
     """Edge shapes: single image / single beam, vocabularies that are not multiples of 4, 8 or 256 (ragged last logits
     tile and record slice), row counts below one 128-row tile, beam sizes on both sides of the fused-selection
-    limit (K <= 4 fused in the GEMM epilogue, K = 8 through materialised logits), very short captions."""
+    limit (4 or 8 candidates per slice in the GEMM epilogue), very short and long (T = 40) captions."""
     m = model(V, 7, "bf16x3")
     p = params(V, 7)
     fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=13)
