@@ -255,6 +255,23 @@ int isc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float clip, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int step, float grad_scale, isc_stream_t stream);
 
+/* ---- image sentiment detector: SentimentDetector.forward / .sample (models/sentiment_detector.py:30-60) -----------
+ * The step before the caption decode at inference (Detector.sample, models/decoder.py:186); SURVEY.md 8(f) row f2.
+ * att_feats fp32 [B,14,14,feat_dim] -> output fp32 [B,n_cls] (the MLP's logits, forward()'s first result), maps fp32
+ * [B,14,14] (forward()'s second result), labels int64 [B] (arg-max of softmax(output), replaced by neu_idx where the
+ * winning probability is below threshold, :49-52) and scores fp32 [B]. eval() semantics (dropout = identity); exactly
+ * two 3x3 convolutions (settings['sentiment_convs_num'] = 2). The convolution weights are passed ALREADY RESHAPED to
+ * [C_out][9 * C_in] with K index ((ky * 3 + kx) * C_in + c_in), i.e. conv.weight.permute(0, 2, 3, 1).reshape(C_out, -1);
+ * isc_senti_pack splits them into bf16 hi/lo planes. w1x1 [n_cls, feat_dim/4]; out_w [n_fc][n_cls][n_cls]. */
+size_t isc_senti_packed_bytes(int feat_dim);
+int isc_senti_pack(int feat_dim, const float* conv0_w, const float* conv1_w, void* packed, size_t packed_bytes,
+                   isc_stream_t stream);
+size_t isc_senti_workspace_bytes(int feat_dim, int B);
+int isc_senti_detect(int feat_dim, int n_cls, const void* packed, const float* conv0_b, const float* conv1_b,
+                     const float* w1x1, const float* b1x1, const float* out_w, const float* out_b, int n_fc,
+                     const float* att_feats, int B, float threshold, int neu_idx, float* output, float* maps,
+                     int64_t* labels, float* scores, void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
 /* ---- dense contraction on its own (validation / profiling of the tensor-core kernel) -------
  * C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]), fp32 in/out; act 0 none, 1 ReLU, 2 tanh.
  * With ISC_PREC_BF16X3 / ISC_PREC_BF16 the operands are split to bf16 planes in the

@@ -104,6 +104,11 @@ SIGNATURES = {
     "isc_train_backward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
                                      _PDR, _vp, _vp, _vp, _i64, _vp, _vp, _PG, _vp, _sz, _vp]),
     "isc_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int, _f32, _vp]),
+    "isc_senti_packed_bytes": (_sz, [C.c_int]),
+    "isc_senti_pack": (C.c_int, [C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "isc_senti_workspace_bytes": (_sz, [C.c_int, C.c_int]),
+    "isc_senti_detect": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _f32, C.c_int,
+                                   _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isc_gemm_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "isc_gemm_tn": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
                               _vp, _sz, _vp]),

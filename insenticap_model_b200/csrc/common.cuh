@@ -153,6 +153,14 @@ int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, c
 int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, int M, int N, int K, int passes,
                  const Epilogue& ep, cudaStream_t stream);
 
+// 3x3 convolution (stride 1, padding 1) as ONE tensor-core GEMM. Activations live on a zero-bordered 16x16 grid per
+// image: row = image * 256 + y * 16 + x, valid pixels at y, x in 1..14. The K loop walks 9 segments (dy, dx), each
+// reading the A rows shifted by dy * 16 + dx through TMA; W is [N][9 * C] with K index ((dy+1)*3 + (dx+1)) * C + c.
+// A is either fp32 (A32, split in-kernel by the converter warps) or bf16 planes. zero_border forces the output's border
+// rows to zero so that it can feed the next convolution directly.
+int gemm_tc_conv3x3(const float* A32, int64_t lda, const Operand& A, const Operand& W, const Dest& C, int M, int N, int C_in,
+                    int passes, const Epilogue& ep, int zero_border, cudaStream_t stream);
+
 // tensor-core GEMM whose epilogue emits LogitsSelect records instead of C (bias added; N = vocabulary)
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
                    const LogitsSelect& sel, cudaStream_t stream);

@@ -83,6 +83,12 @@ struct EpiParams {
   LogitsSelect sel;
   // EPI_LSTM: the LSTM cell applied to the four gate pre-activations of each hidden unit
   LstmEpilogue lstm;
+  // 3x3 convolution as ONE GEMM over a zero-bordered 16x16 grid per image (rows = image * 256 + y * 16 + x): the K loop
+  // runs over 9 segments of seg_kb k-blocks; segment s reads the A rows shifted by seg_off[s] = dy * 16 + dx (TMA
+  // zero-fills rows outside the tensor), W is [N][9 * C] with K index s * C + c. seg_kb == 0: plain GEMM.
+  int seg_kb;
+  int seg_off[9];
+  int zero_border;  // force the output rows on the 16x16 grid's border to zero (they feed the next convolution as padding)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -257,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr int BK = C::kBK;
-  const int num_kb = (ep.K + BK - 1) / BK;
+  const int num_kb = ep.seg_kb > 0 ? 9 * ep.seg_kb : (ep.K + BK - 1) / BK;
   const int tiles_n = (ep.N + BN - 1) / BN;
   const int tiles_m = (ep.M + CG * BM - 1) / (CG * BM);  // CG = 2: a tile is 256 rows, 128 per CTA of the pair
   const int num_tiles = tiles_m * tiles_n;
@@ -319,6 +325,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint8_t* st = smem + s * C::kStageBytes;
           uint8_t* stb = st + C::kPlanes * C::kATileBytes;
           const int k0 = kb * BK;
+          // A coordinates: plain GEMM (k0, m0); convolution segments shift the rows and wrap the column
+          int ak = k0, am = m0;
+          if (ep.seg_kb > 0) {
+            const int sgm = kb / ep.seg_kb;
+            ak = (kb - sgm * ep.seg_kb) * BK;
+            am = m0 + ep.seg_off[sgm];
+          }
           if (AF) {
             // B planes straight into the stage; the fp32 A tile into the staging ring for the converter warps
             mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
@@ -327,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int slot = it & 1;
             mbar_wait(&stg_empty[slot], ((it >> 1) & 1) ^ 1);
             mbar_expect_tx(&stg_full[slot], C::kStgBytes);
-            tma_load_2d(stg + slot * C::kStgBytes, &map_a_hi, &stg_full[slot], k0, m0);
+            tma_load_2d(stg + slot * C::kStgBytes, &map_a_hi, &stg_full[slot], ak, am);
           } else if (CG == 2) {
             // both CTAs' bytes complete on the leader's barrier, which alone is armed and waited on
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kStageBytes);
@@ -349,8 +362,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           } else {
             mbar_expect_tx(&full_bar[s], C::kStageBytes);
-            tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
-            if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
+            tma_load_2d(st, &map_a_hi, &full_bar[s], ak, am);
+            if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], ak, am);
             tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
             if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
           }
@@ -674,6 +687,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
               x.x = act_ct<ACT>(x.x); x.y = act_ct<ACT>(x.y); x.z = act_ct<ACT>(x.z); x.w = act_ct<ACT>(x.w);
+              if (ep.zero_border) {
+                const int g = (int)(row & 255), gy = g >> 4, gx = g & 15;
+                if (gy == 0 || gy == 15 || gx == 0 || gx == 15) x = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
               if (ep.c) {
                 float* dst = ep.c + row * ep.ldc + n;
                 if (full4 && c_vec) {
@@ -875,6 +892,7 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   Maps m;
   ISC_TRY((make_maps<PASSES, BN, CG>(m, A, W, M, N, K)));
   EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
   ep.bias = e.bias;
   ep.rowadd = e.rowadd;
   ep.ld_rowadd = e.ld_rowadd;
@@ -953,6 +971,48 @@ static int launch_af32(const float* A, int64_t lda, const Operand& W, const Dest
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
   if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, 1>(m, ep, grid, stream);
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, 1, 1>(m, ep, grid, stream);
+}
+
+// 3x3 convolution (stride 1, zero padding 1) over 16x16-gridded rows as one GEMM, 128x256 tiles. A: fp32 [M][C]
+// (AF32 != 0, split in-kernel) or bf16 planes [M][C]; W planes [N][9*C].
+template <int PASSES, int AF32>
+static int launch_conv(const float* A32, const Operand& A, int64_t lda, const Operand& W, const Dest& Cd, int M, int N, int C_in,
+                       const Epilogue& e, int zero_border, cudaStream_t stream) {
+  constexpr int BN = 256;
+  using C = Cfg<PASSES, BN, 1, AF32>;
+  Maps m;
+  if (AF32) {
+    ISC_TRY(make_map_f32(&m.a_hi, A32, M, C_in, lda));
+    m.a_lo = m.a_hi;
+  } else {
+    ISC_TRY(make_map(&m.a_hi, A.hi, M, C_in, A.ldp, BM, C::kBK));
+    if (PASSES == 3) ISC_TRY(make_map(&m.a_lo, A.lo, M, C_in, A.ldp, BM, C::kBK));
+    else m.a_lo = m.a_hi;
+  }
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, 9LL * C_in, W.ldp, BN, C::kBK));
+  if (PASSES == 3) ISC_TRY(make_map(&m.b_lo, W.lo, N, 9LL * C_in, W.ldp, BN, C::kBK));
+  else m.b_lo = m.b_hi;
+  EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = e.bias;
+  ep.rows_per_group = 1;
+  ep.act = e.act;
+  ep.c = Cd.f32;
+  ep.ldc = Cd.ld;
+  ep.hi = Cd.hi;
+  ep.lo = Cd.lo;
+  ep.ldp = Cd.ldp;
+  ep.M = M;
+  ep.N = N;
+  ep.K = 9 * C_in;
+  ep.seg_kb = C_in / C::kBK;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) ep.seg_off[(dy + 1) * 3 + (dx + 1)] = dy * 16 + dx;
+  ep.zero_border = zero_border;
+  const int grid = persistent_grid<BN, 1>(M, N);
+  ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * 9.0 * C_in * PASSES, stream);
+  if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, AF32>(m, ep, grid, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, 1, AF32>(m, ep, grid, stream);
 }
 
 template <int PASSES>
@@ -1040,6 +1100,21 @@ int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, i
     return tc::launch_af32<3>(A, lda, W, C, M, N, K, ep, stream);
   }
   return tc::launch_af32<1>(A, lda, W, C, M, N, K, ep, stream);
+}
+
+int gemm_tc_conv3x3(const float* A32, int64_t lda, const Operand& A, const Operand& W, const Dest& C, int M, int N, int C_in,
+                    int passes, const Epilogue& ep, int zero_border, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return 0;
+  ISC_REQUIRE(M % 256 == 0 && C_in % 64 == 0 && N % 8 == 0, "gemm_tc_conv3x3: M must be images * 256, C a multiple of 64");
+  ISC_REQUIRE((A32 || A.hi) && W.hi && (ep.act == ACT_RELU || ep.act == ACT_NONE) && !ep.rowadd && !ep.addmat,
+              "gemm_tc_conv3x3: operands missing / unsupported epilogue");
+  if (passes == 3) {
+    ISC_REQUIRE(W.lo && (A32 || A.lo), "gemm_tc_conv3x3: bf16 lo planes missing for the 3-pass mode");
+    return A32 ? tc::launch_conv<3, 1>(A32, A, lda, W, C, M, N, C_in, ep, zero_border, stream)
+               : tc::launch_conv<3, 0>(nullptr, A, 0, W, C, M, N, C_in, ep, zero_border, stream);
+  }
+  return A32 ? tc::launch_conv<1, 1>(A32, A, lda, W, C, M, N, C_in, ep, zero_border, stream)
+             : tc::launch_conv<1, 0>(nullptr, A, 0, W, C, M, N, C_in, ep, zero_border, stream);
 }
 
 int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,

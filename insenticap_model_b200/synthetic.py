@@ -109,6 +109,42 @@ def synthetic_state_dict(vocab_size: int, seed: int = 0, settings: dict | None =
     return sd
 
 
+def senti_detector_state_dict(seed: int = 0, settings: dict | None = None, n_cls: int = 3, n_convs: int = 2, n_fcs: int = 2,
+                              spread: float = 150.0) -> "OrderedDict[str, torch.Tensor]":
+    """Random-init weights of the image sentiment detector (/root/reference/models/sentiment_detector.py:6-28) under
+    the reference's parameter names. ``spread`` scales the first output layer so that the class probabilities of
+    different random images land on both sides of the 0.7 neutral threshold."""
+    s = dict(DEFAULT_SETTINGS if settings is None else settings)
+    sd = OrderedDict()
+    c = s["fc_feat_dim"]
+    i = 0
+
+    def uni(shape, fan):
+        nonlocal i
+        g = torch.Generator().manual_seed(seed * 1000 + 500 + i)
+        i += 1
+        return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) / math.sqrt(fan)
+
+    for k in range(n_convs):
+        sd["convs.conv_%d.weight" % k] = uni((c // 2, c, 3, 3), c * 9)
+        sd["convs.conv_%d.bias" % k] = uni((c // 2,), c * 9)
+        c //= 2
+    sd["senti_conv.weight"] = uni((n_cls, c, 1, 1), c)
+    sd["senti_conv.bias"] = uni((n_cls,), c)
+    for k in range(n_fcs):
+        sd["output.%d.weight" % k] = uni((n_cls, n_cls), n_cls) * (spread if k == 0 else 1.0)
+        sd["output.%d.bias" % k] = uni((n_cls,), n_cls)
+    return sd
+
+
+def senti_detector_inputs(batch: int = 6, seed: int = 21) -> torch.Tensor:
+    """Region features [B,14,14,2048] for the sentiment-detector tests: random features times a per-image signed scale, so
+    that the winning probabilities land on both sides of the 0.7 threshold."""
+    _, att, _, _, _ = synthetic_inputs(batch, 100, seed=seed)
+    scale = torch.tensor([-3.0, -1.0, -0.3, 0.3, 1.0, 3.0])
+    return att * scale[torch.arange(batch) % 6].view(batch, 1, 1, 1)
+
+
 def synthetic_inputs(batch: int, vocab_size: int, seed: int = 1, settings: dict | None = None,
                      labels: str | int = "cycle"):
     """fc_feats, att_feats, cpt_words, senti_words, senti_labels.

@@ -179,7 +179,31 @@ def cider_goldens():
     print("cider scores head:", scores[:6], "EOS-only:", scores[5], "n df entries:", len(df_arr))
 
 
+def senti_goldens():
+    """The reference's SentimentDetector (models/sentiment_detector.py) on synthetic region features."""
+    from models.sentiment_detector import SentimentDetector as RefDetector
+    settings = dict(syn.DEFAULT_SETTINGS, sentiment_convs_num=2, sentiment_fcs_num=2)
+    m = RefDetector(syn.SENTIMENT_CATEGORIES, settings)
+    m.load_state_dict(syn.senti_detector_state_dict(0))
+    m.eval()
+    att = syn.senti_detector_inputs(6)
+    with torch.no_grad():
+        output, maps = m(att)
+        labels, _, names, scores = m.sample(att, 0.7)
+        m2 = RefDetector(["neutral", "positive", "negative"], settings)  # neutral = class 0: the threshold changes labels
+        m2.load_state_dict(syn.senti_detector_state_dict(0))
+        labels0, _, _, _ = m2.sample(att, 0.7)
+    out = {"output": output.numpy(), "maps": maps.numpy(), "labels": labels.numpy(), "scores": scores.numpy(),
+           "labels_neutral_first": labels0.numpy(), "checksum_att": np.array(checksum(att))}
+    np.savez_compressed(os.path.join(HERE, "senti_golden.npz"), **out)
+    print("senti scores:", scores.numpy(), "labels:", labels.numpy(), names)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    decode_goldens()
-    cider_goldens()
+    if "senti" in sys.argv:
+        senti_goldens()
+    else:
+        decode_goldens()
+        cider_goldens()
+        senti_goldens()

@@ -146,3 +146,22 @@ def test_cider_scores_and_reward(golden_cider):
     r = orc.self_critical_reward(golden_cider["sample"], golden_cider["greedy"], refs[:B])
     np.testing.assert_allclose(r, golden_cider["rewards"], rtol=0, atol=1e-12)
     assert golden_cider["scores"][5] == 0.0  # EOS-only hypothesis
+
+
+def test_senti_detector_oracle_matches_reference_golden():
+    """oracle/senti_oracle.py against the reference SentimentDetector's own outputs (tests/golden/senti_golden.npz)."""
+    import os
+    from oracle import senti_oracle as SO
+    gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "senti_golden.npz"))
+    sd = syn.senti_detector_state_dict(0)
+    att = syn.senti_detector_inputs(6)
+    assert abs(float(att.double().sum()) - float(gd["checksum_att"])) < 1e-6 * abs(float(gd["checksum_att"])) + 1e-6
+    with torch.no_grad():
+        out, maps = SO.forward(sd, att)
+        labels, _, scores = SO.sample(sd, att, 0.7, 2)
+        labels0, _, _ = SO.sample(sd, att, 0.7, 0)
+    np.testing.assert_allclose(out.numpy(), gd["output"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(maps.numpy(), gd["maps"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(scores.numpy(), gd["scores"], rtol=1e-4, atol=1e-5)
+    assert np.array_equal(labels.numpy(), gd["labels"]) and np.array_equal(labels0.numpy(), gd["labels_neutral_first"])
+    assert len(set(gd["labels_neutral_first"].tolist())) > 1  # the threshold branch is exercised
