@@ -272,6 +272,22 @@ int isc_senti_detect(int feat_dim, int n_cls, const void* packed, const float* c
                      const float* att_feats, int B, float threshold, int neu_idx, float* output, float* maps,
                      int64_t* labels, float* scores, void* workspace, size_t workspace_bytes, isc_stream_t stream);
 
+/* ---- sentence sentiment classifier, inference: SentenceSentimentClassifier.forward (models/sent_senti_cls.py:38-56) --
+ * The model behind get_cls_reward (self_critical/utils.py:120-151) and the XE pseudo-labels (train_xe.py:155-158);
+ * SURVEY.md 8(f) row f3. seqs int64 [B, ld_seqs] (first T columns used), lengths int32 [B] (>= 1) -> pred fp32
+ * [B, n_cls] and the per-word weights fp32 [B, T] (zero past each caption's length; the reference returns the first
+ * max(lengths) columns). eval() semantics. Parameters: word_embed [V,H], the nn.LSTM's weight_ih_l0 / weight_hh_l0
+ * [4H,H] and biases, excitation.0 / .2 and sent_senti_cls.0 [H,H], sent_senti_cls.3 [n_cls,H] with their biases. */
+size_t isc_sentcls_packed_bytes(int vocab, int n_cls);
+int isc_sentcls_pack(int vocab, int n_cls, const float* word_embed, const float* w_ih, const float* w_hh,
+                     const float* b_ih, const float* b_hh, const float* exc0_w, const float* exc0_b,
+                     const float* exc2_w, const float* exc2_b, const float* cls0_w, const float* cls0_b,
+                     const float* cls3_w, const float* cls3_b, void* packed, size_t packed_bytes, isc_stream_t stream);
+size_t isc_sentcls_workspace_bytes(int B, int T);
+int isc_sentcls_forward(int vocab, int n_cls, const void* packed, const int64_t* seqs, int64_t ld_seqs,
+                        const int32_t* lengths, int B, int T, float* pred, float* att_weights,
+                        void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
 /* ---- dense contraction on its own (validation / profiling of the tensor-core kernel) -------
  * C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]), fp32 in/out; act 0 none, 1 ReLU, 2 tanh.
  * With ISC_PREC_BF16X3 / ISC_PREC_BF16 the operands are split to bf16 planes in the

@@ -109,6 +109,10 @@ SIGNATURES = {
     "isc_senti_workspace_bytes": (_sz, [C.c_int, C.c_int]),
     "isc_senti_detect": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _f32, C.c_int,
                                    _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "isc_sentcls_packed_bytes": (_sz, [C.c_int, C.c_int]),
+    "isc_sentcls_pack": (C.c_int, [C.c_int, C.c_int] + [_vp] * 14 + [_sz, _vp]),
+    "isc_sentcls_workspace_bytes": (_sz, [C.c_int, C.c_int]),
+    "isc_sentcls_forward": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _i64, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "isc_gemm_workspace_bytes": (_sz, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "isc_gemm_tn": (C.c_int, [C.c_int, _vp, _i64, _vp, _i64, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
                               _vp, _sz, _vp]),

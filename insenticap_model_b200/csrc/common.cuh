@@ -47,7 +47,7 @@ void set_error(const char* fmt, ...);
 
 // ACT_EXPNEG2_RELU: exp(-2 * relu(v)) — the representation of the projected attention features that the
 // e-product tanh of the bf16x3 attention kernel reads (tanh2_eprod below)
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_EXPNEG2_RELU = 3 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_EXPNEG2_RELU = 3, ACT_SIGMOID = 4 };
 
 // Per-kernel-class accounting (isc_profile_* in include/isc.h). Every launcher opens a ProfScope:
 // it counts the launch and, when profiling is enabled, brackets it with CUDA events on the launch
@@ -219,6 +219,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   if (act == ACT_TANH) return tanhf(v);
   if (act == ACT_EXPNEG2_RELU) return exp_neg2(fmaxf(v, 0.0f));
+  if (act == ACT_SIGMOID) return sigmoid_accurate(v);
   return v;
 }
 

@@ -238,6 +238,7 @@ __device__ __forceinline__ float act_ct(float v) {
   if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
   if (ACT == ACT_TANH) return tanhf(v);
   if (ACT == ACT_EXPNEG2_RELU) return exp_neg2(fmaxf(v, 0.0f));
+  if (ACT == ACT_SIGMOID) return sigmoid_accurate(v);
   return v;
 }
 
@@ -914,6 +915,7 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
     case ACT_RELU: return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG>(m, ep, grid, stream);
     case ACT_TANH: return launch_kernel<PASSES, BN, ACT_TANH, EPI_STD, CG>(m, ep, grid, stream);
     case ACT_EXPNEG2_RELU: return launch_kernel<PASSES, BN, ACT_EXPNEG2_RELU, EPI_STD, CG>(m, ep, grid, stream);
+    case ACT_SIGMOID: return launch_kernel<PASSES, BN, ACT_SIGMOID, EPI_STD, CG>(m, ep, grid, stream);
     default: return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, CG>(m, ep, grid, stream);
   }
 }

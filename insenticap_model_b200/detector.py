@@ -5,11 +5,12 @@ captioner passes (sampled decode under autograd, greedy baseline, XE and seq2seq
 reward and the clamp + Adam step run on libisc_b200.so; sampled ids, greedy ids, rewards and losses stay on the
 device (the reference hops through numpy at self_critical/utils.py:59-60 and models/decoder.py:103).
 
-The image sentiment detector and the sentence sentiment classifier are separate models outside this path's scope
-(SURVEY.md section 2 #10 / #11): pass any torch modules with the reference's interfaces
-(``senti_detector.sample(att_feats, threshold) -> (labels, ...)``, ``sent_senti_cls(seqs, lengths) -> (pred [B,3],
-att_weights [B,max_len])``) — the reference's own classes work unchanged. Without them, ``data_type='senti'`` batches
-(which carry their labels) still run, with the classifier reward switched off.
+The image sentiment detector and the sentence sentiment classifier are passed in: ``sentiment_detector.SentimentDetector``
+and ``sent_senti_cls.SentenceSentimentClassifier`` keep them on libisc_b200.so too,
+and any torch modules with the reference's interfaces (``senti_detector.sample(att_feats, threshold) -> (labels, ...)``,
+``sent_senti_cls(seqs, lengths) -> (pred [B,3], att_weights [B,max_len])``) — the reference's own classes included — work
+as well. Without them, ``data_type='senti'`` batches (which carry their labels) still run, with the classifier reward
+switched off.
 """
 from __future__ import annotations
 

@@ -137,6 +137,44 @@ def senti_detector_state_dict(seed: int = 0, settings: dict | None = None, n_cls
     return sd
 
 
+def sent_cls_state_dict(vocab_size: int, seed: int = 0, n_cls: int = 3, hid: int = 512) -> "OrderedDict[str, torch.Tensor]":
+    """Random-init weights of the sentence sentiment classifier (/root/reference/models/sent_senti_cls.py:6-36) under the
+    reference's parameter names (uniform +-1/sqrt(fan_in), embeddings N(0,1) with a zero <PAD> row, like torch's init)."""
+    sd = OrderedDict()
+    i = 0
+
+    def uni(shape, fan):
+        nonlocal i
+        g = torch.Generator().manual_seed(seed * 1000 + 700 + i)
+        i += 1
+        return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) / math.sqrt(fan)
+
+    emb = torch.randn(vocab_size, hid, generator=torch.Generator().manual_seed(seed * 1000 + 699))
+    emb[0] = 0.0
+    sd["word_embed.0.weight"] = emb
+    sd["rnn.weight_ih_l0"] = uni((4 * hid, hid), hid)
+    sd["rnn.weight_hh_l0"] = uni((4 * hid, hid), hid)
+    sd["rnn.bias_ih_l0"] = uni((4 * hid,), hid)
+    sd["rnn.bias_hh_l0"] = uni((4 * hid,), hid)
+    for name, rows in (("excitation.0", hid), ("excitation.2", hid), ("sent_senti_cls.0", hid), ("sent_senti_cls.3", n_cls)):
+        sd[name + ".weight"] = uni((rows, hid), hid)
+        sd[name + ".bias"] = uni((rows,), hid)
+    return sd
+
+
+def sent_cls_inputs(batch: int, vocab_size: int, max_len: int = 16, seed: int = 31):
+    """Captions int64 [B, max_len] (zero = <PAD> past each length) and ragged lengths [B] in 1..max_len, unsorted, with
+    at least one caption of full length and one of length 1."""
+    g = torch.Generator().manual_seed(seed)
+    seqs = torch.randint(4, vocab_size, (batch, max_len), generator=g)
+    lengths = torch.randint(1, max_len + 1, (batch,), generator=g)
+    lengths[batch // 2] = max_len
+    if batch > 1:
+        lengths[0] = 1
+    seqs = seqs * (torch.arange(max_len)[None, :] < lengths[:, None])
+    return seqs, lengths.tolist()
+
+
 def senti_detector_inputs(batch: int = 6, seed: int = 21) -> torch.Tensor:
     """Region features [B,14,14,2048] for the sentiment-detector tests: random features times a per-image signed scale, so
     that the winning probabilities land on both sides of the 0.7 threshold."""

@@ -199,11 +199,31 @@ def senti_goldens():
     print("senti scores:", scores.numpy(), "labels:", labels.numpy(), names)
 
 
+def sentcls_goldens():
+    """The reference's SentenceSentimentClassifier (models/sent_senti_cls.py) on ragged synthetic captions."""
+    from models.sent_senti_cls import SentenceSentimentClassifier as RefCls
+    V, B = 1000, 12
+    m = RefCls(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS))
+    m.load_state_dict(syn.sent_cls_state_dict(V, 0))
+    m.eval()
+    seqs, lengths = syn.sent_cls_inputs(B, V)
+    with torch.no_grad():
+        pred, weights = m(seqs, lengths)
+        result, names, _ = m.sample(seqs, lengths)
+    out = {"pred": pred.numpy(), "weights": weights.numpy(), "result": np.array(result), "lengths": np.array(lengths),
+           "checksum_seqs": np.array(checksum(seqs))}
+    np.savez_compressed(os.path.join(HERE, "sentcls_golden.npz"), **out)
+    print("sentcls pred:", pred.numpy()[:3], "result:", result, "lengths:", lengths)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     if "senti" in sys.argv:
         senti_goldens()
+    elif "sentcls" in sys.argv:
+        sentcls_goldens()
     else:
+        sentcls_goldens()
         decode_goldens()
         cider_goldens()
         senti_goldens()

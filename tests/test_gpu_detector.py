@@ -81,3 +81,39 @@ def test_detector_fact_and_senti_iterations_and_sample():
     fc, att, cpts, sentis, labels = syn.synthetic_inputs(1, V, seed=9)
     caps, sentiments = d.sample(fc[0].cuda(), att[0].cuda(), sentis[0].cuda(), beam_size=3)
     assert len(caps) == 3 and isinstance(caps[0], str) and sentiments == ["positive"]
+
+
+def test_detector_with_on_device_sentiment_models_and_cls_reward():
+    """The whole Detector on libisc_b200.so: image sentiment detector, captioner and sentence sentiment classifier; the
+    classifier reward (self_critical/utils.py:120-151) checked against the CPU oracle of the classifier."""
+    import numpy as np
+    from insenticap_model_b200.detector import get_cls_reward
+    from insenticap_model_b200.sent_senti_cls import SentenceSentimentClassifier
+    from insenticap_model_b200.sentiment_detector import SentimentDetector
+    from oracle import sentcls_oracle as CO
+
+    settings = dict(syn.DEFAULT_SETTINGS, sentiment_convs_num=2, sentiment_fcs_num=2)
+    sd = SentimentDetector(syn.SENTIMENT_CATEGORIES, settings)
+    sd.load_state_dict(syn.senti_detector_state_dict(0))
+    sc = SentenceSentimentClassifier(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, settings)
+    sc.load_state_dict(syn.sent_cls_state_dict(V, 0))
+    torch.manual_seed(0)
+    d = Detector(syn.make_vocab(V), T, syn.SENTIMENT_CATEGORIES, {"cap_lr": 4e-4}, settings, senti_detector=sd, sent_senti_cls=sc)
+    d.captioner.load_state_dict(syn.synthetic_state_dict(V, 1))
+    d = d.cuda()
+    fact, senti, scs, gts = _batches()
+    d.set_ciderd_scorer({"train": gts})
+    out = d((fact, scs), "fact", training=True)
+    assert all(torch.isfinite(torch.tensor(v)) for v in out.values()) and "cls_reward" in out
+    out2 = d((senti, scs), "senti", training=True)
+    assert all(torch.isfinite(torch.tensor(v)) for v in out2.values())
+
+    seqs, lengths = syn.sent_cls_inputs(B, V, max_len=T, seed=77)
+    masks = (torch.arange(T)[None, :] < torch.tensor(lengths)[:, None]).float()
+    labels = torch.arange(B) % 3
+    got = get_cls_reward(seqs.cuda(), masks.cuda(), None, None, labels.cuda(), sc)
+    with torch.no_grad():
+        pred, w = CO.forward(syn.sent_cls_state_dict(V, 0), seqs, lengths)
+    want = torch.nn.functional.pad((pred.argmax(-1) == labels).float()[:, None] * w, (0, T - w.shape[1]))
+    assert tuple(got.shape) == (B, T)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)

@@ -165,3 +165,18 @@ def test_senti_detector_oracle_matches_reference_golden():
     np.testing.assert_allclose(scores.numpy(), gd["scores"], rtol=1e-4, atol=1e-5)
     assert np.array_equal(labels.numpy(), gd["labels"]) and np.array_equal(labels0.numpy(), gd["labels_neutral_first"])
     assert len(set(gd["labels_neutral_first"].tolist())) > 1  # the threshold branch is exercised
+
+
+def test_sentcls_oracle_matches_reference_golden():
+    """oracle/sentcls_oracle.py against the reference SentenceSentimentClassifier's own outputs."""
+    import os
+    from oracle import sentcls_oracle as CO
+    gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sentcls_golden.npz"))
+    V, B = 1000, 12
+    seqs, lengths = syn.sent_cls_inputs(B, V)
+    assert abs(float(seqs.double().sum()) - float(gd["checksum_seqs"])) < 1e-6 and lengths == gd["lengths"].tolist()
+    with torch.no_grad():
+        pred, weights = CO.forward(syn.sent_cls_state_dict(V, 0), seqs, lengths)
+    np.testing.assert_allclose(pred.numpy(), gd["pred"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(weights.numpy(), gd["weights"], rtol=1e-5, atol=1e-6)
+    assert pred.argmax(-1).tolist() == gd["result"].tolist()
