@@ -107,7 +107,7 @@ class Detector(nn.Module):
             sample_captions, sample_logprobs, seq_masks = self.captioner(
                 fc_feats, att_feats, cpts_tensor, sentis_tensor, senti_labels, self.max_seq_len, sample_max=0, mode="rl")
             da_loss = self.cap_da_crit(self.captioner.cpt_feats, self.captioner.fc_feats.detach())
-            all_losses["da_loss"] += float(da_loss)
+            all_losses["da_loss"] += float(da_loss.detach())
 
             self.captioner.eval()
             with torch.no_grad():
