@@ -135,6 +135,16 @@ int isc_prologue(const isc_dims_t* dims, const void* packed, int precision,
                  void* workspace, size_t workspace_bytes, isc_stream_t stream,
                  const isc_dropout_t* dropout /* NULL: eval mode */);
 
+/* The same with fc_feats / att_feats stored as bf16 (a bf16 feature shard, isc_shard_* below): ISC_PREC_BF16 only, eval
+ * mode, not seq2seq. That mode rounds its fp32 inputs to bf16 before the GEMMs, so the result is bit-identical to
+ * isc_prologue on the fp32 values the shard was written from, at half the host->device and HBM bytes. */
+int isc_prologue_bf16in(const isc_dims_t* dims, const void* packed, int precision,
+                        const void* fc_feats_bf16, const void* att_feats_bf16,
+                        const int64_t* cpt_words, int n_cpt,
+                        const int64_t* senti_words, const int64_t* senti_labels,
+                        int B, const isc_feats_t* out,
+                        void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
 /* Convert caller-supplied, already-embedded fp32 features (the att_feats / p_att_feats /
  * p_senti_word_feats arguments of Captioner.forward_step, captioner.py:168) into the
  * representation isc_feats_t holds for `precision`: bf16 for ISC_PREC_BF16 (att, p_att), and for
@@ -287,6 +297,25 @@ size_t isc_sentcls_workspace_bytes(int B, int T);
 int isc_sentcls_forward(int vocab, int n_cls, const void* packed, const int64_t* seqs, int64_t ld_seqs,
                         const int32_t* lengths, int B, int T, float* pred, float* att_weights,
                         void* workspace, size_t workspace_bytes, isc_stream_t stream);
+
+/* ---- feature shards: the input side of the path (dataloader.py:164-204 opens one HDF5 file per item) -----------------
+ * One flat file of fixed-size records (fc_feats [D] then att_feats [L][D] per image; fp32, bit-exact with the
+ * reference's arrays, or bf16), mmap'ed once. HOST-ONLY calls: no GPU is touched. isc_shard_gather copies the records
+ * of indices[0..n) (any order, repeats allowed) into fc_dst [n][D] and att_dst [n][L][D] (either may be NULL) in the
+ * shard's dtype with n_threads host threads; pass pinned buffers and follow with one cudaMemcpyAsync per tensor.
+ * Layout: 64-byte header {"ISCFEAT1", u32 version = 1, u32 dtype, u32 D, u32 L, u64 n, u64 names_bytes, u64 data_offset,
+ * u64 record_bytes}, n NUL-terminated names in record order, zero padding to data_offset, records. */
+#define ISC_SHARD_F32 0
+#define ISC_SHARD_BF16 1
+typedef void* isc_shard_t;
+int isc_shard_write(const char* path, int dtype, int feat_dim, int n_regions, int64_t n_images,
+                    const char* const* names, const float* fc_feats, const float* att_feats);
+int isc_shard_open(const char* path, isc_shard_t* out);
+int isc_shard_close(isc_shard_t shard);
+int isc_shard_info(isc_shard_t shard, int64_t* n_images, int* feat_dim, int* n_regions, int* dtype);
+int64_t isc_shard_find(isc_shard_t shard, const char* name);       /* record index, -1 if absent */
+const char* isc_shard_name(isc_shard_t shard, int64_t index);      /* NULL if out of range */
+int isc_shard_gather(isc_shard_t shard, const int64_t* indices, int64_t n, void* fc_dst, void* att_dst, int n_threads);
 
 /* ---- dense contraction on its own (validation / profiling of the tensor-core kernel) -------
  * C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]), fp32 in/out; act 0 none, 1 ReLU, 2 tanh.

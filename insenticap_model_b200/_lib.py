@@ -109,6 +109,15 @@ SIGNATURES = {
     "isc_senti_workspace_bytes": (_sz, [C.c_int, C.c_int]),
     "isc_senti_detect": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, _f32, C.c_int,
                                    _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "isc_prologue_bf16in": (C.c_int, [C.POINTER(Dims), _vp, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int,
+                                      C.POINTER(Feats), _vp, _sz, _vp]),
+    "isc_shard_write": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, _i64, C.POINTER(C.c_char_p), _vp, _vp]),
+    "isc_shard_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "isc_shard_close": (C.c_int, [_vp]),
+    "isc_shard_info": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "isc_shard_find": (C.c_int64, [_vp, C.c_char_p]),
+    "isc_shard_name": (C.c_char_p, [_vp, _i64]),
+    "isc_shard_gather": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.c_int]),
     "isc_sentcls_packed_bytes": (_sz, [C.c_int, C.c_int]),
     "isc_sentcls_pack": (C.c_int, [C.c_int, C.c_int] + [_vp] * 14 + [_sz, _vp]),
     "isc_sentcls_workspace_bytes": (_sz, [C.c_int, C.c_int]),

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libisc_b200.so")
-SOURCES = ["api.cu", "api_train.cu", "gemm_tc.cu", "gemm_simt.cu", "kernels_step.cu", "kernels_select.cu", "cider.cu", "train.cu", "senti.cu", "sentcls.cu"]
+SOURCES = ["api.cu", "api_train.cu", "gemm_tc.cu", "gemm_simt.cu", "kernels_step.cu", "kernels_select.cu", "cider.cu", "train.cu", "senti.cu", "sentcls.cu", "shard_io.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

@@ -345,9 +345,15 @@ class Captioner(nn.Module):
         f32 = dict(dtype=torch.float32, device=dev)
         t = {}
         n_regions, S = self.n_regions, self.num_senti_words + 1
+        bf16_in = False
         if not seq2seq:
-            fc_feats = fc_feats.reshape(B, -1).float().contiguous()
-            att_feats = att_feats.reshape(B, -1, att_feats.shape[-1]).float().contiguous()
+            # bf16 features (a bf16 feature shard, dataloader.FeatureShard): precision="bf16" rounds its inputs to bf16
+            # anyway, so they go in as they are; every other mode computes on fp32 inputs
+            bf16_in = (fc_feats.dtype == torch.bfloat16 and att_feats.dtype == torch.bfloat16
+                       and self._prec == _lib.PREC_BF16 and not dropout)
+            keep = (lambda x: x.contiguous()) if bf16_in else (lambda x: x.float().contiguous())
+            fc_feats = keep(fc_feats.reshape(B, -1))
+            att_feats = keep(att_feats.reshape(B, -1, att_feats.shape[-1]))
             n_regions = att_feats.shape[1]
             t["att"] = torch.empty(B, n_regions, 512, dtype=self._feat_dtype(), device=dev)
             t["p_att"] = torch.empty_like(t["att"])
@@ -369,6 +375,15 @@ class Captioner(nn.Module):
         feats = self._make_feats(t)
         nbytes = lib.isc_prologue_workspace_bytes(C.byref(d), self._prec, B)
         ws = self._workspace("prologue", nbytes, dev)
+        if bf16_in:
+            with torch.cuda.device(dev):
+                _lib.check(lib.isc_prologue_bf16in(
+                    C.byref(d), _lib.ptr(packed), self._prec, _lib.ptr(fc_feats), _lib.ptr(att_feats),
+                    _lib.ptr(cpt_words), cpt_words.shape[1] if cpt_words is not None else 0,
+                    _lib.ptr(senti_words), _lib.ptr(senti_labels), B, C.byref(feats),
+                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_prologue_bf16in")
+            t["_dims"] = d
+            return t, B
         with torch.cuda.device(dev):
             _lib.check(lib.isc_prologue(
                 C.byref(d), _lib.ptr(packed), self._prec,

@@ -212,6 +212,15 @@ int isc_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
                       out, workspace, workspace_bytes, stream, dropout, nullptr);
 }
 
+int isc_prologue_bf16in(const isc_dims_t* dims, const void* packed, int precision, const void* fc_feats_bf16,
+                        const void* att_feats_bf16, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
+                        const int64_t* senti_labels, int B, const isc_feats_t* out, void* workspace, size_t workspace_bytes,
+                        isc_stream_t stream) {
+  return run_prologue(dims, packed, precision, static_cast<const float*>(fc_feats_bf16), static_cast<const float*>(att_feats_bf16),
+                      cpt_words, n_cpt, senti_words, senti_labels, B, 0, out, workspace, workspace_bytes, stream, nullptr,
+                      nullptr, true);
+}
+
 }  // extern "C"
 
 extern "C" {

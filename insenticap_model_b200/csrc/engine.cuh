@@ -531,7 +531,7 @@ ProWs carve_prologue(const isc_dims_t& d, int precision, int B, void* base) {
 int run_prologue(const isc_dims_t* dims, const void* packed, int precision, const float* fc_feats, const float* att_feats,
                  const int64_t* cpt_words, int n_cpt, const int64_t* senti_words, const int64_t* senti_labels, int B,
                  int seq2seq, const isc_feats_t* out, void* workspace, size_t workspace_bytes, isc_stream_t stream,
-                 const isc_dropout_t* drop, float* fc_embedded);
+                 const isc_dropout_t* drop, float* fc_embedded, bool raw_bf16 = false);
 
 }  // namespace
 }  // namespace isc
@@ -546,10 +546,13 @@ namespace {
 int run_prologue(const isc_dims_t* dims, const void* packed, int precision, const float* fc_feats,
                  const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
                  const int64_t* senti_labels, int B, int seq2seq, const isc_feats_t* out, void* workspace,
-                 size_t workspace_bytes, isc_stream_t stream, const isc_dropout_t* drop, float* fc_embedded) {
+                 size_t workspace_bytes, isc_stream_t stream, const isc_dropout_t* drop, float* fc_embedded, bool raw_bf16) {
+  // raw_bf16: fc_feats / att_feats point at bf16 values (a bf16 feature shard); ISC_PREC_BF16 only, where the fp32
+  // inputs are rounded to exactly these numbers before the GEMMs anyway.
   Ctx c;
   ISC_TRY(make_ctx(c, dims, packed, precision, out, stream));
   ISC_REQUIRE(out != nullptr && B > 0, "out is NULL or B <= 0");
+  ISC_REQUIRE(!raw_bf16 || (precision == ISC_PREC_BF16 && !drop && !seq2seq), "bf16 input features need ISC_PREC_BF16, eval mode");
   const float dscale = drop ? drop->scale : 1.0f;
   ProWs w = carve_prologue(*dims, precision, B, workspace);
   if (!workspace || workspace_bytes < w.total) {
@@ -588,14 +591,19 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
       Planes pfc;
       pfc.hi = w.fc_hi;
       pfc.lo = w.fc_lo;
-      if (tc) ISC_TRY(split_planes(fc_feats, D, w.fc_hi, w.fc_lo, D, B, D, c.s));
+      if (raw_bf16) {
+        pfc.hi = reinterpret_cast<bf16*>(const_cast<float*>(fc_feats));
+        pfc.lo = nullptr;
+      } else if (tc) {
+        ISC_TRY(split_planes(fc_feats, D, w.fc_hi, w.fc_lo, D, B, D, c.s));
+      }
       Epilogue ep;
       ep.bias = pk.bfc;
       ep.act = ACT_RELU;
       Dest dst;
       dst.f32 = out->fc;
       dst.ld = H;
-      ISC_TRY(gemm(precision, operand(fc_feats, D, pfc, D), pk.Wfc.op(), dst, B, H, D, ep, c.s));
+      ISC_TRY(gemm(precision, operand(raw_bf16 ? nullptr : fc_feats, D, pfc, D), pk.Wfc.op(), dst, B, H, D, ep, c.s));
       if (fc_embedded) ISC_TRY(copy_block(fc_embedded, H, out->fc, H, B, H, c.s));
       if (drop && drop->fc) ISC_TRY(launch_apply_mask(out->fc, H, drop->fc, dscale, B, H, RowDest(), c.s));
     }
@@ -630,7 +638,12 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
           patt.lo = w.att_lo;
         }
       }
-      if (tc && fused_split) {
+      if (raw_bf16) {
+        Planes pin;
+        pin.hi = reinterpret_cast<bf16*>(const_cast<float*>(att_feats)) + (long long)b0 * L * D;
+        pin.lo = nullptr;
+        ISC_TRY(gemm_tc(operand(nullptr, 0, pin, D), pk.Watt.op(), dst, (int)rows, H, D, 1, ep, c.s));
+      } else if (tc && fused_split) {
         // the fp32 region features go straight into the GEMM: its converter warps split them in shared memory
         ISC_TRY(gemm_tc_af32(raw, D, pk.Watt.op(), dst, (int)rows, H, D, precision == ISC_PREC_BF16X3 ? 3 : 1, ep, c.s));
       } else {

@@ -175,6 +175,27 @@ def sent_cls_inputs(batch: int, vocab_size: int, max_len: int = 16, seed: int = 
     return seqs, lengths.tolist()
 
 
+def loader_items(n_images: int = 7, vocab_size: int = 50, feat_dim: int = 8, grid: int = 2, seed: int = 41):
+    """Synthetic raw material of the reference's datasets (dataloader.py): per image a name, fc / att features, 1-4
+    captions of 2-24 ids, 0-8 concept ids, 0-14 sentiment-word ids and a label; plus a sentiment corpus. Deterministic."""
+    g = torch.Generator().manual_seed(seed)
+
+    def ids(lo, hi):
+        n = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        return torch.randint(4, vocab_size, (n,), generator=g).tolist()
+
+    names = ["img_%03d.jpg" % i for i in range(n_images)]
+    fc = torch.rand(n_images, feat_dim, generator=g)
+    att = torch.rand(n_images, grid, grid, feat_dim, generator=g)
+    captions = {fn: [[1] + ids(1, 22) + [2] for _ in range(int(torch.randint(1, 5, (1,), generator=g)))] for fn in names}
+    concepts = {fn: ids(0, 8) for fn in names}
+    sentiments = {fn: ids(0, 14) for fn in names}
+    labels = [(fn, int(torch.randint(0, 3, (1,), generator=g))) for fn in names]
+    corpus = [([1] + ids(1, 22) + [2], ids(0, 8), ids(0, 14), int(torch.randint(0, 3, (1,), generator=g))) for _ in range(9)]
+    return {"names": names, "fc": fc, "att": att, "captions": captions, "concepts": concepts, "sentiments": sentiments,
+            "labels": labels, "corpus": corpus}
+
+
 def senti_detector_inputs(batch: int = 6, seed: int = 21) -> torch.Tensor:
     """Region features [B,14,14,2048] for the sentiment-detector tests: random features times a per-image signed scale, so
     that the winning probabilities land on both sides of the 0.7 threshold."""

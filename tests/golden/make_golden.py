@@ -199,6 +199,48 @@ def senti_goldens():
     print("senti scores:", scores.numpy(), "labels:", labels.numpy(), names)
 
 
+def jsonable(x):
+    if torch.is_tensor(x):
+        return {"dtype": str(x.dtype), "shape": list(x.shape), "data": x.reshape(-1).tolist()}
+    if isinstance(x, (tuple, list)):
+        return [jsonable(y) for y in x]
+    if isinstance(x, dict):
+        return {k: jsonable(v) for k, v in x.items()}
+    if isinstance(x, np.generic):
+        return x.item()
+    return x
+
+
+def loader_goldens():
+    """The reference's seven collate functions (dataloader.py:9-151) on synthetic dataset items. The module imports h5py
+    at the top (absent here; only its Dataset classes use it), so an empty stand-in module is registered first."""
+    import json
+    import random
+    import types
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    import dataloader as ref_dl
+    it = syn.loader_items()
+    fc, att = it["fc"].numpy(), it["att"].numpy()
+    row = {fn: i for i, fn in enumerate(it["names"])}
+    items = {
+        "caption": [(fn, fc[row[fn]], att[row[fn]], caps, it["concepts"][fn]) for fn, caps in it["captions"].items()],
+        "rl_fact": [(fn, caps, fc[row[fn]], att[row[fn]], it["concepts"][fn], it["sentiments"][fn]) for fn, caps in it["captions"].items()],
+        "rl_senti": [(fn, fc[row[fn]], att[row[fn]], it["concepts"][fn], it["sentiments"][fn], lab) for fn, lab in it["labels"]],
+        "senti_image": [(fn, att[row[fn]], lab) for fn, lab in it["labels"]],
+        "concept": [(fn, fc[row[fn]], np.eye(1, 20, k=row[fn], dtype=np.int16)[0]) for fn in it["names"]],
+        "senti_corpus_with_sentis": list(it["corpus"]),
+        "senti_sents": [(lab, np.array(cap)) for cap, _, _, lab in it["corpus"]],
+    }
+    out = {}
+    for name, batch in items.items():
+        random.seed(5)  # rl_fact draws one caption per image with random.sample
+        fn = ref_dl.create_collate_fn(name, pad_index=0, max_seq_len=17, num_concepts=5, num_sentiments=10)
+        out[name] = jsonable(fn(list(batch)))
+    with open(os.path.join(HERE, "loader_golden.json"), "w") as f:
+        json.dump(out, f)
+    print("loader goldens:", {k: len(json.dumps(v)) for k, v in out.items()})
+
+
 def sentcls_goldens():
     """The reference's SentenceSentimentClassifier (models/sent_senti_cls.py) on ragged synthetic captions."""
     from models.sent_senti_cls import SentenceSentimentClassifier as RefCls
@@ -222,8 +264,11 @@ if __name__ == "__main__":
         senti_goldens()
     elif "sentcls" in sys.argv:
         sentcls_goldens()
+    elif "loader" in sys.argv:
+        loader_goldens()
     else:
         sentcls_goldens()
+        loader_goldens()
         decode_goldens()
         cider_goldens()
         senti_goldens()
