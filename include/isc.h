@@ -316,6 +316,13 @@ int isc_shard_info(isc_shard_t shard, int64_t* n_images, int* feat_dim, int* n_r
 int64_t isc_shard_find(isc_shard_t shard, const char* name);       /* record index, -1 if absent */
 const char* isc_shard_name(isc_shard_t shard, int64_t index);      /* NULL if out of range */
 int isc_shard_gather(isc_shard_t shard, const int64_t* indices, int64_t n, void* fc_dst, void* att_dst, int n_threads);
+/* Zero-staging variant for shards that fit in host RAM: isc_shard_pin page-locks the records — the mapping in place
+ * (cudaHostRegister, read-only) where the platform allows, else the file is read once into cudaHostAlloc'ed memory —
+ * and isc_shard_copy_to_device then issues one async copy per record and tensor into DEVICE buffers fc_dst [n][D] /
+ * att_dst [n][L][D] (shard dtype) on `stream`. */
+int isc_shard_pin(isc_shard_t shard);
+int isc_shard_copy_to_device(isc_shard_t shard, const int64_t* indices, int64_t n, void* fc_dst, void* att_dst,
+                             isc_stream_t stream);
 
 /* ---- dense contraction on its own (validation / profiling of the tensor-core kernel) -------
  * C[M,N] = act(A[M,K] · W[N,K]^T + bias[N]), fp32 in/out; act 0 none, 1 ReLU, 2 tanh.

@@ -118,6 +118,8 @@ SIGNATURES = {
     "isc_shard_find": (C.c_int64, [_vp, C.c_char_p]),
     "isc_shard_name": (C.c_char_p, [_vp, _i64]),
     "isc_shard_gather": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.c_int]),
+    "isc_shard_pin": (C.c_int, [_vp]),
+    "isc_shard_copy_to_device": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "isc_sentcls_packed_bytes": (_sz, [C.c_int, C.c_int]),
     "isc_sentcls_pack": (C.c_int, [C.c_int, C.c_int] + [_vp] * 14 + [_sz, _vp]),
     "isc_sentcls_workspace_bytes": (_sz, [C.c_int, C.c_int]),

@@ -3,7 +3,8 @@
 // is the bottleneck. A shard is ONE flat file of fixed-size records — fc_feats [D] then att_feats [L][D] per image, fp32
 // (bit-exact with the reference's arrays) or bf16 (what ISC_PREC_BF16 computes in; half the bytes) — that is mmap'ed
 // once; a batch is gathered record by record into the caller's PINNED staging buffers by a few host threads, from where
-// one cudaMemcpyAsync per tensor moves it. Host-only code: nothing here touches the GPU.
+// one cudaMemcpyAsync per tensor moves it (host-only code). Where the platform can page-lock a read-only file mapping,
+// isc_shard_pin + isc_shard_copy_to_device skip the staging pass and DMA each record straight from the page cache.
 //
 // layout (little endian):  [0,64) header | names: n NUL-terminated strings | pad to 256 | records, stride = record_bytes
 #include <fcntl.h>
@@ -19,6 +20,8 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 #include "../../include/isc.h"
 #include "common.cuh"
@@ -39,6 +42,8 @@ struct Shard {
   const uint8_t* map = nullptr;
   size_t map_bytes = 0;
   ShardHeader h;
+  bool pinned = false;   // mapping registered in place
+  uint8_t* copy = nullptr;  // or: the whole file read into page-locked memory (then map points here)
   std::vector<const char*> names;
   std::unordered_map<std::string, int64_t> index;
 };
@@ -55,6 +60,11 @@ uint16_t f32_to_bf16_rne(float f) {  // same rounding as __float2bfloat16_rn (Na
 }
 
 void close_shard(Shard* s) {
+  if (s->map && s->pinned) cudaHostUnregister(const_cast<uint8_t*>(s->map));
+  if (s->copy) {
+    cudaFreeHost(s->copy);
+    s->map = nullptr;
+  }
   if (s->map) munmap(const_cast<uint8_t*>(s->map), s->map_bytes);
   if (s->fd >= 0) close(s->fd);
   delete s;
@@ -228,6 +238,57 @@ int isc_shard_gather(isc_shard_t shard, const int64_t* indices, int64_t n, void*
   pool.reserve(nt);
   for (int t = 0; t < nt; ++t) pool.emplace_back(work, n * t / nt, n * (t + 1) / nt);
   for (auto& th : pool) th.join();
+  return 0;
+}
+
+// Zero-staging path: page-lock the mapping once, then DMA records straight out of the page cache.
+int isc_shard_pin(isc_shard_t shard) {
+  ISC_REQUIRE(shard, "shard_pin: NULL shard");
+  Shard* s = static_cast<Shard*>(shard);
+  if (s->pinned || s->copy) return 0;
+  if (cudaHostRegister(const_cast<uint8_t*>(s->map), s->map_bytes, cudaHostRegisterReadOnly | cudaHostRegisterPortable) ==
+      cudaSuccess) {
+    s->pinned = true;
+    return 0;
+  }
+  cudaGetLastError();  // not every platform can page-lock a read-only file mapping: keep the shard in page-locked RAM
+  uint8_t* buf = nullptr;
+  ISC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&buf), s->map_bytes, cudaHostAllocPortable));
+  const int nt = 8;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([=] {
+      const size_t lo = s->map_bytes * t / nt, hi = s->map_bytes * (t + 1) / nt;
+      memcpy(buf + lo, s->map + lo, hi - lo);
+    });
+  for (auto& th : pool) th.join();
+  const ptrdiff_t shift = buf - s->map;
+  for (auto& nm : s->names) nm += shift;
+  munmap(const_cast<uint8_t*>(s->map), s->map_bytes);
+  s->map = s->copy = buf;
+  return 0;
+}
+
+int isc_shard_copy_to_device(isc_shard_t shard, const int64_t* indices, int64_t n, void* fc_dst, void* att_dst,
+                             isc_stream_t stream) {
+  ISC_REQUIRE(shard && indices && n >= 0 && (fc_dst || att_dst), "shard_copy_to_device: NULL argument");
+  const Shard* s = static_cast<const Shard*>(shard);
+  const ShardHeader& h = s->h;
+  for (int64_t i = 0; i < n; ++i)
+    ISC_REQUIRE(indices[i] >= 0 && (uint64_t)indices[i] < h.n_images,
+                "shard_copy_to_device: index %lld at position %lld out of range [0, %llu)", (long long)indices[i], (long long)i,
+                (unsigned long long)h.n_images);
+  const size_t fc_bytes = (size_t)h.feat_dim * elem_bytes(h.dtype);
+  const size_t att_bytes = fc_bytes * h.n_regions;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int64_t i = 0; i < n; ++i) {
+    const uint8_t* rec = s->map + h.data_offset + (uint64_t)indices[i] * h.record_bytes;
+    if (fc_dst)
+      ISC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(fc_dst) + (size_t)i * fc_bytes, rec, fc_bytes, cudaMemcpyHostToDevice, st));
+    if (att_dst)
+      ISC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(att_dst) + (size_t)i * att_bytes, rec + fc_bytes, att_bytes,
+                               cudaMemcpyHostToDevice, st));
+  }
   return 0;
 }
 

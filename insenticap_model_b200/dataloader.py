@@ -44,6 +44,7 @@ class FeatureShard:
         _lib.check(lib.isc_shard_info(h, C.byref(n), C.byref(d), C.byref(l), C.byref(dt)), "isc_shard_info")
         self.n_images, self.feat_dim, self.n_regions = n.value, d.value, l.value
         self.dtype = torch.bfloat16 if dt.value == 1 else torch.float32
+        self.direct_device = None  # set by pin(): batches are then DMA'd from the page cache, no staging copy
         g = math.isqrt(self.n_regions)
         self.att_shape = (g, g, self.feat_dim) if g * g == self.n_regions else (self.n_regions, self.feat_dim)
 
@@ -61,7 +62,7 @@ class FeatureShard:
         return path
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and _lib is not None:  # (module globals are gone at interpreter shutdown)
             _lib.load().isc_shard_close(self._h)
             self._h = None
 
@@ -85,7 +86,7 @@ class FeatureShard:
             raise IndexError(i)
         return s.decode()
 
-    def gather(self, indices, want_fc=True, want_att=True, threads=8, pin=None):
+    def gather(self, indices, want_fc=True, want_att=True, threads=16, pin=None):
         """-> (fc [n, D] | None, att [n, *att_shape] | None) torch tensors in the shard's dtype; pinned when a GPU is
         present (``pin`` overrides)."""
         idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
@@ -97,6 +98,32 @@ class FeatureShard:
             return fc, att
         _lib.check(_lib.load().isc_shard_gather(self._h, idx.ctypes.data, n, fc.data_ptr() if want_fc else None,
                                                 att.data_ptr() if want_att else None, int(threads)), "isc_shard_gather")
+        return fc, att
+
+    def pin(self, device="cuda:0"):
+        """Page-lock the records (isc_shard_pin: the mapping in place, or a page-locked in-RAM copy of the file) so that
+        batches go host -> HBM without the per-batch staging copy; lazy dataset items then collate straight into CUDA
+        tensors on ``device`` (current stream). For shards that fit in host RAM. Returns False, leaving the staged path
+        in place, if the memory cannot be page-locked."""
+        dev = torch.device(device)
+        with torch.cuda.device(dev):
+            if _lib.load().isc_shard_pin(self._h) != 0:
+                return False
+        self.direct_device = dev
+        return True
+
+    def copy_to_device(self, indices, want_fc=True, want_att=True):
+        """-> (fc, att) CUDA tensors on ``direct_device``, copies queued on its current stream (needs pin())."""
+        dev = self.direct_device
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
+        n = idx.shape[0]
+        fc = torch.empty((n, self.feat_dim), dtype=self.dtype, device=dev) if want_fc else None
+        att = torch.empty((n,) + self.att_shape, dtype=self.dtype, device=dev) if want_att else None
+        if n:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.load().isc_shard_copy_to_device(self._h, idx.ctypes.data, n, fc.data_ptr() if want_fc else None,
+                                                                att.data_ptr() if want_att else None, _lib.stream_ptr(dev)),
+                           "isc_shard_copy_to_device")
         return fc, att
 
     def __getitem__(self, fn):
@@ -122,18 +149,20 @@ def _stack_features(feats):
     """The reference's ``torch.FloatTensor(np.array(feats))``; lazy references become one batched, threaded gather."""
     if feats and isinstance(feats[0], _Lazy):
         sh, which = feats[0].shard, feats[0].which
+        if sh.direct_device is not None:
+            fc, att = sh.copy_to_device([f.idx for f in feats], want_fc=which == "fc", want_att=which == "att")
+            return fc if which == "fc" else att
         fc, att = sh.gather([f.idx for f in feats], want_fc=which == "fc", want_att=which == "att")
         return fc if which == "fc" else att
     return torch.from_numpy(np.array(feats, dtype=np.float32))
 
 
 def _pad_ids(rows, width, pad_index):
-    out = torch.full((len(rows), width), pad_index, dtype=torch.long)
-    for i, r in enumerate(rows):
-        r = list(r)[:width]
-        if r:
-            out[i, :len(r)] = torch.as_tensor(r, dtype=torch.long)
-    return out
+    padded = []
+    for r in rows:
+        r = [int(x) for x in r[:width]]
+        padded.append(r + [pad_index] * (width - len(r)))
+    return torch.tensor(padded, dtype=torch.long).reshape(len(rows), width)
 
 
 def _pad_captions(caps, max_seq_len, pad_index):
@@ -379,8 +408,12 @@ class DevicePrefetcher:
 
         def work():
             try:
-                for batch in self.loader:
-                    with torch.cuda.stream(stream):
+                it = iter(self.loader)
+                while True:
+                    with torch.cuda.stream(stream):  # a pinned shard's collate queues its copies on this stream too
+                        batch = next(it, None)
+                        if batch is None:
+                            break
                         dev_batch = _to_device(batch, self.device)
                         ev = torch.cuda.Event()
                         ev.record(stream)

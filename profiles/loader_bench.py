@@ -39,13 +39,17 @@ try:
     concepts = {fn: cpts[i].tolist() for i, fn in enumerate(names)}
     sentiments = {fn: sentis[i].tolist() for i, fn in enumerate(names)}
     labs = [(fn, int(labels[i])) for i, fn in enumerate(names)]
-    for k, prec in (("fp32", "bf16x3"), ("bf16", "bf16")):
+    for k, prec, pin in (("fp32", "bf16x3", False), ("bf16", "bf16", False), ("fp32", "bf16x3", True), ("bf16", "bf16", True)):
         m = Captioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS), precision=prec)
         m.load_state_dict(syn.synthetic_state_dict(V, 0))
         m = m.cuda().eval()
-        loader = dl.get_rl_senti_dataloader(paths[k], paths[k], concepts, sentiments, labs, 0, 5, 10, batch_size=B, shuffle=True)
+        sh = dl.FeatureShard(paths[k])
+        if pin and not sh.pin("cuda:0"):
+            print("cannot page-lock the mapping on this platform")
+            continue
+        loader = dl.get_rl_senti_dataloader(sh, sh, concepts, sentiments, labs, 0, 5, 10, batch_size=B, shuffle=True)
         with torch.no_grad():
-            for epoch in range(3):
+            for epoch in range(6):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 outs = []
@@ -53,8 +57,8 @@ try:
                     outs.append(m.beam_search(f, a, s, l, 3, 1, 16)[0])
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
-                print("shard(%s) -> prefetch -> beam-3 decode (%s), epoch %d: %d images in %.1f ms = %.0f captions/s"
-                      % (k, prec, epoch, N, dt * 1e3, N / dt))
+                print("shard(%s%s) -> prefetch -> beam-3 decode (%s), epoch %d: %d images in %.1f ms = %.0f captions/s"
+                      % (k, ", page-locked" if pin else "", prec, epoch, N, dt * 1e3, N / dt))
 finally:
     for p in paths.values():
         os.remove(p)

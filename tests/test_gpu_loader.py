@@ -70,3 +70,23 @@ def test_bf16_shard_is_bit_identical_in_bf16_mode_and_rejected_elsewhere(corpus)
         a = x3.beam_search(fc16.cuda(), att16.cuda(), meta["sentis"].cuda(), meta["lab"].cuda(), 3, 1, 16)
         b = x3.beam_search(fc16.float().cuda(), att16.float().cuda(), meta["sentis"].cuda(), meta["lab"].cuda(), 3, 1, 16)
         assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+def test_pinned_shard_collates_straight_into_device_tensors(corpus):
+    """isc_shard_pin + isc_shard_copy_to_device: records DMA'd from the page cache, no staging copy; same bytes."""
+    paths, meta = corpus
+    for kind in ("fp32", "bf16"):
+        sh = dl.FeatureShard(paths[kind])
+        assert sh.pin("cuda:0") and sh.name(3) == meta["names"][3] and sh.index(meta["names"][5]) == 5
+        loader = dl.get_rl_senti_dataloader(sh, sh, meta["concepts"], meta["sentiments"], meta["labels"], 0, 5, 10,
+                                            batch_size=7, shuffle=False)
+        seen = 0
+        for fns, fc, att, cpts, sentis, labels in dl.DevicePrefetcher(loader, "cuda:0", depth=2):
+            n = len(fns)
+            want_fc, want_att = meta["fc"][seen:seen + n], meta["att"][seen:seen + n]
+            if kind == "bf16":
+                want_fc, want_att = want_fc.bfloat16(), want_att.bfloat16()
+            assert fc.is_cuda and torch.equal(fc.cpu(), want_fc) and torch.equal(att.cpu(), want_att)
+            assert labels.is_cuda and labels.tolist() == [l for _, l in meta["labels"][seen:seen + n]]
+            seen += n
+        assert seen == N
