@@ -176,7 +176,8 @@ int isc_pack_weights(const isc_dims_t* dims, const isc_weights_t* w, int precisi
     // W1b = [h_lang_prev | h_att_prev] columns; xt_gates = ReLU(E) . W_ih[:, 2H:3H]^T through the tensor-core GEMM
     ISC_TRY(copy_block(p.W1b.f32, 2 * H, w->att_lstm_w_ih, 3 * H, G4, H, s));
     ISC_TRY(copy_block(p.W1b.f32 + H, 2 * H, w->att_lstm_w_hh, H, G4, H, s));
-    ISC_TRY(finish_mat(p.W1b, precision, s));
+    ISC_TRY(split_planes_gate_interleaved(p.W1b.f32, 2 * H, p.W1b.hi, p.W1b.lo, 2 * H, H, 2 * H, s));
+    ISC_TRY(split_planes_gate_interleaved(p.W4.f32, 3 * H, p.W4g.hi, p.W4g.lo, 3 * H, H, 3 * H, s));
     ISC_TRY(launch_embed_rows(nullptr, V, 1, 0, 0, V, p.emb, [&] {
       RowDest r;
       r.hi = p.erelu_hi;

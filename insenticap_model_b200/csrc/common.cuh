@@ -126,9 +126,10 @@ int gemm_simt(const Operand& A, const Operand& W, const Dest& C, int M, int N, i
 int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, int passes,
             const Epilogue& ep, cudaStream_t stream);
 // LSTM cell fused into the gate GEMM's epilogue (nn.LSTMCell, gate order i,f,g,o): the [M,4H] pre-activations are
-// never written. The B tile of a 128-column output tile is loaded as 8 boxes of 16 weight rows —
-// [i f g o] of hidden units 32t..32t+15, then [i f g o] of units 32t+16..32t+31 — so the thread that owns a row and
-// 64 accumulator columns holds all four gates of 16 units. The weight matrix keeps the reference's row order.
+// never written. The weight planes W must be GATE-INTERLEAVED (split_planes_gate_interleaved: row = 16-unit group * 64 +
+// gate * 16 + unit), so the B rows of an output tile — [i f g o] of units 16g..16g+15 per 64 columns — are contiguous
+// (one TMA box per 128 columns) and the thread that owns a row and 64 accumulator columns holds all four gates of 16
+// units. Tiles are 256 columns wide where that fills the SMs evenly and 128 wide for the rest of a row (lstm_tile).
 struct LstmEpilogue {
   const int* parent = nullptr;   // [M] row of the previous state this row continues from (beam reorder), or null
   const float* c_prev = nullptr; // [*, H]
@@ -175,6 +176,9 @@ inline int gemm(int precision, const Operand& A, const Operand& W, const Dest& C
 // max_blocks > 0 caps the grid (used when the split shares the SMs with a persistent GEMM on another stream)
 int split_planes(const float* src, int64_t ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo,
                  int64_t ld_dst, int64_t rows, int cols, cudaStream_t stream, int max_blocks = 0);
+// the same for an LSTM weight [4 * hidden, cols] (gate-major rows i, f, g, o), planes written gate-interleaved
+int split_planes_gate_interleaved(const float* src, long long ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld_dst,
+                                  int hidden, int cols, cudaStream_t stream);
 
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);

@@ -89,7 +89,8 @@ struct Packed {
   // decode-only shortcut for the attention LSTM's word term: xt_gates[v] = W_ih[:, 2H:3H] . ReLU(E[v]) for every word
   // (tensor-core precisions). The gate GEMM then contracts over [h_lang_prev | h_att_prev] only (W1b, K = 2H) and its
   // fused LSTM epilogue adds the row xt_gates[it] — a third of that GEMM's flops becomes an 8 KB gather per row.
-  Mat W1b;           // [4H, 2H] = W1 columns [h_lang_prev | h_att_prev]
+  Mat W1b;           // [4H, 2H] = W1 columns [h_lang_prev | h_att_prev]; planes GATE-INTERLEAVED (fused LSTM GEMM only)
+  Mat W4g;           // gate-interleaved planes of W4 for the fused LSTM GEMM (no fp32 copy)
   float* xt_gates;   // [V, 4H]
   bf16 *erelu_hi, *erelu_lo;  // [V, H] planes of ReLU(E), operand of the GEMM that builds xt_gates
   float *b1, *b2, *b3, *b4, *b5, *bfc, *batt, *ba2a, *bs2a, *bcpt, *bl2w;
@@ -120,6 +121,10 @@ Packed carve_packed(const isc_dims_t& d, int precision, void* base) {
   p.erelu_hi = p.erelu_lo = nullptr;
   if (precision != ISC_PREC_FP32) {
     mat(p.W1b, G4, 2 * H);
+    p.W4g.rows = G4;
+    p.W4g.cols = 3 * H;
+    p.W4g.hi = b.take<bf16>((size_t)G4 * 3 * H);
+    if (precision == ISC_PREC_BF16X3) p.W4g.lo = b.take<bf16>((size_t)G4 * 3 * H);
     p.xt_gates = b.take<float>((size_t)V * G4);
     p.erelu_hi = b.take<bf16>((size_t)V * H);
     if (precision == ISC_PREC_BF16X3) p.erelu_lo = b.take<bf16>((size_t)V * H);
@@ -441,7 +446,7 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     le.x_col = 0;
     le.mask = io.out_mask;
     le.scale = io.drop_scale;
-    ISC_TRY(gemm_tc_lstm(operand(nullptr, 0, w.pX2, 3 * H), pk.W4.op(), M, 3 * H, passes, pk.b4, nullptr, 0, 1, le, c.s));
+    ISC_TRY(gemm_tc_lstm(operand(nullptr, 0, w.pX2, 3 * H), pk.W4g.op(), M, 3 * H, passes, pk.b4, nullptr, 0, 1, le, c.s));
   } else {
     Epilogue ep;
     ep.bias = pk.b4;

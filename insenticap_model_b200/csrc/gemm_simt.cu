@@ -78,7 +78,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
 // (beside a persistent GEMM, see run_prologue) and must still cover the HBM latency
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ src, long long ld_src,
                                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                    long long ld_dst, long long rows, int cols) {
+                                                    long long ld_dst, long long rows, int cols, int gate_hh) {
+  // gate_hh > 0: the source is an LSTM weight [4 * gate_hh][cols] in nn.LSTMCell's gate-major row order; the planes are
+  // written GATE-INTERLEAVED — destination row r = (16-unit group) * 64 + gate * 16 + unit — so that the rows of all four
+  // gates of a group of hidden units are contiguous and one TMA box fetches a fused-LSTM tile (gemm_tc_lstm)
   const int cols4 = cols >> 2;  // cols % 4 == 0 enforced by the host
   const long long total = rows * cols4;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -92,7 +95,8 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ sr
       if (i < total) {
         r[u] = i / cols4;
         c[u] = (int)(i - r[u] * cols4) * 4;
-        v[u] = __ldg(reinterpret_cast<const float4*>(src + r[u] * ld_src + c[u]));
+        const long long rs = gate_hh > 0 ? ((r[u] >> 4) & 3) * gate_hh + (r[u] >> 6) * 16 + (r[u] & 15) : r[u];
+        v[u] = __ldg(reinterpret_cast<const float4*>(src + rs * ld_src + c[u]));
       }
     }
 #pragma unroll
@@ -136,7 +140,20 @@ int split_planes(const float* src, int64_t ld_src, __nv_bfloat16* hi, __nv_bfloa
   const int cap = max_blocks > 0 ? max_blocks : 148 * 8;
   if (blocks > cap) blocks = cap;
   ProfScope ps(ISC_K_POINTWISE, (double)rows * cols * (4.0 + 2.0 + (lo ? 2.0 : 0.0)), stream);
-  split_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, rows, cols);
+  split_kernel<<<blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, rows, cols, 0);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
+int split_planes_gate_interleaved(const float* src, long long ld_src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long ld_dst,
+                                  int hidden, int cols, cudaStream_t stream) {
+  ISC_REQUIRE(src && hi && hidden > 0 && hidden % 16 == 0 && cols > 0 && cols % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0,
+              "split_planes_gate_interleaved: bad arguments");
+  const long long rows = 4LL * hidden, total = rows * (cols >> 2);
+  long long blocks = (total + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope ps(ISC_K_POINTWISE, (double)rows * cols * (4.0 + 2.0 + (lo ? 2.0 : 0.0)), stream);
+  split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(src, ld_src, hi, lo, ld_dst, rows, cols, hidden);
   ISC_LAUNCH_CHECK();
   return 0;
 }

@@ -83,6 +83,7 @@ struct EpiParams {
   LogitsSelect sel;
   // EPI_LSTM: the LSTM cell applied to the four gate pre-activations of each hidden unit
   LstmEpilogue lstm;
+  int lstm_wide;  // EPI_LSTM with BN = 256: 256-column tiles per 128-row block, the rest of the row in 128-column tiles
   // 3x3 convolution as ONE GEMM over a zero-bordered 16x16 grid per image (rows = image * 256 + y * 16 + x): the K loop
   // runs over 9 segments of seg_kb k-blocks; segment s reads the A rows shifted by seg_off[s] = dy * 16 + dx (TMA
   // zero-fills rows outside the tensor), W is [N][9 * C] with K index s * C + c. seg_kb == 0: plain GEMM.
@@ -242,6 +243,32 @@ __device__ __forceinline__ float act_ct(float v) {
   return v;
 }
 
+// EPI_LSTM tile list. A tile holds all four gates of its hidden units (columns = [i f g o] x 16 units per 64-column
+// group). BN = 128: uniform 32-unit tiles. BN = 256: MIXED widths — per 128-row block `wide` tiles of 64 units (256
+// columns) first, then the remaining units in 32-unit (128-column) tiles, enumerated wide tiles first: with
+// M = 3072 (24 row blocks) and wide = 6 that is 144 wide tiles + 96 narrow ones, i.e. one wide and (for 92 CTAs) one
+// narrow tile per SM instead of 1.3 waves of wide or 2.6 waves of narrow tiles.
+template <int BN>
+__device__ __forceinline__ void lstm_tile(int tile, int tiles_m, int tiles_n, int wide, int& m0, int& u0, int& width) {
+  if (BN == 128) {
+    m0 = (tile / tiles_n) * BM;
+    u0 = (tile % tiles_n) * 32;
+    width = 128;
+    return;
+  }
+  const int n_wide = tiles_m * wide;
+  if (tile < n_wide) {
+    m0 = (tile / wide) * BM;
+    u0 = (tile % wide) * 64;
+    width = 256;
+  } else {
+    const int nn = (tiles_n - wide) * 2, t = tile - n_wide;
+    m0 = (t / nn) * BM;
+    u0 = wide * 64 + (t % nn) * 32;
+    width = 128;
+  }
+}
+
 template <int PASSES, int BN, int ACT, int EPI, int CG, int AF>
 __global__ void __launch_bounds__(NUM_THREADS + (AF ? 128 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -267,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int num_kb = ep.seg_kb > 0 ? 9 * ep.seg_kb : (ep.K + BK - 1) / BK;
   const int tiles_n = (ep.N + BN - 1) / BN;
   const int tiles_m = (ep.M + CG * BM - 1) / (CG * BM);  // CG = 2: a tile is 256 rows, 128 per CTA of the pair
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = (EPI == EPI_LSTM && BN == 256) ? tiles_m * (ep.lstm_wide + (tiles_n - ep.lstm_wide) * 2) : tiles_m * tiles_n;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int walker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // the pair walks the tile list together
   const int walkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -317,8 +344,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       int it = 0;
       for (int tile = walker; tile < num_tiles; tile += walkers) {
-        const int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM;
-        const int n0 = (tile % tiles_n) * BN + cta_rank * C::kBRows;  // CG = 2: this CTA's half of the B rows
+        int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM;
+        int n0 = (tile % tiles_n) * BN + cta_rank * C::kBRows;  // CG = 2: this CTA's half of the B rows
+        int lw = BN;                                            // EPI_LSTM: n0 = first hidden unit, lw = tile width
+        if (EPI == EPI_LSTM) lstm_tile<BN>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, n0, lw);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -350,16 +379,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_2d_pair(stb, &map_b_hi, &full_bar[s], k0, n0);
             if (PASSES == 3) tma_load_2d_pair(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
           } else if (EPI == EPI_LSTM) {
-            // gate-interleaved B tile: box q = 16 weight rows of gate (q & 3) for the unit half (q >> 2) of this tile
-            mbar_expect_tx(&full_bar[s], C::kStageBytes);
+            // the weight planes are gate-interleaved: the tile's B rows start at 4 * (first unit), one 128-row box per
+            // 128 columns
+            mbar_expect_tx(&full_bar[s], C::kPlanes * (C::kATileBytes + lw * BK * 2));
             tma_load_2d(st, &map_a_hi, &full_bar[s], k0, m0);
             if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
-            const int u0 = (tile % tiles_n) * 32;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int wrow = (q & 3) * (ep.N >> 2) + u0 + (q >> 2) * 16;
-              tma_load_2d(stb + q * 16 * BK * 2, &map_b_hi, &full_bar[s], k0, wrow);
-              if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes + q * 16 * BK * 2, &map_b_lo, &full_bar[s], k0, wrow);
+            for (int q = 0; q < BN / 128; ++q) {
+              if (q * 128 < lw) {
+                tma_load_2d(stb + q * 128 * BK * 2, &map_b_hi, &full_bar[s], k0, 4 * n0 + q * 128);
+                if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes + q * 128 * BK * 2, &map_b_lo, &full_bar[s], k0, 4 * n0 + q * 128);
+              }
             }
           } else {
             mbar_expect_tx(&full_bar[s], C::kStageBytes);
@@ -382,6 +412,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         uint32_t accumulate = 0;
+        uint32_t idesc_t = idesc;
+        if (EPI == EPI_LSTM && BN == 256 && tile >= tiles_m * ep.lstm_wide) idesc_t = umma_idesc_bf16(BM, 128);  // narrow tile
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -398,9 +430,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int k = 0; k < BK / 16; ++k) {
               // +32 B per 16-element K step inside the 128 B swizzle atom
               if (CG == 2)
-                umma_bf16_pair(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc, accumulate);
+                umma_bf16_pair(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc_t, accumulate);
               else
-                umma_bf16(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc, accumulate);
+                umma_bf16(tmem_d, umma_desc_sw<2 * BK>(a + k * 32), umma_desc_sw<2 * BK>(b + k * 32), idesc_t, accumulate);
               accumulate = 1;
             }
           }
@@ -534,28 +566,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       __syncwarp();  // bias slice is rewritten for the next tile
     }
   } else if (EPI == EPI_LSTM) {
-    // ===================== epilogue: LSTM cell on the gate pre-activations (tile columns = [i f g o] x 16 units, twice) =====
+    // ===================== epilogue: LSTM cell on the gate pre-activations (tile columns = [i f g o] x 16 units per group) =====
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
-    const int half = ew >> 2;      // which 16 of the tile's 32 hidden units
+    const int half = ew >> 2;      // which half of the tile's 16-unit groups
     const LstmEpilogue& L = ep.lstm;
     const int HH = ep.N >> 2;      // hidden size
     int j = 0;
     for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
-      const int m0 = (tile / tiles_n) * BM;
-      const int u0 = (tile % tiles_n) * 32 + half * 16;  // first hidden unit of this thread
+      int m0, ut, width;
+      lstm_tile<BN>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, ut, width);
+      const int nsub = width >> 7;  // 16-unit groups per warp: 1 (128-column tile) or 2 (256-column tile)
       const int as = j & 1;
       const long long row = m0 + quarter * 32 + lane;
       const bool live = row < ep.M;
       const long long src = (live && L.parent) ? L.parent[row] : row;
-      float cp[16];
-      if (live) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(L.c_prev + src * HH + u0) + q);
-          cp[4 * q] = t.x; cp[4 * q + 1] = t.y; cp[4 * q + 2] = t.z; cp[4 * q + 3] = t.w;
-        }
-      }
       const float* radd = ep.rowadd ? ep.rowadd + (long long)((unsigned)row / (unsigned)ep.rows_per_group) * ep.ld_rowadd : nullptr;
       const float* gat = nullptr;
       if (live && L.gather_tab) {
@@ -563,68 +588,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         tok = tok < 0 ? 0 : (tok >= L.gather_rows ? L.gather_rows - 1 : tok);
         gat = L.gather_tab + tok * ep.N;
       }
-      mbar_wait(&acc_full[as], (j >> 1) & 1);
-      tcgen05_fence_after();
-      float vif[32], vgo[32];  // [i(16) | f(16)], [g(16) | o(16)]
-      const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + half * 64;
-      tmem_ld32(tcol, vif);
-      tmem_ld32(tcol + 32, vgo);
-      // the accumulator stage is drained: release it to the MMA warp before the math and the stores
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
-      if (live) {
-        // same association as the unfused path: (acc + bias) + rowadd, then nn.LSTMCell's pointwise math
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float* v = (g < 2 ? vif : vgo) + (g & 1) * 16;
-          const int col = g * HH + u0;
+      for (int ss = 0; ss < nsub; ++ss) {
+        const int grp = half * nsub + ss;
+        const int u0 = ut + grp * 16;  // first hidden unit of this thread in this pass
+        float cp[16];
+        if (live) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (ep.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + q);
-              v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
-            }
-            if (radd) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(radd + col) + q);
-              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-            }
-            if (gat) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(gat + col) + q);
-              v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
-            }
+            const float4 t = __ldg(reinterpret_cast<const float4*>(L.c_prev + src * HH + u0) + q);
+            cp[4 * q] = t.x; cp[4 * q + 1] = t.y; cp[4 * q + 2] = t.z; cp[4 * q + 3] = t.w;
           }
         }
-        float hn[16], cn[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          cn[u] = sigmoid_accurate(vif[16 + u]) * cp[u] + sigmoid_accurate(vif[u]) * tanhf(vgo[u]);
-          hn[u] = sigmoid_accurate(vgo[16 + u]) * tanhf(cn[u]);
+        if (ss == 0) {
+          mbar_wait(&acc_full[as], (j >> 1) & 1);
+          tcgen05_fence_after();
         }
-        float4* co = reinterpret_cast<float4*>(L.c_out + row * HH + u0);
-        float4* ho = reinterpret_cast<float4*>(L.h_out + row * HH + u0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          co[q] = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
-          ho[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+        float vif[32], vgo[32];  // [i(16) | f(16)], [g(16) | o(16)]
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + grp * 64;
+        tmem_ld32(tcol, vif);
+        tmem_ld32(tcol + 32, vgo);
+        if (ss == nsub - 1) {
+          // the accumulator stage is drained: release it to the MMA warp before the math and the stores
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
         }
-        if (L.x_hi) {
-          if (L.mask) {
-            const uint4 k = __ldg(reinterpret_cast<const uint4*>(L.mask + row * HH + u0));
-            const unsigned char* kb = reinterpret_cast<const unsigned char*>(&k);
+        if (live) {
+          // same association as the unfused path: (acc + bias) + rowadd, then nn.LSTMCell's pointwise math
 #pragma unroll
-            for (int u = 0; u < 16; ++u) hn[u] *= kb[u] ? L.scale : 0.f;
+          for (int g = 0; g < 4; ++g) {
+            float* v = (g < 2 ? vif : vgo) + (g & 1) * 16;
+            const int col = g * HH + u0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (ep.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + q);
+                v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+              }
+              if (radd) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(radd + col) + q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+              }
+              if (gat) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(gat + col) + q);
+                v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+              }
+            }
           }
-          __align__(16) __nv_bfloat16 hh[16], ll[16];
+          float hn[16], cn[16];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) split_bf16(hn[u], hh[u], ll[u]);
-          uint4* dh = reinterpret_cast<uint4*>(L.x_hi + row * L.ldx + L.x_col + u0);
-          dh[0] = reinterpret_cast<const uint4*>(hh)[0];
-          dh[1] = reinterpret_cast<const uint4*>(hh)[1];
-          if (L.x_lo) {
-            uint4* dl = reinterpret_cast<uint4*>(L.x_lo + row * L.ldx + L.x_col + u0);
-            dl[0] = reinterpret_cast<const uint4*>(ll)[0];
-            dl[1] = reinterpret_cast<const uint4*>(ll)[1];
+          for (int u = 0; u < 16; ++u) {
+            cn[u] = sigmoid_accurate(vif[16 + u]) * cp[u] + sigmoid_accurate(vif[u]) * tanhf(vgo[u]);
+            hn[u] = sigmoid_accurate(vgo[16 + u]) * tanhf(cn[u]);
+          }
+          float4* co = reinterpret_cast<float4*>(L.c_out + row * HH + u0);
+          float4* ho = reinterpret_cast<float4*>(L.h_out + row * HH + u0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            co[q] = make_float4(cn[4 * q], cn[4 * q + 1], cn[4 * q + 2], cn[4 * q + 3]);
+            ho[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+          }
+          if (L.x_hi) {
+            if (L.mask) {
+              const uint4 k = __ldg(reinterpret_cast<const uint4*>(L.mask + row * HH + u0));
+              const unsigned char* kb = reinterpret_cast<const unsigned char*>(&k);
+#pragma unroll
+              for (int u = 0; u < 16; ++u) hn[u] *= kb[u] ? L.scale : 0.f;
+            }
+            __align__(16) __nv_bfloat16 hh[16], ll[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) split_bf16(hn[u], hh[u], ll[u]);
+            uint4* dh = reinterpret_cast<uint4*>(L.x_hi + row * L.ldx + L.x_col + u0);
+            dh[0] = reinterpret_cast<const uint4*>(hh)[0];
+            dh[1] = reinterpret_cast<const uint4*>(hh)[1];
+            if (L.x_lo) {
+              uint4* dl = reinterpret_cast<uint4*>(L.x_lo + row * L.ldx + L.x_col + u0);
+              dl[0] = reinterpret_cast<const uint4*>(ll)[0];
+              dl[1] = reinterpret_cast<const uint4*>(ll)[1];
+            }
           }
         }
       }
@@ -1017,18 +1058,40 @@ static int launch_conv(const float* A32, const Operand& A, int64_t lda, const Op
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, 1, AF32>(m, ep, grid, stream);
 }
 
-template <int PASSES>
+// Number of 256-column tiles per 128-row block for the mixed-width LSTM tile list (lstm_tile): the static round-robin
+// walk is simulated for every choice and the cheapest one kept (cost of a wide tile 2, of a narrow one 1.15 — it
+// moves more operand bytes per flop — plus 0.25 per tile for fill and epilogue).
+static int lstm_wide_tiles(int M) {
+  const int tiles_m = (M + BM - 1) / BM, slots = num_sms(), groups = (4 * H) / 256;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int w = groups; w >= 0; --w) {
+    const int n_wide = tiles_m * w, total = n_wide + tiles_m * (groups - w) * 2;
+    double worst = 0;
+    for (int c = 0; c < slots && c < total; ++c) {
+      double cost = 0;
+      for (int t = c; t < total; t += slots) cost += (t < n_wide ? 2.0 : 1.15) + 0.25;
+      worst = cost > worst ? cost : worst;
+    }
+    if (worst < best_cost - 1e-9) {
+      best_cost = worst;
+      best = w;
+    }
+  }
+  return best;
+}
+
+template <int PASSES, int BN>
 static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const float* bias, const float* rowadd,
                        int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream) {
-  constexpr int BN = 128;
   using C = Cfg<PASSES, BN, 1>;
   const int N = 4 * H;
   Maps m;
   ISC_TRY(make_map(&m.a_hi, A.hi, M, K, A.ldp, BM, C::kBK));
-  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, 16, C::kBK));  // 16-row boxes: see the EPI_LSTM producer
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, 128, C::kBK));  // gate-interleaved rows, one box per 128 columns
   if (PASSES == 3) {
     ISC_TRY(make_map(&m.a_lo, A.lo, M, K, A.ldp, BM, C::kBK));
-    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, 16, C::kBK));
+    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, 128, C::kBK));
   } else {
     m.a_lo = m.a_hi;
     m.b_lo = m.b_hi;
@@ -1043,7 +1106,12 @@ static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const f
   ep.N = N;
   ep.K = K;
   ep.lstm = lstm;
-  const int grid = persistent_grid<BN, 1>(M, N);
+  int grid = persistent_grid<BN, 1>(M, N);
+  if (BN == 256) {
+    ep.lstm_wide = lstm_wide_tiles(M);
+    const int tiles = ((M + BM - 1) / BM) * (ep.lstm_wide + (N / 256 - ep.lstm_wide) * 2);
+    grid = tiles < num_sms() ? tiles : num_sms();
+  }
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_LSTM, 1>(m, ep, grid, stream);
 }
@@ -1123,6 +1191,7 @@ int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, c
                  int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream) {
   if (M <= 0) return 0;
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_lstm: K=%d must be a positive multiple of 8", K);
+  static const bool mixed = getenv("ISC_LSTM_UNIFORM_TILES") == nullptr;  // set to use the uniform 128-column tile list
   ISC_REQUIRE(A.hi && W.hi && lstm.c_prev && lstm.h_out && lstm.c_out, "gemm_tc_lstm: planes / state buffers missing");
   ISC_REQUIRE(!lstm.x_hi || ((lstm.ldx % 8) == 0 && (lstm.x_col % 8) == 0 && (reinterpret_cast<uintptr_t>(lstm.x_hi) & 15) == 0),
               "gemm_tc_lstm: operand planes must be 16-byte aligned");
@@ -1131,9 +1200,11 @@ int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, c
               "gemm_tc_lstm: rowadd must be 16-byte aligned");
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc_lstm: bf16 lo planes missing for the 3-pass mode");
-    return tc::launch_lstm<3>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+    if (!mixed) return tc::launch_lstm<3, 128>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+    return tc::launch_lstm<3, 256>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
   }
-  return tc::launch_lstm<1>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+  if (!mixed) return tc::launch_lstm<1, 128>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+  return tc::launch_lstm<1, 256>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
 }
 
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,

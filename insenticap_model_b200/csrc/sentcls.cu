@@ -152,7 +152,8 @@ int isc_sentcls_pack(int vocab, int n_cls, const float* word_embed, const float*
   ISC_TRY(add_vec(p.bc0, cls0_b, nullptr, H, s));
   ISC_TRY(add_vec(p.bc3, cls3_b, nullptr, n_cls, s));
   ISC_TRY(copy_block(p.emb, H, word_embed, H, vocab, H, s));
-  const Mat* mats[] = {&p.Wl, &p.We0, &p.We2, &p.Wc0, &p.Wc3};
+  ISC_TRY(split_planes_gate_interleaved(p.Wl.f32, 2 * H, p.Wl.hi, p.Wl.lo, 2 * H, H, 2 * H, s));  // fused LSTM GEMM layout
+  const Mat* mats[] = {&p.We0, &p.We2, &p.Wc0, &p.Wc3};
   for (const Mat* m : mats) ISC_TRY(finish_mat(*m, ISC_PREC_BF16X3, s));
   return 0;
 }
