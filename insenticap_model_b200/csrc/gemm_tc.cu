@@ -338,6 +338,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's shared memory, TMEM and kernel parameters: it may run while the previous
+  // kernel of the stream is still draining (programmatic dependent launch); global memory is read from here on
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (one elected lane) =====================
@@ -898,7 +902,7 @@ static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStrea
     cfg.numAttrs = 1;
     ISC_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a_hi, m.a_lo, m.b_hi, m.b_lo, ep));
   } else {
-    kern<<<grid, NUM_THREADS, smem, stream>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, ep);
+    ISC_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), smem, stream, m.a_hi, m.a_lo, m.b_hi, m.b_lo, ep));
   }
   ISC_LAUNCH_CHECK();
   return 0;

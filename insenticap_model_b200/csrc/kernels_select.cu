@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(NT) beam_select_kernel(BeamParams p) {
 template <int SEL_K>
 __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
   constexpr int SEL_REC = sel_rec(SEL_K);
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, K = p.K, t = p.t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int kk = warp; kk < K; kk += 4) {
@@ -448,6 +450,8 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
 
 // Fused greedy pick (sample_max = 1): a warp per row takes the argmax and the normaliser from the records.
 __global__ void __launch_bounds__(256) greedy_merge_kernel(GreedyParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int t = p.t;
   if (b >= p.B) return;
@@ -538,7 +542,7 @@ int launch_greedy_select(const GreedyParams& p, cudaStream_t stream) {
   if (p.rec) {
     ISC_REQUIRE(p.sample_mode == 0, "fused greedy pick only serves sample_max = 1");
     ProfScope ps(ISC_K_SELECT, (double)p.B * p.np * sel_rec(4) * 4.0, stream);
-    greedy_merge_kernel<<<(p.B + 7) / 8, 256, 0, stream>>>(p);
+    ISC_CUDA(launch_pdl(greedy_merge_kernel, dim3((p.B + 7) / 8), dim3(256), 0, stream, p));
     ISC_LAUNCH_CHECK();
     return 0;
   }
@@ -554,8 +558,8 @@ int launch_beam_select(const BeamParams& p, cudaStream_t stream) {
     ISC_REQUIRE(p.K <= p.k_sel && (p.k_sel == 4 || p.k_sel == 8), "fused beam merge: beam size %d exceeds the %d candidates per slice",
                 p.K, p.k_sel);
     ProfScope ps(ISC_K_SELECT, (double)p.B * p.K * p.np * sel_rec(p.k_sel) * 4.0, stream);
-    if (p.k_sel == 8) beam_merge_kernel<8><<<p.B, 128, 0, stream>>>(p);
-    else beam_merge_kernel<4><<<p.B, 128, 0, stream>>>(p);
+    if (p.k_sel == 8) ISC_CUDA(launch_pdl(beam_merge_kernel<8>, dim3(p.B), dim3(128), 0, stream, p));
+    else ISC_CUDA(launch_pdl(beam_merge_kernel<4>, dim3(p.B), dim3(128), 0, stream, p));
     ISC_LAUNCH_CHECK();
     return 0;
   }

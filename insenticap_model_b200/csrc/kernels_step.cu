@@ -16,6 +16,8 @@ namespace isc {
 __global__ void __launch_bounds__(128) embed_pack_kernel(const long long* __restrict__ it, const int* __restrict__ parent,
                                                          const float* __restrict__ h_in, long long M, int V,
                                                          const float* __restrict__ emb, RowDest x1, RowDest x2) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x;
   const int src = parent ? parent[m] : m;
   long long tok = it[m];
@@ -291,6 +293,8 @@ __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int
 template <typename FeatT, int TANH_MODE, int RT>
 __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   extern __shared__ __align__(16) float sm[];
+  pdl_trigger();
+  pdl_wait();
   const int R = RT > 0 ? RT : p.R, L = p.L, S = p.S;
   const int Lp = (L + 3) & ~3, Sp = (S + 3) & ~3;  // padded score rows keep 16-byte alignment
   float* q_c = sm;                 // [R][H] content query  h2att(h)
@@ -343,7 +347,7 @@ static int launch_attention_t(const AttnParams& p, int B, size_t smem, cudaStrea
     default: k = attention_kernel<FeatT, TANH_MODE, 0>; break;
   }
   ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k<<<B, 256, smem, stream>>>(p);
+  ISC_CUDA(launch_pdl(k, dim3(B), dim3(256), smem, stream, p));
   ISC_LAUNCH_CHECK();
   return 0;
 }
@@ -373,6 +377,8 @@ __global__ void __launch_bounds__(128) gate_mix_kernel(const float* __restrict__
                                                        RowDest ctx, float* __restrict__ gate_w, long long ld_gate_w) {
   __shared__ float red[4];
   __shared__ float wsh;
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x;
   const int c = threadIdx.x * 4;
   float4 g = *reinterpret_cast<const float4*>(g3 + (long long)m * H + c);
@@ -445,7 +451,7 @@ __global__ void fill_kernel(float* p, long long n, float v) {
 int launch_embed_pack(const long long* it, const int* parent, const float* h_in, int M, int V, const float* emb,
                       RowDest x1, RowDest x2, cudaStream_t stream) {
   ProfScope ps(ISC_K_POINTWISE, (double)M * H * 4.0 * 7, stream);
-  embed_pack_kernel<<<M, 128, 0, stream>>>(it, parent, h_in, M, V, emb, x1, x2);
+  ISC_CUDA(launch_pdl(embed_pack_kernel, dim3((unsigned)M), dim3(128), 0, stream, it, parent, h_in, M, V, emb, x1, x2));
   ISC_LAUNCH_CHECK();
   return 0;
 }
@@ -459,7 +465,7 @@ int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_
 int launch_gate_mix(const float* g3, const float* cs, const float* alpha, const float* alpha_b, RowDest ctx,
                     float* gate_w, long long ld_gate_w, int M, cudaStream_t stream) {
   ProfScope ps(ISC_K_POINTWISE, (double)M * H * 4.0 * 4, stream);
-  gate_mix_kernel<<<M, 128, 0, stream>>>(g3, cs, alpha, alpha_b, ctx, gate_w, ld_gate_w);
+  ISC_CUDA(launch_pdl(gate_mix_kernel, dim3((unsigned)M), dim3(128), 0, stream, g3, cs, alpha, alpha_b, ctx, gate_w, ld_gate_w));
   ISC_LAUNCH_CHECK();
   return 0;
 }
