@@ -379,6 +379,9 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
   ISC_TRY(launch_beam_init(w.it, w.alive[0], w.len[0], w.score[0], w.parent, B, K, dims->sos_id, c.s));
   const bool fused = precision != ISC_PREC_FP32;  // masks + top-K inside the logits GEMM epilogue
   const int k_sel = K <= 4 ? 4 : 8;               // candidates kept per 128-column slice
+  // before the first word the K beams of an image are identical (captioner.py:378-381 starts from ONE state): step 0
+  // runs on one row per image, and the merge kernel fans its candidates out to the K beams
+  const bool compact0 = fused && K > 1;
   for (int t = 0; t < T; ++t) {
     StepIO io;
     if (fused) {
@@ -400,8 +403,14 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
     io.c_out = w.state_c[(t + 1) & 1];
     io.logits = w.logits;
     io.ld_logits = w.ld_logits;
-    ISC_TRY(run_step(c, w, M, K, io));
+    if (compact0 && t == 0) {
+      io.state_rows = M;
+      ISC_TRY(run_step(c, w, B, 1, io));
+    } else {
+      ISC_TRY(run_step(c, w, M, K, io));
+    }
     BeamParams bp;
+    bp.compact0 = compact0 ? 1 : 0;
     bp.logits = fused ? nullptr : w.logits;
     bp.ld = w.ld_logits;
     bp.rec = io.sel.rec;

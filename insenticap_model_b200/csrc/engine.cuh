@@ -331,6 +331,9 @@ struct StepIO {
   LogitsSelect sel;  // sel.rec != null: the classifier GEMM emits selection records instead of logits
   const unsigned char* out_mask = nullptr;  // dropout keep-mask [M,H] on h_lang before the classifier (captioner.py:182)
   float drop_scale = 1.0f;
+  // rows of one plane of the OUTPUT state ([2][state_rows][H]: attention LSTM, language LSTM); 0 = M. Larger than M when
+  // a beam search's first step runs on one row per image but the following steps index B * K rows.
+  long long state_rows = 0;
 };
 
 // One decode step over M rows (captioner.py:168-186), raw classifier logits out.
@@ -344,6 +347,7 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
   ISC_REQUIRE(!has_sw || (f.p_sw && f.sl && f.pre_word), "feats.p_sw / sl / pre_word missing");
   const bool rl = has_att && has_sw;
   const long long m = M;
+  const long long so = io.state_rows > 0 ? io.state_rows : m;  // rows per plane of the output state
 
   const bool fuse_lstm = c.precision != ISC_PREC_FP32 && !w.tape;  // LSTM cell inside the gate GEMM's epilogue
   const int passes = c.precision == ISC_PREC_BF16X3 ? 3 : 1;
@@ -438,8 +442,8 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     LstmEpilogue le;
     le.parent = io.parent;
     le.c_prev = io.c_in + m * H;
-    le.h_out = io.h_out + m * H;
-    le.c_out = io.c_out + m * H;
+    le.h_out = io.h_out + so * H;
+    le.c_out = io.c_out + so * H;
     le.x_hi = w.phL.hi;  // h_lang (after dropout, if any) is the classifier's operand
     le.x_lo = w.phL.lo;
     le.ldx = H;
@@ -455,7 +459,7 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     dst.ld = G4;
     ISC_TRY(gemm(c.precision, operand(w.X2, 3 * H, w.pX2, 3 * H), pk.W4.op(), dst, M, G4, 3 * H, ep, c.s));
     RowDest hl = rowdest(nullptr, 0, w.phL, H);
-    ISC_TRY(launch_lstm_pointwise(w.gates2, io.parent, io.c_in + m * H, io.h_out + m * H, io.c_out + m * H, hl, 0, M, c.s,
+    ISC_TRY(launch_lstm_pointwise(w.gates2, io.parent, io.c_in + m * H, io.h_out + so * H, io.c_out + so * H, hl, 0, M, c.s,
                                   io.out_mask, io.drop_scale));
   }
   // classifier logits
@@ -465,7 +469,7 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     Dest dst;
     dst.f32 = io.logits;
     dst.ld = io.ld_logits;
-    Operand a = operand(io.h_out + m * H, H, w.phL, H);
+    Operand a = operand(io.h_out + so * H, H, w.phL, H);
     if (io.sel.rec) {
       ISC_TRY(gemm_tc_logits(a, pk.W5.op(), M, c.d.vocab, H, c.precision == ISC_PREC_BF16X3 ? 3 : 1, pk.b5, io.sel, c.s));
     } else {

@@ -121,6 +121,9 @@ struct BeamParams {
   int* cand_word = nullptr;  // [B*K, 8]
   int* cand_count = nullptr; // [B*K]
   int* ticket = nullptr;     // [B]
+  // step 0 ran on ONE row per image (all K beams of an image are identical before the first word): its records and
+  // state rows are indexed by image, and the parents written for step 1 point at those rows
+  int compact0 = 0;
 };
 int launch_beam_select(const BeamParams& p, cudaStream_t stream);
 int launch_beam_init(long long* it, int* alive, int* len, double* score, int* parent, int B, int K, int sos_id,

@@ -203,7 +203,7 @@ __device__ __forceinline__ void beam_pool(const BeamParams& p, int b) {
       p.score_out[b * K + j] = pool_score[best];
       p.alive_out[b * K + j] = 1;
       p.len_out[b * K + j] = p.len_in[b * K + kk] + (w >= 0 ? 1 : 0);
-      p.parent[b * K + j] = b * K + kk;
+      p.parent[b * K + j] = (p.compact0 && t == 0) ? b : b * K + kk;
       p.it[b * K + j] = (w >= 0) ? (long long)w : lasts[kk];
     }
     sel_n = j;
@@ -211,7 +211,7 @@ __device__ __forceinline__ void beam_pool(const BeamParams& p, int b) {
       p.score_out[b * K + j] = 0.0;
       p.alive_out[b * K + j] = 0;
       p.len_out[b * K + j] = 0;
-      p.parent[b * K + j] = b * K + j;
+      p.parent[b * K + j] = (p.compact0 && t == 0) ? b : b * K + j;
       p.it[b * K + j] = p.sos_id;
     }
   }
@@ -428,7 +428,8 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
     if (alive && !finished) {
       float mx, lse, v[SEL_K];
       int w[SEL_K];
-      merge_row<SEL_K>(p.rec + (long long)m * p.np * SEL_REC, p.np, K, lane, mx, lse, v, w);
+      const long long mrec = (p.compact0 && t == 0) ? b : m;  // step 0 computed one row per image
+      merge_row<SEL_K>(p.rec + mrec * p.np * SEL_REC, p.np, K, lane, mx, lse, v, w);
       if (lane == 0) {
         int cnt = 0;
 #pragma unroll
