@@ -716,6 +716,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const bool full4 = n + 3 < ep.N;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias) b4 = (full4 && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
+          // the addends of all eight rows are requested up front: issued one by one in front of their use, each load's
+          // latency is exposed (ncu: the epilogue sat on the dependent FADDs)
+          float4 radd4[8], madd4[8];
+          if (ep.rowadd) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              radd4[i] = i < nvalid ? ((full4 && radd_vec) ? __ldg(reinterpret_cast<const float4*>(radd[i] + n)) : load4_guarded(radd[i] + n, n, ep.N))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          if (ep.addmat) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float* mp = ep.addmat + (long long)(row0 + 4 * i) * ep.ld_addmat + n;
+              madd4[i] = i < nvalid ? ((full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i < nvalid) {
@@ -724,12 +741,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               float4 x = sc[r * 8 + (c4 ^ (r & 7))];
               x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
               if (ep.rowadd) {
-                float4 t = (full4 && radd_vec) ? __ldg(reinterpret_cast<const float4*>(radd[i] + n)) : load4_guarded(radd[i] + n, n, ep.N);
+                const float4 t = radd4[i];
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
               if (ep.addmat) {
-                const float* mp = ep.addmat + row * ep.ld_addmat + n;
-                float4 t = (full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N);
+                const float4 t = madd4[i];
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
               x.x = act_ct<ACT>(x.x); x.y = act_ct<ACT>(x.y); x.z = act_ct<ACT>(x.z); x.w = act_ct<ACT>(x.w);
