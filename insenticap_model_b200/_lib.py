@@ -148,11 +148,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("ISC_B200_LIB", LIB_PATH)  # another build of the same library, for A/B measurements
+    if not os.path.exists(path):
         raise RuntimeError(
             "libisc_b200.so is not built: run `python -m insenticap_model_b200.build` "
             "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for this path.")
-    lib = C.CDLL(LIB_PATH, mode=os.RTLD_NOW)
+    lib = C.CDLL(path, mode=os.RTLD_NOW)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
         fn.restype = res
