@@ -541,12 +541,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(scale) : "f"((mx - mn) * kLog2e));  // mx = -inf -> 0
         sum = fmaf(sum, scale, part);
         mx = mn;
+        if (SEL_K == 4) {
+          // Branch-free: every lane owns a different row, so a per-column "does it enter the list" branch diverges on
+          // nearly every column and the warp pays branch + reconvergence 128 times per slice (ncu: more than half of
+          // this epilogue's stall samples sat on FSETP / BRA / BSYNC, and the kernel was epilogue-bound). The
+          // select-based insertion of a value that does not qualify (or of -inf for a masked column) changes nothing,
+          // so it simply runs for all 32 columns. The special ids only occur in the chunk that holds them.
+          const int max_special = max(sel.pad_id, max(sel.sos_id, sel.unk_id));
+          if (sel.mask_special && nb <= max_special) {  // warp-uniform
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          if (v[q] > cv[SEL_K - 1]) {
+            for (int q = 0; q < 32; ++q) {
+              const int n = nb + q;
+              if (n == sel.pad_id || n == sel.sos_id || n == sel.unk_id) v[q] = -INFINITY;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
             const int n = nb + q;
-            const bool masked = (sel.mask_special && (n == sel.pad_id || n == sel.sos_id || n == sel.unk_id)) || n == last_w;
-            if (!masked) topk_insert<SEL_K>(cv, ci, v[q], n);
+            topk_insert<SEL_K>(cv, ci, n == last_w ? -INFINITY : v[q], n);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            if (v[q] > cv[SEL_K - 1]) {
+              const int n = nb + q;
+              const bool masked = (sel.mask_special && (n == sel.pad_id || n == sel.sos_id || n == sel.unk_id)) || n == last_w;
+              if (!masked) topk_insert<SEL_K>(cv, ci, v[q], n);
+            }
           }
         }
       }
