@@ -250,6 +250,18 @@ __device__ __forceinline__ void tanh2_eprod(float ea0, float ea1, float eb0, flo
   t0 = fmaf(-e0, i0, i0);
   t1 = fmaf(-e1, i1, i1);
 }
+// The attention SCORE only enters a softmax over the regions, which ignores anything constant per query:
+//   sum_j a_j tanh(p_j + q_j) = sum_j 2 a_j / (1 + e_j)  -  sum_j a_j,     e_j = ea_j * eb_j,
+// so the kernel accumulates sum_j (2 a_j) / (1 + e_j) and never forms a tanh. Two terms share one reciprocal:
+//   2a0/d0 + 2a1/d1 = (2a0 d1 + 2a1 d0) / (d0 d1),   d = fma(ea, eb, 1)
+// — six FMA-pipe instructions and one MUFU per PAIR (tanh2_eprod + two FMAs: eleven). a0x2 / a1x2 are the doubled
+// alphas. Same operand domain as tanh2_eprod (d0 * d1 cannot overflow).
+__device__ __forceinline__ float score2_eprod(float ea0, float ea1, float eb0, float eb1, float a0x2, float a1x2, float acc) {
+  const float d0 = fmaf(ea0, eb0, 1.0f), d1 = fmaf(ea1, eb1, 1.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  return fmaf(r, fmaf(a0x2, d1, a1x2 * d0), acc);
+}
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -132,18 +132,19 @@ __device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kCh
 #pragma unroll
         for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
           const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
-          float t[4];
           if (TANH_MODE == 1) {
-            // pv = exp(-2 p), q = exp(-2 q): tanh(p + q) = (1 - pv q) / (1 + pv q), one reciprocal per pair
-            tanh2_eprod(pv[i][j4], pv[i][j4 + 1], qv.x, qv.y, t[0], t[1]);
-            tanh2_eprod(pv[i][j4 + 2], pv[i][j4 + 3], qv.z, qv.w, t[2], t[3]);
+            // pv = exp(-2 p), q = exp(-2 q), al = 2 alpha: the softmax-equivalent score sum 2 alpha / (1 + pv q)
+            // (score2_eprod, common.cuh), one reciprocal per pair
+            acc = score2_eprod(pv[i][j4], pv[i][j4 + 1], qv.x, qv.y, al[i][j4], al[i][j4 + 1], acc);
+            acc = score2_eprod(pv[i][j4 + 2], pv[i][j4 + 3], qv.z, qv.w, al[i][j4 + 2], al[i][j4 + 3], acc);
           } else {
+            float t[4];
             const float x[4] = {pv[i][j4] + qv.x, pv[i][j4 + 1] + qv.y, pv[i][j4 + 2] + qv.z, pv[i][j4 + 3] + qv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) t[j] = TANH_MODE == 2 ? tanh_fast(x[j]) : tanhf(x[j]);
-          }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc = fmaf(al[i][j4 + j], t[j], acc);
+            for (int j = 0; j < 4; ++j) acc = fmaf(al[i][j4 + j], t[j], acc);
+          }
         }
       }
       acc = warp_sum(acc);
@@ -166,7 +167,7 @@ __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int
 #pragma unroll
   for (int i = 0; i < L::kChunks; ++i)
 #pragma unroll
-    for (int j = 0; j < L::kWidth; ++j) al[i][j] = alpha_smem[L::col(lane, i) + j];
+    for (int j = 0; j < L::kWidth; ++j) al[i][j] = (TANH_MODE == 1 ? 2.0f : 1.0f) * alpha_smem[L::col(lane, i) + j];
   auto prefetch = [&](int l, int slot) {
     if (l < n_items) {
 #pragma unroll
