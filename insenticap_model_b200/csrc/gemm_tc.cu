@@ -269,6 +269,21 @@ __device__ __forceinline__ void lstm_tile(int tile, int tiles_m, int tiles_n, in
   }
 }
 
+#ifdef ISC_GEMM_TRACE
+// Debug build only (profiles/gemm_trace.py): per-CTA globaltimer stamps of the fused-LSTM GEMM's phases.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_stamp(int slot) {
+  if (g_trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[blockIdx.x * 16 + slot] = t;
+  }
+}
+#define ISC_TRACE(cond, slot) do { if (EPI == EPI_LSTM && (cond)) trace_stamp(slot); } while (0)
+#else
+#define ISC_TRACE(cond, slot) do { } while (0)
+#endif
+
 template <int PASSES, int BN, int ACT, int EPI, int CG, int AF>
 __global__ void __launch_bounds__(NUM_THREADS + (AF ? 128 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -290,6 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  ISC_TRACE(threadIdx.x == 0, 0);
   constexpr int BK = C::kBK;
   const int num_kb = ep.seg_kb > 0 ? 9 * ep.seg_kb : (ep.K + BK - 1) / BK;
   const int tiles_n = (ep.N + BN - 1) / BN;
@@ -342,6 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   // kernel of the stream is still draining (programmatic dependent launch); global memory is read from here on
   pdl_trigger();
   pdl_wait();
+  ISC_TRACE(threadIdx.x == 0, 1);
 
   if (warp == 0) {
     // ===================== TMA producer (one elected lane) =====================
@@ -423,6 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
+          ISC_TRACE(it == 0, 2);
           const uint32_t st = smem_u32(smem + s * C::kStageBytes);
           const uint32_t a_hi = st, a_lo = st + C::kATileBytes;
           const uint32_t b_hi = st + C::kPlanes * C::kATileBytes, b_lo = b_hi + C::kBTileBytes;
@@ -447,6 +465,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // accumulator of this tile complete (signalled to the epilogue warps of both CTAs of a pair)
         if (CG == 2) umma_commit_pair(&acc_full[as]);
         else umma_commit(&acc_full[as]);
+        ISC_TRACE(j < 2, 3 + j);
       }
     }
   } else if (AF && warp >= 2 + EPI_WARPS) {
@@ -627,6 +646,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (ss == 0) {
           mbar_wait(&acc_full[as], (j >> 1) & 1);
           tcgen05_fence_after();
+          ISC_TRACE(threadIdx.x == 64 && j < 2, 8 + 2 * j);
         }
         float vif[32], vgo[32];  // [i(16) | f(16)], [g(16) | o(16)]
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + grp * 64;
@@ -694,6 +714,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
       }
+      ISC_TRACE(threadIdx.x == 64 && j < 2, 9 + 2 * j);
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> global =====================
@@ -821,6 +842,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   tcgen05_fence_before();
   if (CG == 2) cluster_sync_all();  // no CTA of the pair leaves while the other may still signal into its smem
   else __syncthreads();
+  ISC_TRACE(threadIdx.x == 0, 15);
   if (warp == 1) {
     tcgen05_fence_after();
     if (CG == 2)
@@ -1184,6 +1206,13 @@ static bool use_wide_tiles(int M, int N) {
 }
 
 }  // namespace tc
+
+#ifdef ISC_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int isc_debug_gemm_trace(void* buf) {
+  unsigned long long* p = static_cast<unsigned long long*>(buf);
+  return (int)cudaMemcpyToSymbol(tc::g_trace, &p, sizeof(p));
+}
+#endif
 
 int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int K, int passes, const Epilogue& ep,
             cudaStream_t stream) {
