@@ -132,6 +132,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 cache-policy operands (the encodings createpolicy.fractional.L2::evict_* 1.0 produces). The weight operand of the
+// step GEMMs is re-read sixteen times per call but the attention kernel streams 0.8 GB through L2 between two uses:
+// loaded evict_last, the ~50 MB of weight planes a step touches survive that stream and the GEMM pipelines turn around
+// in L2 latency instead of HBM latency.
+constexpr unsigned long long kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 // cta_group::2 variants: the load signals the LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared),
 // the MMA spans both CTAs of the pair, the commit arrives on the same barrier offset in both CTAs.
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -248,22 +267,22 @@ __device__ __forceinline__ float act_ct(float v) {
 // columns) first, then the remaining units in 32-unit (128-column) tiles, enumerated wide tiles first: with
 // M = 3072 (24 row blocks) and wide = 6 that is 144 wide tiles + 96 narrow ones, i.e. one wide and (for 92 CTAs) one
 // narrow tile per SM instead of 1.3 waves of wide or 2.6 waves of narrow tiles.
-template <int BN>
+template <int BN, int ROWS /* rows of a tile: BM, or 2 * BM for a CTA pair */>
 __device__ __forceinline__ void lstm_tile(int tile, int tiles_m, int tiles_n, int wide, int& m0, int& u0, int& width) {
   if (BN == 128) {
-    m0 = (tile / tiles_n) * BM;
+    m0 = (tile / tiles_n) * ROWS;
     u0 = (tile % tiles_n) * 32;
     width = 128;
     return;
   }
   const int n_wide = tiles_m * wide;
   if (tile < n_wide) {
-    m0 = (tile / wide) * BM;
+    m0 = (tile / wide) * ROWS;
     u0 = (tile % wide) * 64;
     width = 256;
   } else {
     const int nn = (tiles_n - wide) * 2, t = tile - n_wide;
-    m0 = (t / nn) * BM;
+    m0 = (t / nn) * ROWS;
     u0 = wide * 64 + (t % nn) * 32;
     width = 128;
   }
@@ -364,15 +383,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================== TMA producer (one elected lane) =====================
     if (lane == 0) {
       int it = 0;
+      const unsigned long long wpol = kEvictLast;  // weight (B) operand: keep in L2 across the decode steps
       for (int tile = walker; tile < num_tiles; tile += walkers) {
         int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM;
         int n0 = (tile % tiles_n) * BN + cta_rank * C::kBRows;  // CG = 2: this CTA's half of the B rows
         int lw = BN;                                            // EPI_LSTM: n0 = first hidden unit, lw = tile width
-        if (EPI == EPI_LSTM) lstm_tile<BN>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, n0, lw);
+        if (EPI == EPI_LSTM) {
+          lstm_tile<BN, CG * BM>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, n0, lw);
+          m0 += cta_rank * BM;
+        }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
+          ISC_TRACE(it == 8, 12);
           mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
+          ISC_TRACE(it == 8, 13);
           uint8_t* st = smem + s * C::kStageBytes;
           uint8_t* stb = st + C::kPlanes * C::kATileBytes;
           const int k0 = kb * BK;
@@ -386,19 +411,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (AF) {
             // B planes straight into the stage; the fp32 A tile into the staging ring for the converter warps
             mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
-            tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
-            if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+            tma_load_2d_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
+            if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
             const int slot = it & 1;
             mbar_wait(&stg_empty[slot], ((it >> 1) & 1) ^ 1);
             mbar_expect_tx(&stg_full[slot], C::kStgBytes);
             tma_load_2d(stg + slot * C::kStgBytes, &map_a_hi, &stg_full[slot], ak, am);
+          } else if (CG == 2 && EPI == EPI_LSTM) {
+            // CTA pair: each CTA loads its 128 rows of A and HALF of the tile's (gate-interleaved, contiguous) B rows,
+            // 64-row boxes; every byte of both CTAs completes on the leader's barrier
+            const int half_rows = lw >> 1;
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kPlanes * (C::kATileBytes + half_rows * BK * 2));
+            tma_load_2d_pair(st, &map_a_hi, &full_bar[s], k0, m0);
+            if (PASSES == 3) tma_load_2d_pair(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
+#pragma unroll
+            for (int q = 0; q < BN / 128; ++q) {
+              if (q * 64 < half_rows) {
+                const int brow = 4 * n0 + cta_rank * half_rows + q * 64;
+                tma_load_2d_pair_hint(stb + q * 64 * BK * 2, &map_b_hi, &full_bar[s], k0, brow, wpol);
+                if (PASSES == 3) tma_load_2d_pair_hint(stb + C::kBTileBytes + q * 64 * BK * 2, &map_b_lo, &full_bar[s], k0, brow, wpol);
+              }
+            }
           } else if (CG == 2) {
             // both CTAs' bytes complete on the leader's barrier, which alone is armed and waited on
             if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kStageBytes);
             tma_load_2d_pair(st, &map_a_hi, &full_bar[s], k0, m0);
             if (PASSES == 3) tma_load_2d_pair(st + C::kATileBytes, &map_a_lo, &full_bar[s], k0, m0);
-            tma_load_2d_pair(stb, &map_b_hi, &full_bar[s], k0, n0);
-            if (PASSES == 3) tma_load_2d_pair(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+            tma_load_2d_pair_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
+            if (PASSES == 3) tma_load_2d_pair_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
           } else if (EPI == EPI_LSTM) {
             // the weight planes are gate-interleaved: the tile's B rows start at 4 * (first unit), one 128-row box per
             // 128 columns
@@ -408,17 +448,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int q = 0; q < BN / 128; ++q) {
               if (q * 128 < lw) {
-                tma_load_2d(stb + q * 128 * BK * 2, &map_b_hi, &full_bar[s], k0, 4 * n0 + q * 128);
-                if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes + q * 128 * BK * 2, &map_b_lo, &full_bar[s], k0, 4 * n0 + q * 128);
+                tma_load_2d_hint(stb + q * 128 * BK * 2, &map_b_hi, &full_bar[s], k0, 4 * n0 + q * 128, wpol);
+                if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes + q * 128 * BK * 2, &map_b_lo, &full_bar[s], k0, 4 * n0 + q * 128, wpol);
               }
             }
           } else {
             mbar_expect_tx(&full_bar[s], C::kStageBytes);
             tma_load_2d(st, &map_a_hi, &full_bar[s], ak, am);
             if (PASSES == 3) tma_load_2d(st + C::kATileBytes, &map_a_lo, &full_bar[s], ak, am);
-            tma_load_2d(stb, &map_b_hi, &full_bar[s], k0, n0);
-            if (PASSES == 3) tma_load_2d(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0);
+            tma_load_2d_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
+            if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
           }
+          ISC_TRACE(it == 0, 5);
+          ISC_TRACE(it == 8, 6);
         }
       }
     }
@@ -434,13 +476,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t tmem_d = tmem_base + as * BN;
         uint32_t accumulate = 0;
         uint32_t idesc_t = idesc;
-        if (EPI == EPI_LSTM && BN == 256 && tile >= tiles_m * ep.lstm_wide) idesc_t = umma_idesc_bf16(BM, 128);  // narrow tile
+        if (EPI == EPI_LSTM && BN == 256 && tile >= tiles_m * ep.lstm_wide) idesc_t = umma_idesc_bf16(CG * BM, 128);  // narrow tile
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           ISC_TRACE(it == 0, 2);
+          ISC_TRACE(it == 8, 7);
           const uint32_t st = smem_u32(smem + s * C::kStageBytes);
           const uint32_t a_hi = st, a_lo = st + C::kATileBytes;
           const uint32_t b_hi = st + C::kPlanes * C::kATileBytes, b_lo = b_hi + C::kBTileBytes;
@@ -619,7 +662,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     int j = 0;
     for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
       int m0, ut, width;
-      lstm_tile<BN>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, ut, width);
+      lstm_tile<BN, CG * BM>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, ut, width);
+      m0 += cta_rank * BM;
       const int nsub = width >> 7;  // 16-unit groups per warp: 1 (128-column tile) or 2 (256-column tile)
       const int as = j & 1;
       const long long row = m0 + quarter * 32 + lane;
@@ -656,7 +700,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           // the accumulator stage is drained: release it to the MMA warp before the math and the stores
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cta(&acc_empty[as], 0);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+          }
         }
         if (live) {
           // same association as the unfused path: (acc + bias) + rowadd, then nn.LSTMCell's pointwise math
@@ -1124,8 +1171,8 @@ static int launch_conv(const float* A32, const Operand& A, int64_t lda, const Op
 // Number of 256-column tiles per 128-row block for the mixed-width LSTM tile list (lstm_tile): the static round-robin
 // walk is simulated for every choice and the cheapest one kept (cost of a wide tile 2, of a narrow one 1.15 — it
 // moves more operand bytes per flop — plus 0.25 per tile for fill and epilogue).
-static int lstm_wide_tiles(int M) {
-  const int tiles_m = (M + BM - 1) / BM, slots = num_sms(), groups = (4 * H) / 256;
+static int lstm_wide_tiles(int M, int cg) {
+  const int tiles_m = (M + cg * BM - 1) / (cg * BM), slots = num_sms() / cg, groups = (4 * H) / 256;
   int best = 0;
   double best_cost = 1e30;
   for (int w = groups; w >= 0; --w) {
@@ -1144,17 +1191,20 @@ static int lstm_wide_tiles(int M) {
   return best;
 }
 
-template <int PASSES, int BN>
+template <int PASSES, int BN, int CG>
 static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const float* bias, const float* rowadd,
                        int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream) {
-  using C = Cfg<PASSES, BN, 1>;
+  using C = Cfg<PASSES, BN, CG>;
   const int N = 4 * H;
+  // gate-interleaved weight rows: one 128-row box per 128 columns; a CTA pair loads half of a tile's rows per CTA in
+  // 64-row boxes
+  const int b_box = CG == 2 ? 64 : 128;
   Maps m;
   ISC_TRY(make_map(&m.a_hi, A.hi, M, K, A.ldp, BM, C::kBK));
-  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, 128, C::kBK));  // gate-interleaved rows, one box per 128 columns
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, b_box, C::kBK));
   if (PASSES == 3) {
     ISC_TRY(make_map(&m.a_lo, A.lo, M, K, A.ldp, BM, C::kBK));
-    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, 128, C::kBK));
+    ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, b_box, C::kBK));
   } else {
     m.a_lo = m.a_hi;
     m.b_lo = m.b_hi;
@@ -1169,14 +1219,15 @@ static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const f
   ep.N = N;
   ep.K = K;
   ep.lstm = lstm;
-  int grid = persistent_grid<BN, 1>(M, N);
+  int grid = persistent_grid<BN, CG>(M, N);
   if (BN == 256) {
-    ep.lstm_wide = lstm_wide_tiles(M);
-    const int tiles = ((M + BM - 1) / BM) * (ep.lstm_wide + (N / 256 - ep.lstm_wide) * 2);
-    grid = tiles < num_sms() ? tiles : num_sms();
+    ep.lstm_wide = lstm_wide_tiles(M, CG);
+    const int tiles = ((M + CG * BM - 1) / (CG * BM)) * (ep.lstm_wide + (N / 256 - ep.lstm_wide) * 2);
+    const int slots = num_sms() / CG;
+    grid = CG * (tiles < slots ? tiles : slots);
   }
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
-  return launch_kernel<PASSES, BN, ACT_NONE, EPI_LSTM, 1>(m, ep, grid, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_LSTM, CG>(m, ep, grid, stream);
 }
 
 // CTA pairs pay off on large GEMMs only (measured: 8192^3 1.41 -> 1.57 PFLOP/s x3-equivalent, logits-shaped 85 -> 75 us,
@@ -1262,6 +1313,9 @@ int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, c
   if (M <= 0) return 0;
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_lstm: K=%d must be a positive multiple of 8", K);
   static const bool mixed = getenv("ISC_LSTM_UNIFORM_TILES") == nullptr;  // set to use the uniform 128-column tile list
+  // CTA pairs (a third fewer operand bytes per flop) once M spans several 256-row blocks; ISC_LSTM_PAIR=0/1 forces
+  static const int pair_env = getenv("ISC_LSTM_PAIR") ? atoi(getenv("ISC_LSTM_PAIR")) : -1;
+  const bool pair = M > tc::BM && (pair_env == 1 || (pair_env < 0 && M >= 8 * tc::BM));
   ISC_REQUIRE(A.hi && W.hi && lstm.c_prev && lstm.h_out && lstm.c_out, "gemm_tc_lstm: planes / state buffers missing");
   ISC_REQUIRE(!lstm.x_hi || ((lstm.ldx % 8) == 0 && (lstm.x_col % 8) == 0 && (reinterpret_cast<uintptr_t>(lstm.x_hi) & 15) == 0),
               "gemm_tc_lstm: operand planes must be 16-byte aligned");
@@ -1270,11 +1324,13 @@ int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, c
               "gemm_tc_lstm: rowadd must be 16-byte aligned");
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc_lstm: bf16 lo planes missing for the 3-pass mode");
-    if (!mixed) return tc::launch_lstm<3, 128>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
-    return tc::launch_lstm<3, 256>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+    if (!mixed) return tc::launch_lstm<3, 128, 1>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+    if (pair) return tc::launch_lstm<3, 256, 2>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+    return tc::launch_lstm<3, 256, 1>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
   }
-  if (!mixed) return tc::launch_lstm<1, 128>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
-  return tc::launch_lstm<1, 256>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+  if (!mixed) return tc::launch_lstm<1, 128, 1>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+  if (pair) return tc::launch_lstm<1, 256, 2>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
+  return tc::launch_lstm<1, 256, 1>(A, W, M, K, bias, rowadd, ld_rowadd, rows_per_group, lstm, stream);
 }
 
 int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int passes, const float* bias,
