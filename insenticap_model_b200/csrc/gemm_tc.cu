@@ -1339,7 +1339,10 @@ int gemm_tc_logits(const Operand& A, const Operand& W, int M, int N, int K, int 
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_logits: K=%d must be a positive multiple of 8", K);
   ISC_REQUIRE(A.hi && W.hi && sel.rec && sel.np == logits_slices(N) && (sel.k_sel == 4 || sel.k_sel == 8),
               "gemm_tc_logits: planes / records missing");
-  const bool pair = tc::pair_mode() == 1 && M > tc::BM;
+  // CTA pairs: a 256x256 pair tile takes a third fewer operand bytes per SM (the step GEMMs are bound by the L2 -> SM
+  // port); worth it once there are several rounds of pair tiles
+  static const int lp_env = getenv("ISC_LOGITS_PAIR") ? atoi(getenv("ISC_LOGITS_PAIR")) : -1;
+  const bool pair = M > tc::BM && (tc::pair_mode() == 1 || lp_env == 1 || (lp_env < 0 && tc::pair_mode() < 0 && tc::pair_pays(M, N, true)));
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc_logits: bf16 lo planes missing for the 3-pass mode");
     return pair ? tc::launch_logits<3, 2>(A, W, M, N, K, bias, sel, stream) : tc::launch_logits<3, 1>(A, W, M, N, K, bias, sel, stream);

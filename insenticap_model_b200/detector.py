@@ -132,7 +132,7 @@ class Detector(nn.Module):
                 rewards = fact_reward + torch.zeros_like(seq_masks)
             all_losses["all_rewards"] += float(rewards.mean(-1).mean(-1))
             cap_loss = self.cap_rl_crit(sample_logprobs, seq_masks, rewards)
-            all_losses["cap_loss"] += float(cap_loss)
+            all_losses["cap_loss"] += float(cap_loss.detach())
 
             xe_loss = 0.0
             if data_type == "fact":

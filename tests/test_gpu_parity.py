@@ -62,16 +62,17 @@ def test_gemm(precision, shape):
 
 
 def test_gemm_and_decode_with_cta_pairs_forced():
-    """ISC_GEMM_PAIR=1 routes every multi-tile GEMM through the cta_group::2 kernel (cluster of 2, 256-row tiles):
-    the GEMM shapes and the golden beam / greedy decodes must hold there too (run in a subprocess: the switch is
-    read once per process)."""
+    """ISC_GEMM_PAIR=1 / ISC_LSTM_PAIR=1 / ISC_LOGITS_PAIR=1 route every multi-tile GEMM — plain, fused-LSTM and logits
+    epilogues — through the cta_group::2 kernels (cluster of 2, 256-row tiles), also at the small and ragged row counts
+    where the heuristics would keep single-CTA tiles: the GEMM shapes and the golden beam / greedy decodes must hold
+    there too (run in a subprocess: the switches are read once per process)."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
                         "test_gemm and not pairs or cfg1_matches or ragged"], cwd=root, capture_output=True, text=True,
-                       env=dict(os.environ, ISC_GEMM_PAIR="1"), timeout=900)
+                       env=dict(os.environ, ISC_GEMM_PAIR="1", ISC_LSTM_PAIR="1", ISC_LOGITS_PAIR="1"), timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
