@@ -298,7 +298,11 @@ __device__ __forceinline__ void trace_stamp(int slot) {
     g_trace[blockIdx.x * 16 + slot] = t;
   }
 }
+#ifdef ISC_TRACE_AF  // trace the fp32-A (converter-warp) GEMM of the prologue instead
+#define ISC_TRACE(cond, slot) do { if (AF == 1 && (cond)) trace_stamp(slot); } while (0)
+#else
 #define ISC_TRACE(cond, slot) do { if (EPI == EPI_LSTM && (cond)) trace_stamp(slot); } while (0)
+#endif
 #else
 #define ISC_TRACE(cond, slot) do { } while (0)
 #endif
@@ -522,6 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t ph = (it / C::kStages) & 1;
         const int slot = it & 1;
         mbar_wait(&stg_full[slot], (it >> 1) & 1);
+        ISC_TRACE(r == 0 && it == 8, 14);
         const uint8_t* src = stg + slot * C::kStgBytes + r * 128;
         float v[32];
 #pragma unroll
@@ -791,6 +796,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       mbar_wait(&acc_full[as], (j >> 1) & 1);
       tcgen05_fence_after();
+      ISC_TRACE(threadIdx.x == 64 && j < 2, 8 + 2 * j);
 #pragma unroll 1
       for (int cc = 0; cc < BN / 64; ++cc) {
         const int c = half * (BN / 64) + cc;
@@ -883,6 +889,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (CG == 2) mbar_arrive_cta(&acc_empty[as], 0);
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
       }
+      ISC_TRACE(threadIdx.x == 64 && j < 2, 9 + 2 * j);
     }
   }
 

@@ -17,6 +17,7 @@ from insenticap_model_b200.captioner import Captioner  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+# with a -DISC_TRACE_AF build the stamps come from the prologue's att_embed GEMM (last chunk) instead
 V = 10000
 lib = _lib.load()
 raw = C.CDLL(os.environ["ISC_B200_LIB"])
@@ -37,7 +38,7 @@ t = trace.cpu().numpy().reshape(148, 16).astype(np.float64)
 t0 = t[:, 0][t[:, 0] > 0].min()
 names = {0: "kernel entry", 1: "set-up done", 5: "stage 0 loads issued", 2: "first operand stage landed",
          12: "k-block 8: producer waits for a free stage", 13: "k-block 8: stage free", 6: "k-block 8: loads issued",
-         7: "k-block 8: stage landed (MMA thread)", 3: "tile0 MMAs issued", 4: "tile1 MMAs issued",
+         14: "k-block 8: fp32 A tile in staging (converter)", 7: "k-block 8: stage landed (MMA thread)", 3: "tile0 MMAs issued", 4: "tile1 MMAs issued",
          8: "tile0 accumulator ready", 9: "tile0 epilogue done", 10: "tile1 accumulator ready", 11: "tile1 epilogue done", 15: "exit"}
 print("fused-LSTM GEMM, last launch of a B=%d beam-3 call with T=%d: us since the first CTA's entry" % (B, steps))
 for k in sorted(names):
