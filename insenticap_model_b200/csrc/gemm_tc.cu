@@ -34,6 +34,7 @@ constexpr int BM = 128;
 constexpr int EPI_WARPS = 8;                // two per TMEM lane quarter, each owns half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2;               // TMEM accumulator double buffer
+constexpr int CONV_WARPS = 8;               // AF kernels: warps that split the fp32 A tile into bf16 planes (half a row per thread)
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one XOR-swizzled 32x32 fp32 staging tile per epilogue warp
 
 // BN = 128 for the step GEMMs (M = 3072 rows: more, smaller tiles fill 148 SMs better), BN = 256 where there are many
@@ -60,7 +61,7 @@ struct Cfg {
   static constexpr int kTmemCols = ACC_STAGES * BN;  // 256 / 512 columns (power of two)
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStgSlots * kStgBytes + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kThreads = NUM_THREADS + (AF ? 128 : 0);
+  static constexpr int kThreads = NUM_THREADS + (AF ? CONV_WARPS * 32 : 0);
 };
 
 enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2, EPI_LOGITS8 = 3 };  // EPI_LOGITS8: 8 candidates per slice
@@ -308,7 +309,7 @@ __device__ __forceinline__ void trace_stamp(int slot) {
 #endif
 
 template <int PASSES, int BN, int ACT, int EPI, int CG, int AF>
-__global__ void __launch_bounds__(NUM_THREADS + (AF ? 128 : 0), 1)
+__global__ void __launch_bounds__(NUM_THREADS + (AF ? CONV_WARPS * 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const EpiParams ep) {
@@ -346,12 +347,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
     }
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full_bar[s], AF ? 5 : 1);  // AF: the producer's arrive (B bytes) + one arrive per converter warp (A tiles)
+      mbar_init(&full_bar[s], AF ? 1 + CONV_WARPS : 1);  // AF: the producer's arrive (B bytes) + one arrive per converter warp (A tiles)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < C::kStgSlots; ++s) {
       mbar_init(&stg_full[s], 1);
-      mbar_init(&stg_empty[s], 4);
+      mbar_init(&stg_empty[s], CONV_WARPS);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&acc_full[s], 1);
@@ -400,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           ISC_TRACE(it == 8, 12);
-          mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately
+          if (!AF) mbar_wait(&empty_bar[s], ph ^ 1);  // first round passes immediately (AF: see below)
           ISC_TRACE(it == 8, 13);
           uint8_t* st = smem + s * C::kStageBytes;
           uint8_t* stb = st + C::kPlanes * C::kATileBytes;
@@ -413,14 +414,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             am = m0 + ep.seg_off[sgm];
           }
           if (AF) {
-            // B planes straight into the stage; the fp32 A tile into the staging ring for the converter warps
-            mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
-            tma_load_2d_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
-            if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
+            // The fp32 A tile goes into the staging ring for the converter warps FIRST: it only needs a free staging
+            // slot, so its load latency (~1.1 us) runs while the operand stage is still being read by the MMAs. (Issued
+            // after the wait for the operand stage, the stage's round trip was free -> issue -> A lands -> converted =
+            // 2.1 us, i.e. 0.7 us per k-block with three stages against 0.39 us of MMAs: phase trace, DESIGN.md.)
             const int slot = it & 1;
             mbar_wait(&stg_empty[slot], ((it >> 1) & 1) ^ 1);
             mbar_expect_tx(&stg_full[slot], C::kStgBytes);
             tma_load_2d(stg + slot * C::kStgBytes, &map_a_hi, &stg_full[slot], ak, am);
+            // B planes straight into the stage
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
+            tma_load_2d_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
+            if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
           } else if (CG == 2 && EPI == EPI_LSTM) {
             // CTA pair: each CTA loads its 128 rows of A and HALF of the tile's (gate-interleaved, contiguous) B rows,
             // 64-row boxes; every byte of both CTAs completes on the leader's barrier
@@ -517,8 +523,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (AF && warp >= 2 + EPI_WARPS) {
     // ===================== converters: fp32 A tile (staging) -> bf16 hi/lo operand tiles of the stage =====================
-    // thread r owns row r: 32 floats = 128 B in the 128B-swizzled staging tile -> 2 x 64 B in the 64B-swizzled operand tiles
-    const int r = threadIdx.x - (2 + EPI_WARPS) * 32;
+    // thread t owns half of row r = t & 127: 16 floats = 64 B of the 128B-swizzled staging row -> 32 B in each of the
+    // 64B-swizzled operand tiles. Eight warps: with four (a whole row per thread) the converters, one warp per scheduler
+    // and latency-bound, needed ~0.5 us per k-block against 0.39 us of MMAs and set the kernel's pace (phase trace).
+    const int t = threadIdx.x - (2 + EPI_WARPS) * 32;
+    const int r = t & 127, hf = t >> 7;
     int it = 0;
     for (int tile = walker; tile < num_tiles; tile += walkers) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -526,31 +535,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const uint32_t ph = (it / C::kStages) & 1;
         const int slot = it & 1;
         mbar_wait(&stg_full[slot], (it >> 1) & 1);
-        ISC_TRACE(r == 0 && it == 8, 14);
+        ISC_TRACE(t == 0 && it == 8, 14);
         const uint8_t* src = stg + slot * C::kStgBytes + r * 128;
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 t = *reinterpret_cast<const float4*>(src + ((c ^ (r & 7)) << 4));
-          v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+        for (int c = 0; c < 4; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(src + (((hf * 4 + c) ^ (r & 7)) << 4));
+          v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
         }
-        __align__(16) __nv_bfloat16 hh[32], ll[32];
+        // the fp32 values are in registers: hand the staging slot back to the producer now, not after the writes
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&stg_empty[slot])) : "memory");
+        __align__(16) __nv_bfloat16 hh[16], ll[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) split_bf16(v[i], hh[i], ll[i]);
+        for (int i = 0; i < 16; ++i) split_bf16(v[i], hh[i], ll[i]);
         mbar_wait(&empty_bar[s], ph ^ 1);  // the MMAs that read this stage's previous contents are done
         uint8_t* dh = smem + s * C::kStageBytes + r * 64;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int pos = (c ^ ((r >> 1) & 3)) << 4;
+        for (int c = 0; c < 2; ++c) {
+          const int pos = ((hf * 2 + c) ^ ((r >> 1) & 3)) << 4;
           *reinterpret_cast<uint4*>(dh + pos) = reinterpret_cast<const uint4*>(hh)[c];
           if (PASSES == 3) *reinterpret_cast<uint4*>(dh + C::kATileBytes + pos) = reinterpret_cast<const uint4*>(ll)[c];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) {
+        if ((threadIdx.x & 31) == 0)
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&stg_empty[slot])) : "memory");
-        }
       }
     }
   } else if (EPI == EPI_LOGITS || EPI == EPI_LOGITS8) {
