@@ -34,7 +34,8 @@ constexpr int BM = 128;
 constexpr int EPI_WARPS = 8;                // two per TMEM lane quarter, each owns half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int ACC_STAGES = 2;               // TMEM accumulator double buffer
-constexpr int CONV_WARPS = 8;               // AF kernels: warps that split the fp32 A tile into bf16 planes (half a row per thread)
+constexpr int CONV_WARPS = 4;               // AF kernels: warps that split the fp32 A tile into bf16 planes (4: a row per thread; 8: half a row,
+                                            // measured no faster and the 576-thread kernel spills)
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // one XOR-swizzled 32x32 fp32 staging tile per epilogue warp
 
 // BN = 128 for the step GEMMs (M = 3072 rows: more, smaller tiles fill 148 SMs better), BN = 256 where there are many
@@ -252,6 +253,10 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int n, int N) {
   if (n + 2 < N) r.z = __ldg(p + 2);
   if (n + 3 < N) r.w = __ldg(p + 3);
   return r;
+}
+
+__device__ __forceinline__ unsigned pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (unsigned)__bfloat16_as_ushort(a) | ((unsigned)__bfloat16_as_ushort(b) << 16);
 }
 
 template <int ACT>
@@ -523,9 +528,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (AF && warp >= 2 + EPI_WARPS) {
     // ===================== converters: fp32 A tile (staging) -> bf16 hi/lo operand tiles of the stage =====================
-    // thread t owns half of row r = t & 127: 16 floats = 64 B of the 128B-swizzled staging row -> 32 B in each of the
-    // 64B-swizzled operand tiles. Eight warps: with four (a whole row per thread) the converters, one warp per scheduler
-    // and latency-bound, needed ~0.5 us per k-block against 0.39 us of MMAs and set the kernel's pace (phase trace).
+    // thread t owns 1 / PARTS of row r = t & 127: PER floats of the 128B-swizzled staging row -> PER bf16 in each of the
+    // 64B-swizzled operand tiles
+    constexpr int PARTS = CONV_WARPS / 4, PER = 32 / PARTS;
     const int t = threadIdx.x - (2 + EPI_WARPS) * 32;
     const int r = t & 127, hf = t >> 7;
     int it = 0;
@@ -537,24 +542,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mbar_wait(&stg_full[slot], (it >> 1) & 1);
         ISC_TRACE(t == 0 && it == 8, 14);
         const uint8_t* src = stg + slot * C::kStgBytes + r * 128;
-        float v[16];
+        float v[PER];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float4 x = *reinterpret_cast<const float4*>(src + (((hf * 4 + c) ^ (r & 7)) << 4));
+        for (int c = 0; c < PER / 4; ++c) {
+          const float4 x = *reinterpret_cast<const float4*>(src + (((hf * (PER / 4) + c) ^ (r & 7)) << 4));
           v[4 * c] = x.x; v[4 * c + 1] = x.y; v[4 * c + 2] = x.z; v[4 * c + 3] = x.w;
         }
         // the fp32 values are in registers: hand the staging slot back to the producer now, not after the writes
         __syncwarp();
         if ((threadIdx.x & 31) == 0)
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&stg_empty[slot])) : "memory");
-        __align__(16) __nv_bfloat16 hh[16], ll[16];
+        __align__(16) __nv_bfloat16 hh[PER], ll[PER];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) split_bf16(v[i], hh[i], ll[i]);
+        for (int i = 0; i < PER; ++i) split_bf16(v[i], hh[i], ll[i]);
         mbar_wait(&empty_bar[s], ph ^ 1);  // the MMAs that read this stage's previous contents are done
         uint8_t* dh = smem + s * C::kStageBytes + r * 64;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int pos = ((hf * 2 + c) ^ ((r >> 1) & 3)) << 4;
+        for (int c = 0; c < PER / 8; ++c) {
+          const int pos = ((hf * (PER / 8) + c) ^ ((r >> 1) & 3)) << 4;
           *reinterpret_cast<uint4*>(dh + pos) = reinterpret_cast<const uint4*>(hh)[c];
           if (PASSES == 3) *reinterpret_cast<uint4*>(dh + C::kATileBytes + pos) = reinterpret_cast<const uint4*>(ll)[c];
         }
@@ -823,20 +828,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias) b4 = (full4 && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
           // the addends of all eight rows are requested up front: issued one by one in front of their use, each load's
-          // latency is exposed (ncu: the epilogue sat on the dependent FADDs)
-          float4 radd4[8], madd4[8];
+          // latency is exposed (ncu: the epilogue sat on the dependent FADDs). One register array serves rowadd or, when
+          // there is no rowadd, addmat (no caller passes both; if one did, addmat is loaded in the loop).
+          float4 add4[8];
+          const bool pre_madd = ep.addmat && !ep.rowadd;
           if (ep.rowadd) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              radd4[i] = i < nvalid ? ((full4 && radd_vec) ? __ldg(reinterpret_cast<const float4*>(radd[i] + n)) : load4_guarded(radd[i] + n, n, ep.N))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          if (ep.addmat) {
+              add4[i] = i < nvalid ? ((full4 && radd_vec) ? __ldg(reinterpret_cast<const float4*>(radd[i] + n)) : load4_guarded(radd[i] + n, n, ep.N))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (pre_madd) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float* mp = ep.addmat + (long long)(row0 + 4 * i) * ep.ld_addmat + n;
-              madd4[i] = i < nvalid ? ((full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+              add4[i] = i < nvalid ? ((full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
 #pragma unroll
@@ -846,12 +852,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               const long long row = row0 + 4 * i;
               float4 x = sc[r * 8 + (c4 ^ (r & 7))];
               x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-              if (ep.rowadd) {
-                const float4 t = radd4[i];
+              if (ep.rowadd || pre_madd) {
+                const float4 t = add4[i];
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
-              if (ep.addmat) {
-                const float4 t = madd4[i];
+              if (ep.addmat && !pre_madd) {
+                const float* mp = ep.addmat + row * ep.ld_addmat + n;
+                const float4 t = (full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N);
                 x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
               }
               x.x = act_ct<ACT>(x.x); x.y = act_ct<ACT>(x.y); x.z = act_ct<ACT>(x.z); x.w = act_ct<ACT>(x.w);
@@ -879,8 +886,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 __nv_bfloat16* dh = ep.hi + row * ep.ldp + n;
                 __nv_bfloat16* dl = ep.lo ? ep.lo + row * ep.ldp + n : nullptr;
                 if (full4 && p_vec) {
-                  *reinterpret_cast<uint2*>(dh) = *reinterpret_cast<uint2*>(h);
-                  if (dl) *reinterpret_cast<uint2*>(dl) = *reinterpret_cast<uint2*>(l);
+                  // packed in registers (taking the arrays' address sent them through the local-memory stack)
+                  *reinterpret_cast<uint2*>(dh) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                  if (dl) *reinterpret_cast<uint2*>(dl) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
                 } else {
                   for (int q = 0; q < 4 && n + q < ep.N; ++q) {
                     dh[q] = h[q];
