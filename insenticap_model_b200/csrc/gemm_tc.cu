@@ -304,11 +304,16 @@ __device__ __forceinline__ void trace_stamp(int slot) {
     g_trace[blockIdx.x * 16 + slot] = t;
   }
 }
-#ifdef ISC_TRACE_AF  // trace the fp32-A (converter-warp) GEMM of the prologue instead
-#define ISC_TRACE(cond, slot) do { if (AF == 1 && (cond)) trace_stamp(slot); } while (0)
+// which instantiation stamps: the fused-LSTM GEMM by default, -DISC_TRACE_AF the fp32-A prologue GEMM, or any
+// expression over the template parameters, e.g. -DISC_TRACE_SEL="(EPI==EPI_STD&&BN==256&&ACT==ACT_NONE&&AF==0&&CG==1)"
+#ifndef ISC_TRACE_SEL
+#ifdef ISC_TRACE_AF
+#define ISC_TRACE_SEL (AF == 1)
 #else
-#define ISC_TRACE(cond, slot) do { if (EPI == EPI_LSTM && (cond)) trace_stamp(slot); } while (0)
+#define ISC_TRACE_SEL (EPI == EPI_LSTM)
 #endif
+#endif
+#define ISC_TRACE(cond, slot) do { if (ISC_TRACE_SEL && (cond)) trace_stamp(slot); } while (0)
 #else
 #define ISC_TRACE(cond, slot) do { } while (0)
 #endif
@@ -810,6 +815,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         for (int i = 0; i < 8; ++i)
           radd[i] = ep.rowadd + (long long)((unsigned)(row0 + 4 * i) / (unsigned)ep.rows_per_group) * ep.ld_rowadd;
       }
+      // the bias of this lane's columns does not depend on the MMAs: fetched before the wait for the accumulator (phase
+      // trace: with one tile per SM the epilogue is 40 % of the kernel and sat on this load once per 32-column chunk)
+      // (not in the fp32-A kernels: their 448 threads leave 128 registers per thread and the epilogue would spill)
+      constexpr int NB4 = AF ? 1 : BN / 64;
+      float4 bias4[NB4];
+      if (!AF) {
+#pragma unroll
+        for (int cc = 0; cc < NB4; ++cc) {
+          const int n = n0 + (half * (BN / 64) + cc) * 32 + c4 * 4;
+          bias4[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias && n < ep.N)
+            bias4[cc] = (n + 3 < ep.N && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
+        }
+      }
       mbar_wait(&acc_full[as], (j >> 1) & 1);
       tcgen05_fence_after();
       ISC_TRACE(threadIdx.x == 64 && j < 2, 8 + 2 * j);
@@ -825,8 +844,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int n = n0 + c * 32 + c4 * 4;
         if (n < ep.N) {
           const bool full4 = n + 3 < ep.N;
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ep.bias) b4 = (full4 && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
+          float4 b4;
+          if (AF) {
+            b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ep.bias) b4 = (full4 && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
+          } else {
+            b4 = bias4[0];  // (a select chain, not an indexed register array: the chunk loop is not unrolled)
+#pragma unroll
+            for (int k = 1; k < NB4; ++k)
+              if (cc == k) b4 = bias4[k];
+          }
           // the addends of all eight rows are requested up front: issued one by one in front of their use, each load's
           // latency is exposed (ncu: the epilogue sat on the dependent FADDs). One register array serves rowadd or, when
           // there is no rowadd, addmat (no caller passes both; if one did, addmat is loaded in the loop).
