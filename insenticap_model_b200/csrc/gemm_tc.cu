@@ -837,10 +837,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int c = half * (BN / 64) + cc;
         float v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN + c * 32, v);
+        ISC_TRACE(threadIdx.x == 64 && j == 0 && cc == 0, 3);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           sc[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         __syncwarp();
+        ISC_TRACE(threadIdx.x == 64 && j == 0 && cc == 0, 4);
         const int n = n0 + c * 32 + c4 * 4;
         if (n < ep.N) {
           const bool full4 = n + 3 < ep.N;
@@ -927,6 +929,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
         }
         __syncwarp();  // staging tile is reused by the next chunk
+        ISC_TRACE(threadIdx.x == 64 && j == 0 && cc < 2, 5 + cc);
       }
       // release the accumulator stage to the (leader's) MMA warp
       tcgen05_fence_before();

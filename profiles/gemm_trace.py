@@ -36,11 +36,15 @@ with torch.no_grad():
     raw.isc_debug_gemm_trace(C.c_void_p(0))
 t = trace.cpu().numpy().reshape(148, 16).astype(np.float64)
 t0 = t[:, 0][t[:, 0] > 0].min()
+std = "--std" in sys.argv  # plain-epilogue trace build: slots 3-6 are epilogue chunk stamps, not MMA / producer stamps
 names = {0: "kernel entry", 1: "set-up done", 5: "stage 0 loads issued", 2: "first operand stage landed",
          12: "k-block 8: producer waits for a free stage", 13: "k-block 8: stage free", 6: "k-block 8: loads issued",
          14: "k-block 8: fp32 A tile in staging (converter)", 7: "k-block 8: stage landed (MMA thread)", 3: "tile0 MMAs issued", 4: "tile1 MMAs issued",
          8: "tile0 accumulator ready", 9: "tile0 epilogue done", 10: "tile1 accumulator ready", 11: "tile1 epilogue done", 15: "exit"}
-print("fused-LSTM GEMM, last launch of a B=%d beam-3 call with T=%d: us since the first CTA's entry" % (B, steps))
+if std:
+    names.update({3: "epilogue chunk 0: TMEM loaded", 4: "epilogue chunk 0: staged in smem", 5: "epilogue chunk 0: stored",
+                  6: "epilogue chunk 1: stored"})
+print("traced GEMM, last launch of a B=%d beam-3 call with T=%d: us since the first CTA's entry" % (B, steps))
 for k in sorted(names):
     col = t[:, k]
     ok = col > 0
