@@ -403,6 +403,7 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
     io.c_out = w.state_c[(t + 1) & 1];
     io.logits = w.logits;
     io.ld_logits = w.ld_logits;
+    io.skip_pack = fused && t > 0;  // the merge kernel of step t - 1 has packed this step's recurrent operand rows
     if (compact0 && t == 0) {
       io.state_rows = M;
       ISC_TRY(run_step(c, w, B, 1, io));
@@ -411,6 +412,12 @@ int isc_decode_beam(const isc_dims_t* dims, const void* packed, int precision, c
     }
     BeamParams bp;
     bp.compact0 = compact0 ? 1 : 0;
+    if (fused && t + 1 < T) {
+      bp.h_state = io.h_out;
+      bp.state_rows = M;
+      bp.x1 = rowdest(nullptr, 0, w.pX1, 3 * H);
+      bp.x2 = rowdest(nullptr, 0, w.pX2, 3 * H);
+    }
     bp.logits = fused ? nullptr : w.logits;
     bp.ld = w.ld_logits;
     bp.rec = io.sel.rec;

@@ -334,6 +334,7 @@ struct StepIO {
   // rows of one plane of the OUTPUT state ([2][state_rows][H]: attention LSTM, language LSTM); 0 = M. Larger than M when
   // a beam search's first step runs on one row per image but the following steps index B * K rows.
   long long state_rows = 0;
+  bool skip_pack = false;  // X1 / X2's recurrent rows were already written (by the previous step's beam merge)
 };
 
 // One decode step over M rows (captioner.py:168-186), raw classifier logits out.
@@ -354,7 +355,8 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
   RowDest x1 = rowdest(w.X1, 3 * H, w.pX1, 3 * H);
   RowDest x2 = rowdest(w.X2, 3 * H, w.pX2, 3 * H);
   // fused path: X1 = [h_lang_prev | h_att_prev] only, the word term comes from the xt_gates table in the epilogue
-  ISC_TRY(launch_embed_pack(io.it, io.parent, io.h_in, M, c.d.vocab, fuse_lstm ? nullptr : pk.emb, x1, x2, c.s));
+  if (!io.skip_pack)
+    ISC_TRY(launch_embed_pack(io.it, io.parent, io.h_in, M, c.d.vocab, fuse_lstm ? nullptr : pk.emb, x1, x2, c.s));
 
   // attention LSTM
   if (fuse_lstm) {

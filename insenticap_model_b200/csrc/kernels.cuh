@@ -124,6 +124,12 @@ struct BeamParams {
   // step 0 ran on ONE row per image (all K beams of an image are identical before the first word): its records and
   // state rows are indexed by image, and the parents written for step 1 point at those rows
   int compact0 = 0;
+  // fused path: the merge kernel also builds the NEXT step's recurrent operand rows — X1[m] = [h_lang | h_att] and
+  // X2[m, 2H:3H] = h_lang of the state row parent[m] it has just chosen (what embed_pack does at step 0), which
+  // saves a launch per step. h_state = this step's output state [2][state_rows][H]; null = leave it to embed_pack.
+  const float* h_state = nullptr;
+  long long state_rows = 0;
+  RowDest x1, x2;
 };
 int launch_beam_select(const BeamParams& p, cudaStream_t stream);
 int launch_beam_init(long long* it, int* alive, int* len, double* score, int* parent, int B, int K, int sos_id,

@@ -447,6 +447,19 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
   __threadfence_block();
   __syncthreads();
   beam_pool(p, b);
+  if (p.h_state) {  // the next step's operand rows of this image's beams, read through the parents chosen above
+    __syncthreads();
+    const int c = threadIdx.x * 4;
+    for (int j = 0; j < K; ++j) {
+      const long long m = (long long)b * K + j;
+      const long long src = p.parent[m];
+      const float4 ha = *reinterpret_cast<const float4*>(p.h_state + src * H + c);
+      const float4 hl = *reinterpret_cast<const float4*>(p.h_state + (p.state_rows + src) * H + c);
+      p.x1.store4(m, c, hl);
+      p.x1.store4(m, H + c, ha);
+      p.x2.store4(m, 2 * H + c, hl);
+    }
+  }
 }
 
 // Fused greedy pick (sample_max = 1): a warp per row takes the argmax and the normaliser from the records.
