@@ -28,18 +28,20 @@ def main(path):
     print("total %.1f us over %d launches" % (tot, len(seq)))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%-58s n=%4d total %10.1f us  avg %8.1f  share %.3f" % (k[:58], v[0], v[1], v[1] / v[0], v[1] / tot))
-    idx = [i for i, s in enumerate(seq) if "embed_pack" in s[0]]
-    if len(idx) > 2:
+    # a decode step ends with its merge kernel (beam search) — the one kernel every step has exactly once
+    ends = [i for i, s in enumerate(seq) if "beam_merge" in s[0] or "beam_select" in s[0] or "greedy_merge" in s[0]]
+    if len(ends) > 2:
         print("decode step t=1:")
-        for s in seq[idx[1]:idx[2]]:
+        for s in seq[ends[0] + 1:ends[1] + 1]:
             print("   %-50s %9.1f us grid %s" % (s[0][:50], s[1], s[2]))
-        print("   step total %.1f us" % sum(s[1] for s in seq[idx[1]:idx[2]]))
+        print("   step total %.1f us" % sum(s[1] for s in seq[ends[0] + 1:ends[1] + 1]))
         first_gemm = next(i for i, s in enumerate(seq) if "gemm_tc" in s[0] or "gemm_simt" in s[0])
-        print("prologue (first GEMM .. first embed_pack): %.1f us" % sum(s[1] for s in seq[first_gemm:idx[0]]))
+        first_step = next(i for i, s in enumerate(seq) if "embed_pack" in s[0] or "beam_init" in s[0])
+        print("prologue (first GEMM .. beam init): %.1f us" % sum(s[1] for s in seq[first_gemm:first_step]))
+        print("decode step t=0 (one row per image): %.1f us" % sum(s[1] for s in seq[first_step + 1:ends[0] + 1]))
         print("prologue head:")
         for s in seq[first_gemm:first_gemm + 6]:
             print("   %-50s %9.1f us grid %s" % (s[0][:50], s[1], s[2]))
-
 
 if __name__ == "__main__":
     main(sys.argv[1])
