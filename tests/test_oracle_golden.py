@@ -180,3 +180,33 @@ def test_sentcls_oracle_matches_reference_golden():
     np.testing.assert_allclose(pred.numpy(), gd["pred"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(weights.numpy(), gd["weights"], rtol=1e-5, atol=1e-6)
     assert pred.argmax(-1).tolist() == gd["result"].tolist()
+
+
+def test_port_matches_unmodified_reference_bytecode():
+    """When oracle/_ref exists (built by oracle/build_ref.py from /root/reference), the oracle port and the UNMODIFIED
+    reference `Captioner.sample` / `forward(mode='rl')` must agree on fresh inputs (not only on the committed goldens)."""
+    import pytest
+    from oracle import build_ref
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = build_ref.import_reference()
+    V, B = 1000, 3
+    p = syn.synthetic_state_dict(V, 5)
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=11)
+    m = ref.Captioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS))
+    m.load_state_dict(p)
+    m.eval()
+    with torch.no_grad():
+        seq_r, lp_r, _ = m(fc, att, cpts, sentis, labels, T, 1, mode="rl")
+        f = O.prologue(p, fc, att, cpts, sentis, labels)
+        seq, lp, _ = O.decode_greedy(p, f, B, T)
+        assert np.array_equal(seq.numpy(), seq_r.numpy())
+        np.testing.assert_allclose(lp.numpy(), lp_r.numpy(), rtol=1e-5, atol=1e-5)
+        tk, sc, ln = O.beam_search(p, O.prologue(p, fc, att, None, sentis, labels), B, 3, 1, T)
+        for i in range(B):
+            caps, scores = m.sample(fc[i], att[i], sentis[i], labels[i:i + 1], beam_size=3, decoding_constraint=1, max_seq_len=T)
+            for k in range(3):
+                n = int(ln[i, k])
+                words = [w for w in tk[i, k, :n].tolist() if w != 2]
+                assert caps[k] == " ".join(m.idx2word[w] for w in words)
+            np.testing.assert_allclose(scores, sc[i].numpy(), atol=2e-4)
