@@ -9,9 +9,11 @@ PyTorch is plumbing here (parameters, device memory, streams); every FLOP of the
 C-ABI library. There is no CPU and no eager-PyTorch fallback: calling a compute method with the
 library missing, on CPU tensors, or on a non-sm_100 device raises.
 
-Scope of this build: inference-mode semantics (dropout = identity, ss_prob = 0). Calling
-forward_xe / forward_seq2seq / forward_rl with ``self.training`` set raises — the autograd
-(backward) path of the fused step is not built yet (DESIGN.md "out of scope this round").
+Training: in ``train()`` mode (or ``eval()`` with gradients enabled, in ``precision="bf16x3"``) forward_xe /
+forward_seq2seq / forward_rl(sample_max=0) carry autograd history through the hand-written backward
+(isc_train_forward / isc_train_backward): dropout from torch-drawn keep masks, scheduled sampling by Gumbel-max.
+Host-tensor inputs to ``beam_search`` / ``sample`` take the pipelined host path and return host tensors that are
+complete when the call returns.
 """
 from __future__ import annotations
 
@@ -192,6 +194,9 @@ class Captioner(nn.Module):
         self.ss_override = None  # tests: {"uniform": [T,B], "noise": [T,B,V]} for scheduled sampling
         self.dropout_override = None  # tests: dict of uint8 keep masks {fc, att, sw, sl, out, scale}
         self.use_cuda_graph = False  # beam_search: capture the device-side call once and replay it
+        # graph replay writes into the SAME output tensors every time; True returns copies (0.4 MB at B = 1024) so that a
+        # caller may keep results across calls like with the reference, False hands out the graph's own buffers
+        self.graph_outputs_fresh = True
         self._graphs = {}
         self._copy_stream = None
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
@@ -221,6 +226,9 @@ class Captioner(nn.Module):
         key = (kind, dev.index)
         buf = self._ws.get(key)
         if buf is None or buf.numel() < nbytes:
+            # a captured CUDA graph holds the raw address of the workspace it was captured with: growing the buffer
+            # frees that block, so every graph captured so far is dropped (recaptured on its next use)
+            self._graphs.clear()
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
             self._ws[key] = buf
         return buf
@@ -636,8 +644,11 @@ class Captioner(nn.Module):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = self._beam_search_device(*args, beam_size, decoding_constraint, max_seq_len)
-            hit = self._graphs[key] = (g, out, args)  # args kept alive: the graph holds their addresses
+            # args, workspaces and packed weights kept alive: the graph holds their addresses
+            hit = self._graphs[key] = (g, out, args, tuple(self._ws.values()), self._packed)
         hit[0].replay()
+        if self.graph_outputs_fresh:
+            return tuple(o.clone() for o in hit[1])
         return hit[1]
 
     def _beam_search_host(self, fc_feats, att_feats, senti_words, senti_labels, beam_size, decoding_constraint,
@@ -672,6 +683,11 @@ class Captioner(nn.Module):
             h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
             h.copy_(x, non_blocking=True)
             outs.append(h)
+        # host tensors are handed to code that reads them with the CPU: the call returns only when the D2H copies
+        # have landed (an event on the current stream, not a device-wide synchronize)
+        done = torch.cuda.Event()
+        done.record(cur)
+        done.synchronize()
         return tuple(outs)
 
     def _beam_search_device(self, fc_feats, att_feats, senti_words, senti_labels, beam_size, decoding_constraint,

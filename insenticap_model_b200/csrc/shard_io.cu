@@ -155,10 +155,12 @@ int isc_shard_open(const char* path, isc_shard_t* out) {
   memcpy(&s->h, s->map, sizeof(ShardHeader));
   const ShardHeader& h = s->h;
   const bool sane = memcmp(h.magic, "ISCFEAT1", 8) == 0 && h.version == 1 &&
-                    (h.dtype == ISC_SHARD_F32 || h.dtype == ISC_SHARD_BF16) && h.feat_dim > 0 && h.n_regions > 0 &&
+                    (h.dtype == ISC_SHARD_F32 || h.dtype == ISC_SHARD_BF16) && h.feat_dim > 0 && h.n_regions > 0 && h.feat_dim <= (1u << 24) && h.n_regions <= (1u << 24) &&
                     h.record_bytes >= (uint64_t)h.feat_dim * (1 + (uint64_t)h.n_regions) * elem_bytes(h.dtype) &&
-                    h.data_offset >= sizeof(ShardHeader) + h.names_bytes &&
-                    h.data_offset + h.n_images * h.record_bytes <= s->map_bytes;
+                    // every bound is checked without a product or sum that could wrap for a crafted header
+                    h.record_bytes > 0 && h.names_bytes <= s->map_bytes - sizeof(ShardHeader) &&
+                    h.data_offset >= sizeof(ShardHeader) + h.names_bytes && h.data_offset <= s->map_bytes &&
+                    h.n_images <= (s->map_bytes - h.data_offset) / h.record_bytes;
   if (!sane) {
     isc::set_error("shard_open: %s is not a version-1 ISCFEAT1 shard (bad magic, header or truncated file)", path);
     close_shard(s);

@@ -91,7 +91,11 @@ class FeatureShard:
         present (``pin`` overrides)."""
         idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
         n = idx.shape[0]
-        pin = torch.cuda.is_available() if pin is None else pin
+        if pin is None:
+            # a DataLoader worker is a forked child: CUDA (and so cudaHostAlloc) cannot be initialised there once the
+            # parent has used it; workers gather into pageable memory and the loader's pin_memory thread / the consumer
+            # page-locks it
+            pin = torch.cuda.is_available() and torch.utils.data.get_worker_info() is None
         fc = torch.empty((n, self.feat_dim), dtype=self.dtype, pin_memory=pin) if want_fc else None
         att = torch.empty((n,) + self.att_shape, dtype=self.dtype, pin_memory=pin) if want_att else None
         if n == 0:
@@ -149,7 +153,8 @@ def _stack_features(feats):
     """The reference's ``torch.FloatTensor(np.array(feats))``; lazy references become one batched, threaded gather."""
     if feats and isinstance(feats[0], _Lazy):
         sh, which = feats[0].shard, feats[0].which
-        if sh.direct_device is not None:
+        # the direct path issues CUDA copies: only in the process that owns the CUDA context (not in a forked worker)
+        if sh.direct_device is not None and torch.utils.data.get_worker_info() is None:
             fc, att = sh.copy_to_device([f.idx for f in feats], want_fc=which == "fc", want_att=which == "att")
             return fc if which == "fc" else att
         fc, att = sh.gather([f.idx for f in feats], want_fc=which == "fc", want_att=which == "att")

@@ -26,16 +26,22 @@ from .train import FusedClampAdam
 
 def get_cls_reward(sample_captions, sample_masks, greedy_captions, greedy_masks, senti_labels, sent_senti_cls):
     """self_critical/utils.py:120-151 on device tensors: 1[argmax(classifier(sample)) == label] * the classifier's
-    per-word weights, zero-padded to the caption length. Returns a float tensor [B, T]."""
+    per-word weights, zero-padded to the caption length. Returns a float tensor [B, T].
+    A classifier with ``forward_device`` (sent_senti_cls.SentenceSentimentClassifier) takes the lengths as a DEVICE tensor
+    and returns weights already padded to T: no host round trip; any other module (the reference's class) gets the
+    reference's python list of lengths."""
     training = sent_senti_cls.training
-    lens = [int(x) for x in sample_masks.sum(dim=-1).to(torch.int).tolist()]
+    T = sample_captions.shape[1]
     sent_senti_cls.eval()
     with torch.no_grad():
-        preds, att_w = sent_senti_cls(sample_captions, lens)
+        if hasattr(sent_senti_cls, "forward_device"):
+            preds, att_w = sent_senti_cls.forward_device(sample_captions, sample_masks.sum(dim=-1).to(torch.int32))
+        else:
+            lens = [int(x) for x in sample_masks.sum(dim=-1).to(torch.int).tolist()]
+            preds, att_w = sent_senti_cls(sample_captions, lens)
         hit = (preds.softmax(dim=-1).argmax(dim=-1) == senti_labels).to(att_w.dtype).unsqueeze(1)
         scores = hit * att_w
     sent_senti_cls.train(training)
-    T = sample_captions.shape[1]
     return torch.nn.functional.pad(scores, (0, T - scores.shape[1])).float()
 
 
@@ -60,6 +66,7 @@ class Detector(nn.Module):
         self.seq_flag = 1.0
         self.senti_threshold = 0.7
         self.grad_clip = 0.1  # clip_gradient's default (models/decoder.py:14)
+        self.sample_noise = None  # tests: Gumbel noise [T, B, V] for the sampled pass (forward_rl(noise=...))
 
     def set_ciderd_scorer(self, captions):
         self.ciderd_scorer = get_ciderd_scorer(captions, self.captioner.sos_id, self.captioner.eos_id,
@@ -79,8 +86,11 @@ class Detector(nn.Module):
     def forward(self, data, data_type, training):
         """models/decoder.py:52-180. ``data`` = (caption batches, senti-corpus batches), any iterables with len()."""
         self.captioner.train(training)
-        all_losses = defaultdict(float)
+        # every loss / reward stays a DEVICE scalar inside the loop and the sums come back in ONE stacked D2H copy after it
+        # (the reference pulls seven floats per iteration, models/decoder.py:88-160)
+        acc = defaultdict(lambda: 0.0)
         device = next(self.parameters()).device
+        collect, self.captioner.collect_attention_weights = self.captioner.collect_attention_weights, False  # no consumer
         if training:
             seq2seq_data = iter(data[1])
         caption_data = iter(data[0])
@@ -101,38 +111,43 @@ class Detector(nn.Module):
                 if self.senti_detector is None:
                     raise RuntimeError("Detector: 'fact' batches (and evaluation) need the image sentiment detector: pass "
                                        "senti_detector= (e.g. the reference's SentimentDetector)")
-                senti_labels, _, _, _ = self.senti_detector.sample(att_feats, self.senti_threshold)
+                if hasattr(self.senti_detector, "sample_labels"):  # device labels only: no D2H for the sentiment names
+                    senti_labels = self.senti_detector.sample_labels(att_feats, self.senti_threshold)
+                else:
+                    senti_labels, _, _, _ = self.senti_detector.sample(att_feats, self.senti_threshold)
                 senti_labels = senti_labels.detach()
 
             sample_captions, sample_logprobs, seq_masks = self.captioner(
-                fc_feats, att_feats, cpts_tensor, sentis_tensor, senti_labels, self.max_seq_len, sample_max=0, mode="rl")
+                fc_feats, att_feats, cpts_tensor, sentis_tensor, senti_labels, self.max_seq_len, sample_max=0, mode="rl",
+                **({"noise": self.sample_noise} if self.sample_noise is not None else {}))
             da_loss = self.cap_da_crit(self.captioner.cpt_feats, self.captioner.fc_feats.detach())
-            all_losses["da_loss"] += float(da_loss.detach())
+            acc["da_loss"] = acc["da_loss"] + da_loss.detach()
 
             self.captioner.eval()
             with torch.no_grad():
                 greedy_captions, _, greedy_masks = self.captioner(
                     fc_feats, att_feats, cpts_tensor, sentis_tensor, senti_labels, self.max_seq_len, sample_max=1, mode="rl")
             self.captioner.train(training)
+            self.last_captions = (sample_captions, greedy_captions)  # device tensors of the last iteration (inspection)
 
             if data_type == "fact":
                 fact_reward = get_self_critical_reward(sample_captions, greedy_captions, fns, ground_truth,
                                                        self.captioner.sos_id, self.captioner.eos_id, self.ciderd_scorer,
                                                        as_tensor=True).float()
-                all_losses["fact_reward"] += float(fact_reward[:, 0].mean())
+                acc["fact_reward"] = acc["fact_reward"] + fact_reward[:, 0].mean()
             else:
                 fact_reward = 0
 
             if self.sent_senti_cls is not None:
                 cls_reward = get_cls_reward(sample_captions, seq_masks, greedy_captions, greedy_masks, senti_labels,
                                             self.sent_senti_cls)
-                all_losses["cls_reward"] += float(cls_reward.mean(-1).mean(-1))
+                acc["cls_reward"] = acc["cls_reward"] + cls_reward.mean(-1).mean(-1)
                 rewards = fact_reward + self.cls_flag * cls_reward
             else:
                 rewards = fact_reward + torch.zeros_like(seq_masks)
-            all_losses["all_rewards"] += float(rewards.mean(-1).mean(-1))
+            acc["all_rewards"] = acc["all_rewards"] + rewards.mean(-1).mean(-1)
             cap_loss = self.cap_rl_crit(sample_logprobs, seq_masks, rewards)
-            all_losses["cap_loss"] += float(cap_loss.detach())
+            acc["cap_loss"] = acc["cap_loss"] + cap_loss.detach()
 
             xe_loss = 0.0
             if data_type == "fact":
@@ -144,7 +159,7 @@ class Detector(nn.Module):
                     xe_senti_labels = xe_senti_labels.softmax(dim=-1).argmax(dim=-1).detach()
                 pred = self.captioner(fc_feats, att_feats, cpts_tensor, caps_tensor, xe_senti_labels, ss_prob=0.5, mode="xe")
                 xe_loss = self.cap_xe_crit(pred, caps_tensor[:, 1:], lengths)
-                all_losses["xe_loss"] += float(xe_loss)
+                acc["xe_loss"] = acc["xe_loss"] + xe_loss.detach()
 
             seq2seq_loss = 0.0
             if training:
@@ -157,7 +172,7 @@ class Detector(nn.Module):
                 s_sentis, s_labels = s_sentis.to(device), s_labels.to(device)
                 pred = self.captioner(s_caps, s_cpts, s_sentis, s_labels, ss_prob=0.25, mode="seq2seq")
                 seq2seq_loss = self.seq_flag * self.cap_xe_crit(pred, s_caps[:, 1:], s_lengths)
-                all_losses["seq2seq_loss"] += float(seq2seq_loss)
+                acc["seq2seq_loss"] = acc["seq2seq_loss"] + seq2seq_loss.detach()
 
             cap_loss = cap_loss + xe_loss + da_loss + seq2seq_loss
             if training:
@@ -166,8 +181,13 @@ class Detector(nn.Module):
                 cap_loss.backward()
                 optim.step()  # clip_gradient (+-0.1) and Adam in one kernel
 
-        for k, v in all_losses.items():
-            all_losses[k] = v / len(data)  # the reference divides by len(data), a 2-tuple (decoder.py:178-179); kept
+        self.captioner.collect_attention_weights = collect
+        all_losses = defaultdict(float)
+        if acc:
+            keys = list(acc)
+            vals = torch.stack([torch.as_tensor(acc[k], dtype=torch.float32, device=device).reshape(()) for k in keys]).tolist()
+            for k, v in zip(keys, vals):
+                all_losses[k] = v / len(data)  # the reference divides by len(data), a 2-tuple (decoder.py:178-179); kept
         return all_losses
 
     def sample(self, fc_feats, att_feats, sentis_tensor, beam_size=3, decoding_constraint=1):

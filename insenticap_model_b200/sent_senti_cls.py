@@ -54,6 +54,24 @@ class SentenceSentimentClassifier(nn.Module):
 
     def forward(self, seqs, lengths):
         """seqs int64 [bs, max_seq_len], lengths list/tensor [bs] -> (pred [bs, n], word weights [bs, max(lengths)])."""
+        lens = [int(x) for x in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
+        if min(lens) < 1:
+            raise RuntimeError("lengths must be >= 1 (pack_padded_sequence rejects empty sequences)")
+        T = max(lens)
+        if T > seqs.shape[1]:
+            raise RuntimeError("a length exceeds the caption tensor's width")
+        return self._run(seqs, torch.tensor(lens, dtype=torch.int32), T)
+
+    def forward_device(self, seqs, lengths):
+        """The same forward with the lengths as a DEVICE int tensor [bs] (each >= 1) and no host round trip: the word
+        weights come back [bs, seqs.shape[1]], with the columns at and past max(lengths) — which the reference's output
+        does not have, and which its callers zero-pad (self_critical/utils.py:142-143) — set to zero."""
+        T = seqs.shape[1]
+        lens = lengths.to(torch.int32)
+        pred, att = self._run(seqs, lens, T)
+        return pred, att * (torch.arange(T, device=att.device) < lens.max()).to(att.dtype)
+
+    def _run(self, seqs, lens_t, T):
         if self.training:
             raise NotImplementedError("SentenceSentimentClassifier runs in eval() mode on the B200 path")
         dev = self.sent_senti_cls[0].weight.device
@@ -62,14 +80,9 @@ class SentenceSentimentClassifier(nn.Module):
                                "captions to a B200; there is no CPU fallback")
         lib = _lib.load()
         packed = self._pack(dev)
-        lens = [int(x) for x in (lengths.tolist() if torch.is_tensor(lengths) else lengths)]
-        if min(lens) < 1:
-            raise RuntimeError("lengths must be >= 1 (pack_padded_sequence rejects empty sequences)")
-        B, T = seqs.shape[0], max(lens)
-        if T > seqs.shape[1]:
-            raise RuntimeError("a length exceeds the caption tensor's width")
+        B = seqs.shape[0]
         seqs = seqs.long().contiguous()
-        lens_t = torch.tensor(lens, dtype=torch.int32, device=dev)
+        lens_t = lens_t.to(dev).contiguous()
         n = len(self.sentiment_categories)
         nbytes = lib.isc_sentcls_workspace_bytes(B, T)
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:

@@ -100,5 +100,11 @@ class SentimentDetector(nn.Module):
         sentiments = [self.sentiment_categories[i] for i in labels.tolist()]
         return labels, maps, sentiments, scores
 
+    def sample_labels(self, features, senti_threshold=0):
+        """``sample(...)[0]`` only: the thresholded labels as a device tensor, without the D2H copy that building the
+        list of sentiment NAMES costs (the RL-iteration driver uses nothing else, models/decoder.py:83-84)."""
+        self.eval()
+        return self._detect(features, senti_threshold)[2]
+
     def get_optim_criterion(self, lr, weight_decay=0):
         return torch.optim.Adam(self.parameters(), lr=lr, weight_decay=weight_decay), nn.CrossEntropyLoss()

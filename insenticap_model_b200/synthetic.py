@@ -247,3 +247,29 @@ def synthetic_references(n_images: int, vocab_size: int, refs_per_image: int = 5
             caps.append([1] + ids.tolist() + [2])
         out.append(caps)
     return out
+
+
+def gumbel_noise(T: int, batch: int, vocab_size: int, seed: int = 21) -> torch.Tensor:
+    """Standard Gumbel noise [T, B, V] for reproducible sampled decodes (argmax(log p + g) draws from p)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(T, batch, vocab_size, generator=g).clamp_(1e-10, 1.0 - 1e-7)
+    return -torch.log(-torch.log(u))
+
+
+def detector_batches(batch: int, vocab_size: int, max_seq_len: int):
+    """In-memory batches with the tuple layouts Detector.forward consumes (/root/reference/models/decoder.py:64-76,
+    :149-158; the loaders' collate outputs, dataloader.py:70-109): one 'fact' batch, one 'senti' batch and one
+    sentiment-corpus (seq2seq) batch, plus the ground-truth dict of the fact images."""
+    fc, _, cpts, sentis, labels = synthetic_inputs(batch, vocab_size, seed=5)
+    att = senti_detector_inputs(batch)  # signed per-image scales: the image sentiment detector then yields varied labels
+    g = torch.Generator().manual_seed(6)
+    caps = torch.randint(4, vocab_size, (batch, max_seq_len + 1), generator=g)
+    caps[:, 0] = 1
+    lengths = [max_seq_len] * batch
+    refs = synthetic_references(batch, vocab_size, 5, seed=3)
+    fns = ["img%d" % i for i in range(batch)]
+    gts = {fn: refs[i] for i, fn in enumerate(fns)}
+    fact = [(fns, fc, att, (caps, lengths), cpts, sentis, gts)]
+    senti = [(fns, fc, att, cpts, sentis, labels)]
+    scs = [((caps, lengths), cpts, sentis, labels)]
+    return fact, senti, scs, gts

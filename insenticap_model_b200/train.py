@@ -50,6 +50,27 @@ def allreduce_gradients(flat_grads: torch.Tensor, group=None) -> int:
     return world
 
 
+class _HyperView(dict):
+    """The single param group of FusedClampAdam: a dict whose 'lr' / 'weight_decay' / 'betas' / 'eps' entries write
+    through to the optimizer (``for g in optim.param_groups: g['lr'] = lr`` as in train_xe.py:132-133)."""
+    _KEYS = ("lr", "weight_decay", "betas", "eps")
+
+    def __init__(self, opt):
+        super().__init__()
+        self._opt = opt
+        for k in self._KEYS:
+            dict.__setitem__(self, k, getattr(opt, k))
+        dict.__setitem__(self, "params", list(opt.model.parameters()))
+
+    def __getitem__(self, k):
+        return getattr(self._opt, k) if k in self._KEYS else dict.__getitem__(self, k)
+
+    def __setitem__(self, k, v):
+        if k in self._KEYS:
+            setattr(self._opt, k, v)
+        dict.__setitem__(self, k, v)
+
+
 class FusedClampAdam:
     """clip_gradient(optimizer, grad_clip) + torch.optim.Adam.step() (train_xe.py:19-23, :191-192;
     models/decoder.py:168-170) as one kernel over the flat parameter / gradient / moment buffers."""
@@ -63,6 +84,34 @@ class FusedClampAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.steps = 0
         model._packed_key = None
+
+    # -- torch.optim.Optimizer surface the reference's scripts use: param_groups[...]['lr'] for the learning-rate decay
+    #    (train_xe.py:130-133), state_dict()/load_state_dict() for checkpoint save / resume (train_xe.py:53, :245)
+    @property
+    def param_groups(self):
+        return [self._group]
+
+    @property
+    def _group(self):
+        g = self.__dict__.get("_group_dict")
+        if g is None:
+            g = self.__dict__["_group_dict"] = _HyperView(self)
+        return g
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "steps": int(self.steps),
+                "lr": float(self.lr), "weight_decay": float(self.weight_decay), "betas": tuple(self.betas),
+                "eps": float(self.eps), "grad_clip": float(self.grad_clip)}
+
+    def load_state_dict(self, sd):
+        for k in ("exp_avg", "exp_avg_sq"):
+            t = sd[k]
+            if t.numel() != self.flat_p.numel():
+                raise ValueError("optimizer state %s has %d elements, the model has %d" % (k, t.numel(), self.flat_p.numel()))
+            getattr(self, k).copy_(t.to(self.flat_p.device).reshape(-1))
+        self.steps = int(sd["steps"])
+        self.lr, self.weight_decay = float(sd["lr"]), float(sd["weight_decay"])
+        self.betas, self.eps, self.grad_clip = tuple(sd["betas"]), float(sd["eps"]), float(sd["grad_clip"])
 
     def zero_grad(self):
         self.flat_g.zero_()

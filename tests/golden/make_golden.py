@@ -241,6 +241,77 @@ def loader_goldens():
     print("loader goldens:", {k: len(json.dumps(v)) for k, v in out.items()})
 
 
+def detector_goldens():
+    """The reference's Detector (models/decoder.py:21-192) with its OWN SentimentDetector and SentenceSentimentClassifier on
+    in-memory synthetic batches, ``training=False`` (dropout off, no scheduled sampling, no optimizer step). The sampled
+    pass draws through torch.multinomial, whose stream no other implementation can reproduce: it is patched HERE (the
+    reference files stay untouched) to Gumbel-max over injected noise, argmax(log p + g_t) — the form the B200 path's
+    forward_rl(noise=...) consumes — so that sampled ids, both rewards and the REINFORCE loss become comparable."""
+    from models.decoder import Detector as RefDetector
+    V, B, Tm = 64, 6, 12  # the EOS-heavy recipe (SURVEY 8c): peaked word distributions, captions of varied length
+    settings = dict(syn.DEFAULT_SETTINGS, sentiment_convs_num=2, sentiment_fcs_num=2)
+    torch.manual_seed(0)
+    # neutral FIRST: with it last every synthetic image is labelled neutral (see senti_goldens); this order yields mixed
+    # labels. The classifier seed is the first whose reward is non-zero on these captions (recorded in the golden).
+    cats = ["neutral", "positive", "negative"]
+    d = RefDetector(syn.make_vocab(V), Tm, cats, {"cap_lr": 4e-4}, settings)
+    d.captioner.load_state_dict(syn.synthetic_state_dict(V, 0, eos_heavy=True))
+    d.senti_detector.load_state_dict(syn.senti_detector_state_dict(0))
+    cls_seed = int(os.environ.get("ISC_GOLDEN_CLS_SEED", "3"))
+    d.sent_senti_cls.load_state_dict(syn.sent_cls_state_dict(V, cls_seed))
+    fact, senti, scs, gts = syn.detector_batches(B, V, Tm)
+    d.set_ciderd_scorer({"train": gts})
+    noise = syn.gumbel_noise(Tm, B, V, seed=21)
+    state = {"t": 0}
+    real_multinomial = torch.multinomial
+
+    def gumbel_max(probs, n, *a, **k):
+        t = state["t"]
+        state["t"] += 1
+        return (probs.log() + noise[t]).argmax(dim=1, keepdim=True)
+
+    calls = []
+    real_forward = d.captioner.forward
+
+    def recording_forward(*args, **kwargs):
+        out = real_forward(*args, **kwargs)
+        if kwargs.get("mode") == "rl":
+            calls.append([o.detach().clone() for o in out])
+        return out
+
+    d.captioner.forward = recording_forward
+    out = {"cls_seed": np.array(cls_seed), "categories": np.array(cats)}
+    torch.multinomial = gumbel_max
+    try:
+        for tag, data, dtype in (("fact", (fact, scs), "fact"), ("senti", (senti, scs), "senti")):
+            state["t"] = 0
+            del calls[:]
+            with torch.no_grad():  # evaluation call (train_rl.py:258 runs it under no_grad as well)
+                losses = d(data, dtype, training=False)
+            for k, v in losses.items():
+                out["%s_%s" % (tag, k)] = np.array(float(v))
+            (s_seq, s_lp, s_mask), (g_seq, g_lp, g_mask) = calls[0], calls[1]
+            out[tag + "_sample_seq"] = s_seq.numpy()
+            out[tag + "_sample_lp"] = s_lp.numpy()
+            out[tag + "_sample_mask"] = s_mask.numpy()
+            out[tag + "_greedy_seq"] = g_seq.numpy()
+            print(tag, "sampled:", s_seq[:3].tolist(), "greedy:", g_seq[:3].tolist())
+            print("detector", tag, {k: float(v) for k, v in losses.items()})
+    finally:
+        torch.multinomial = real_multinomial
+        d.captioner.forward = real_forward
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(2, V, seed=9)
+    caps, sentiments = [], []
+    for i in range(2):
+        c, s_ = d.sample(fc[i], att[i], sentis[i], beam_size=3)
+        caps.append(c)
+        sentiments.append(s_)
+    out["sample_captions"] = np.array(caps)
+    out["sample_sentiments"] = np.array(sentiments)
+    np.savez_compressed(os.path.join(HERE, "detector_golden.npz"), **out)
+    print("detector sample:", caps[0][0], sentiments)
+
+
 def sentcls_goldens():
     """The reference's SentenceSentimentClassifier (models/sent_senti_cls.py) on ragged synthetic captions."""
     from models.sent_senti_cls import SentenceSentimentClassifier as RefCls
@@ -266,7 +337,10 @@ if __name__ == "__main__":
         sentcls_goldens()
     elif "loader" in sys.argv:
         loader_goldens()
+    elif "detector" in sys.argv:
+        detector_goldens()
     else:
+        detector_goldens()
         sentcls_goldens()
         loader_goldens()
         decode_goldens()

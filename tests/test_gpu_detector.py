@@ -117,3 +117,76 @@ def test_detector_with_on_device_sentiment_models_and_cls_reward():
     want = torch.nn.functional.pad((pred.argmax(-1) == labels).float()[:, None] * w, (0, T - w.shape[1]))
     assert tuple(got.shape) == (B, T)
     np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def _ref_config_detector(golden):
+    """Our Detector in the configuration tests/golden/make_golden.py::detector_goldens ran the REFERENCE Detector in."""
+    from insenticap_model_b200.sent_senti_cls import SentenceSentimentClassifier
+    from insenticap_model_b200.sentiment_detector import SentimentDetector
+    Vg, Tg = 64, 12
+    cats = [str(c) for c in golden["categories"]]
+    settings = dict(syn.DEFAULT_SETTINGS, sentiment_convs_num=2, sentiment_fcs_num=2)
+    sd = SentimentDetector(cats, settings)
+    sd.load_state_dict(syn.senti_detector_state_dict(0))
+    sc = SentenceSentimentClassifier(syn.make_vocab(Vg), cats, settings)
+    sc.load_state_dict(syn.sent_cls_state_dict(Vg, int(golden["cls_seed"])))
+    torch.manual_seed(0)
+    d = Detector(syn.make_vocab(Vg), Tg, cats, {"cap_lr": 4e-4}, settings, senti_detector=sd, sent_senti_cls=sc)
+    d.captioner.load_state_dict(syn.synthetic_state_dict(Vg, 0, eos_heavy=True))
+    return d.cuda(), Vg, Tg
+
+
+def test_detector_matches_reference_detector_golden():
+    """Detector.forward(training=False) and Detector.sample against the REFERENCE Detector (models/decoder.py:52-192) with
+    the reference's own SentimentDetector / SentenceSentimentClassifier, on the same synthetic batches, same weights and
+    the same injected Gumbel noise for the sampled pass: sampled and greedy ids exact, every reported loss / reward equal."""
+    import os
+    import numpy as np
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "detector_golden.npz"))
+    d, Vg, Tg = _ref_config_detector(golden)
+    Bg = 6
+    fact, senti, scs, gts = syn.detector_batches(Bg, Vg, Tg)
+    d.set_ciderd_scorer({"train": gts})
+    d.sample_noise = syn.gumbel_noise(Tg, Bg, Vg, seed=21).cuda()
+    for tag, data, dtype in (("fact", (fact, scs), "fact"), ("senti", (senti, scs), "senti")):
+        with torch.no_grad():
+            out = d(data, dtype, training=False)
+        sample, greedy = d.last_captions
+        assert np.array_equal(sample.cpu().numpy(), golden[tag + "_sample_seq"]), tag
+        assert np.array_equal(greedy.cpu().numpy(), golden[tag + "_greedy_seq"]), tag
+        keys = [k[len(tag) + 1:] for k in golden.files if k.startswith(tag + "_") and golden[k].shape == ()]
+        assert set(keys) == set(out), (keys, sorted(out))
+        for k in keys:
+            np.testing.assert_allclose(out[k], float(golden[tag + "_" + k]), rtol=2e-3, atol=2e-5, err_msg=tag + " " + k)
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(2, Vg, seed=9)
+    for i in range(2):
+        caps, sentiments = d.sample(fc[i].cuda(), att[i].cuda(), sentis[i].cuda(), beam_size=3)
+        assert caps == [str(c) for c in golden["sample_captions"][i]]
+        assert sentiments == [str(s) for s in golden["sample_sentiments"][i]]
+
+
+def test_detector_iteration_has_one_host_sync():
+    """The RL iteration keeps ids, rewards and losses on the device: the only torch-level host synchronisation of a
+    Detector.forward call is the ONE stacked read of the loss sums after the loop (the reference does seven per iteration)."""
+    import os
+    import warnings
+    import numpy as np
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "detector_golden.npz"))
+    d, Vg, Tg = _ref_config_detector(golden)
+    fact, senti, scs, gts = syn.detector_batches(6, Vg, Tg)
+    d.set_ciderd_scorer({"train": gts})
+    fact = [tuple(x.cuda() if torch.is_tensor(x) else x for x in fact[0][:3]) + ((fact[0][3][0].cuda(), fact[0][3][1]),)
+            + tuple(x.cuda() if torch.is_tensor(x) else x for x in fact[0][4:])] * 3  # three iterations, inputs resident
+    with torch.no_grad():
+        d((fact, scs), "fact", training=False)  # warm-up: packs weights, sizes workspaces
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("warn")
+    try:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            with torch.no_grad():
+                d((fact, scs), "fact", training=False)
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    syncs = [str(x.message) for x in w if "synchroniz" in str(x.message).lower()]
+    assert len(syncs) <= 1, syncs

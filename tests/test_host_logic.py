@@ -84,3 +84,29 @@ def test_reward_host_packing():
     mk = torch.tensor([[1.0, 1.0], [1.0, 0.0]])
     rw = torch.tensor([[0.5, 0.5], [2.0, 2.0]])
     assert abs(float(crit(lp, mk, rw)) - (0.5 + 1.0 + 6.0) / 3) < 1e-6
+
+
+def test_fused_adam_state_dict_and_param_groups_roundtrip():
+    """FusedClampAdam offers the optimizer surface the reference scripts use: param_groups[...]['lr'] writes through
+    (train_xe.py:130-133) and state_dict()/load_state_dict() carry moments, step count and hyper-parameters (train_xe.py:53, :245)."""
+    import torch
+    from insenticap_model_b200 import train as TR
+    lin = torch.nn.Linear(4, 3)
+    lin._packed_key = None
+    opt = TR.FusedClampAdam(lin, lr=1e-3, grad_clip=0.1)
+    for g in opt.param_groups:
+        g["lr"] = 5e-4
+    assert opt.lr == 5e-4 and opt.param_groups[0]["lr"] == 5e-4 and len(opt.param_groups[0]["params"]) == 2
+    opt.exp_avg.fill_(0.25)
+    opt.exp_avg_sq.fill_(0.5)
+    opt.steps = 7
+    sd = opt.state_dict()
+    lin2 = torch.nn.Linear(4, 3)
+    lin2._packed_key = None
+    opt2 = TR.FusedClampAdam(lin2, lr=1.0)
+    opt2.load_state_dict(sd)
+    assert opt2.steps == 7 and opt2.lr == 5e-4 and opt2.grad_clip == 0.1
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    import pytest
+    with pytest.raises(ValueError):
+        TR.FusedClampAdam(torch.nn.Linear(2, 2), lr=1.0).load_state_dict(sd)
