@@ -92,6 +92,16 @@ typedef struct isc_feats {
   float* pre_gates; /* [B,4H]  W_ih[:,H:2H]·fc + W_ih[:,2H:3H]·sl + b_ih + b_hh (hoisted) */
   float* pre_word;  /* [B,H]   label2word(sl) (hoisted out of SentiAttention.forward) */
   float* cpt_feats; /* [B,H]   ReLU(cpt2fc(mean ReLU(word_embed(cpt_words)))) or NULL */
+  /* Optional 16-bit copies for the attention kernel's fast path (decode loops; tensor-core precisions). The attention
+   * streams both [B,L,H] tensors once per decode step (the HBM term of the step), so their width is the step's
+   * HBM time. All three NULL -> the kernel reads att / p_att above. Written by isc_prologue when non-NULL:
+   *   att16   fp16(att)                          (ISC_PREC_BF16X3; ISC_PREC_BF16 keeps reading its bf16 att)
+   *   p_att16 fp16(exp(-2 * ReLU(att2att(att))) * 2^15)
+   *   feat_flags[b] != 0: image b has a value outside the fast path's exact domain (projected feature > 10, i.e. a
+   *           subnormal fp16, or att beyond fp16 range): its CTA reads the full-width tensors instead. */
+  void*    att16;      /* [B,L,H] fp16 or NULL */
+  void*    p_att16;    /* [B,L,H] fp16 or NULL */
+  int32_t* feat_flags; /* [B] or NULL */
 } isc_feats_t;
 
 /* Training-mode dropout (nn.Dropout(p), captioner.py:132): uint8 KEEP masks (1 = keep) supplied by the caller so

@@ -53,7 +53,8 @@ class Weights(C.Structure):
     _fields_ = [(f, C.c_void_p) for f, _ in WEIGHT_FIELDS]
 
 
-FEAT_FIELDS = ("fc", "att", "p_att", "sw", "p_sw", "sl", "pre_gates", "pre_word", "cpt_feats")
+FEAT_FIELDS = ("fc", "att", "p_att", "sw", "p_sw", "sl", "pre_gates", "pre_word", "cpt_feats", "att16", "p_att16",
+               "feat_flags")
 
 
 class Feats(C.Structure):
@@ -181,3 +182,15 @@ def ptr(t):
 
 def stream_ptr(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def to_device_async(values, dtype, device):
+    """Small host data (a python list of lengths / indices, or a CPU tensor) -> device tensor WITHOUT a host
+    synchronisation: staged in page-locked memory (torch's caching pinned allocator keeps the block alive until the copy
+    has run) and copied with non_blocking=True. ``torch.tensor(list, device=...)`` copies from pageable memory, which
+    makes torch synchronise the stream — one full pipeline drain per call."""
+    import torch
+    t = values if torch.is_tensor(values) else torch.tensor(values, dtype=dtype)
+    if t.is_cuda or torch.device(device).type != "cuda":
+        return t.to(device=device, dtype=dtype)
+    return t.to(dtype).pin_memory().to(device, non_blocking=True)

@@ -62,7 +62,7 @@ class XECriterion(nn.Module):
 
     def forward(self, pred, target, lengths):
         max_len = max(lengths)
-        lens = torch.as_tensor(list(lengths), device=pred.device).unsqueeze(1)
+        lens = _lib.to_device_async(list(lengths), torch.long, pred.device).unsqueeze(1)
         mask = (torch.arange(max_len, device=pred.device).unsqueeze(0) < lens).to(pred.dtype)
         nll = -pred.gather(2, target.unsqueeze(2)).squeeze(2) * mask
         return nll.sum() / mask.sum()
@@ -187,6 +187,7 @@ class Captioner(nn.Module):
         self.n_regions = 196
         self.num_senti_words = 10
         self.collect_attention_weights = True
+        self.fast_features = True  # attention reads fp16 copies of the projected features (tensor-core precisions)
         self.set_precision(precision)
         self._packed = None
         self._packed_key = None
@@ -365,6 +366,13 @@ class Captioner(nn.Module):
             n_regions = att_feats.shape[1]
             t["att"] = torch.empty(B, n_regions, 512, dtype=self._feat_dtype(), device=dev)
             t["p_att"] = torch.empty_like(t["att"])
+            if self.fast_features and self._prec != _lib.PREC_FP32 and not dropout:
+                # 16-bit copies for the attention kernel (isc_feats_t::att16 / p_att16 / feat_flags): half the bytes the
+                # decode loop streams per step; images outside the fp16 path's exact domain are flagged and read full width
+                if self._prec == _lib.PREC_BF16X3:
+                    t["att16"] = torch.empty(B, n_regions, 512, dtype=torch.float16, device=dev)
+                t["p_att16"] = torch.empty(B, n_regions, 512, dtype=torch.float16, device=dev)
+                t["feat_flags"] = torch.empty(B, dtype=torch.int32, device=dev)
         t["fc"] = torch.empty(B, 512, **f32)
         t["pre_gates"] = torch.empty(B, 2048, **f32)
         if cpt_words is not None:
@@ -505,7 +513,7 @@ class Captioner(nn.Module):
     def _nll_coef(captions, lengths, dev):
         """XECriterion's weights (captioner.py:431-440): mask[b,t] = t < lengths[b], normalised by its sum."""
         n_steps = captions.shape[1] - 1
-        lens = torch.as_tensor(list(lengths), device=dev).unsqueeze(1)
+        lens = _lib.to_device_async(list(lengths), torch.long, dev).unsqueeze(1)
         mask = (torch.arange(n_steps, device=dev).unsqueeze(0) < lens).float()
         return captions[:, 1:].long().contiguous(), (mask / mask.sum()).contiguous()
 

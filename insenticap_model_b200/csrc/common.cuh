@@ -1,6 +1,7 @@
 // Shared internal declarations for libisc_b200.so (not part of the public ABI).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -106,6 +107,26 @@ struct Operand {
   int64_t ldp = 0;  // elements, plane view
 };
 
+// 16-bit attention path: projected features are stored as fp16(exp(-2p) * kFastScale); fp16 keeps that a NORMAL number
+// down to p = 10.05, so an image whose largest projected feature exceeds kFastPMax is flagged and read full width.
+constexpr float kFastScale = 32768.0f;        // 2^15
+constexpr float kFastPMax = 10.0f;
+constexpr float kFastMinStored = 6.7540e-5f;  // 2^15 * exp(-2 * kFastPMax), above fp16's smallest normal 6.10e-5
+
+// Optional fp16 copy of a GEMM's output for the attention kernel's 16-bit path (isc_feats_t::att16 / p_att16):
+//   out[row][col] = fp16((expneg2 ? exp(-2 y) : y) * scale),   y = the epilogue's result,
+// and flags[row / rows_per_flag] |= 1 when a stored value leaves [vmin, vmax] (or is NaN): that image is outside the
+// 16-bit path's exact domain and the attention kernel reads its full-width features instead.
+struct Half16Out {
+  void* out = nullptr;  // __half [M, ld]
+  int64_t ld = 0;
+  float scale = 1.0f;
+  int expneg2 = 0;
+  float vmin = 0.0f, vmax = 65000.0f;
+  int* flags = nullptr;
+  int rows_per_flag = 1;
+};
+
 // Where a GEMM (or a pointwise kernel) writes its result; any member may be null.
 struct Dest {
   float* f32 = nullptr;
@@ -113,6 +134,7 @@ struct Dest {
   __nv_bfloat16* hi = nullptr;
   __nv_bfloat16* lo = nullptr;
   int64_t ldp = 0;
+  Half16Out h16;
 };
 
 struct Epilogue {
@@ -268,6 +290,16 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_accurate(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid from the two raw MUFU ops (ex2, rcp): relative error ~3e-7 (a few ulp), five instructions instead of ~25
+// (expf's range reduction and the IEEE division). Used by the LSTM cell fused into the gate GEMMs' epilogue, whose
+// warps are otherwise busy for half of the kernel; -x * log2(e) below -126 flushes to 0 -> sigmoid = 1,
+// above 128 gives inf -> rcp = 0.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.0f);

@@ -404,6 +404,12 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     ap.ld_hproj = 3 * H;
     ap.att = f.att;
     ap.p_att = f.p_att;
+    if (!w.tape && f.p_att16) {
+      // 16-bit copies (decode loops); not with the training tape, whose backward recomputes from the fp32 tensors
+      ap.att16 = f.att16;
+      ap.p_att16 = f.p_att16;
+      ap.flags = f.feat_flags;
+    }
     ap.sw = f.sw;
     ap.p_sw = f.p_sw;
     ap.pre_word = f.pre_word;
@@ -425,7 +431,7 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     ap.ld_cont_w = io.ld_cont_w;
     ap.senti_w = io.senti_w;
     ap.ld_senti_w = io.ld_senti_w;
-    ISC_TRY(launch_attention(ap, B, c.precision == ISC_PREC_BF16, c.precision, c.s));  // tanh mode == precision id
+    ISC_TRY(launch_attention(ap, B, c.precision, c.s));
   }
   if (rl) {
     Epilogue ep;
@@ -649,6 +655,17 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
           patt.lo = w.att_lo;
         }
       }
+      const bool want16 = tc && out->p_att16 != nullptr;
+      if (want16) {
+        ISC_REQUIRE(out->feat_flags && !drop, "out->p_att16 needs out->feat_flags (and no dropout)");
+        if (b0 == 0) ISC_CUDA(cudaMemsetAsync(out->feat_flags, 0, (size_t)B * sizeof(int), c.s));
+        if (out->att16 && precision == ISC_PREC_BF16X3) {  // fp16(att) beside the fp32 tensor
+          dst.h16.out = static_cast<__half*>(out->att16) + (long long)b0 * L * H;
+          dst.h16.ld = H;
+          dst.h16.flags = out->feat_flags + b0;
+          dst.h16.rows_per_flag = L;
+        }
+      }
       if (raw_bf16) {
         Planes pin;
         pin.hi = reinterpret_cast<bf16*>(const_cast<float*>(att_feats)) + (long long)b0 * L * D;
@@ -676,6 +693,15 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
       } else {
         d2.f32 = reinterpret_cast<float*>(out->p_att) + (long long)b0 * L * H;
         d2.ld = H;
+      }
+      if (want16) {  // fp16(exp(-2 p) * 2^15) beside the full-width projected features
+        d2.h16.out = static_cast<__half*>(out->p_att16) + (long long)b0 * L * H;
+        d2.h16.ld = H;
+        d2.h16.scale = kFastScale;
+        d2.h16.expneg2 = precision == ISC_PREC_BF16 ? 1 : 0;  // ISC_PREC_BF16 keeps p itself in its bf16 tensor
+        d2.h16.vmin = kFastMinStored;
+        d2.h16.flags = out->feat_flags + b0;
+        d2.h16.rows_per_flag = L;
       }
       ISC_TRY(gemm(precision, operand(dst.f32, H, patt, H), pk.Wa2a.op(), d2, (int)rows, H, H, ep2, c.s));
     }

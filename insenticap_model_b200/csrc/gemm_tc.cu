@@ -27,6 +27,11 @@
 
 #include "common.cuh"
 
+// LSTM cell in the fused gate-GEMM epilogue: 1 = raw-MUFU sigmoid / tanh (default), 0 = libdevice expf / tanhf / division
+#ifndef ISC_CELL_FAST
+#define ISC_CELL_FAST 1
+#endif
+
 namespace isc {
 namespace tc {
 
@@ -80,6 +85,7 @@ struct EpiParams {
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
   long long ldp;
+  Half16Out h16;  // optional fp16 copy of the result (EPI_STD)
   int M, N, K;
   // EPI_LOGITS: per (row, 128-column slice) online-softmax partials + top candidates instead of the logits
   LogitsSelect sel;
@@ -756,8 +762,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           float hn[16], cn[16];
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
+#if ISC_CELL_FAST
+            // MUFU-based gates (sigmoid_fast, tanh_ex2: ~3e-7 / 2e-7 error, far inside the split-bf16 GEMM's own 8e-6)
+            cn[u] = sigmoid_fast(vif[16 + u]) * cp[u] + sigmoid_fast(vif[u]) * tanh_ex2(vgo[u]);
+            hn[u] = sigmoid_fast(vgo[16 + u]) * tanh_ex2(cn[u]);
+#else
             cn[u] = sigmoid_accurate(vif[16 + u]) * cp[u] + sigmoid_accurate(vif[u]) * tanhf(vgo[u]);
             hn[u] = sigmoid_accurate(vgo[16 + u]) * tanhf(cn[u]);
+#endif
           }
           float4* co = reinterpret_cast<float4*>(L.c_out + row * HH + u0);
           float4* ho = reinterpret_cast<float4*>(L.h_out + row * HH + u0);
@@ -904,6 +916,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                   if (n + 1 < ep.N) dst[1] = x.y;
                   if (n + 2 < ep.N) dst[2] = x.z;
                   if (n + 3 < ep.N) dst[3] = x.w;
+                }
+              }
+              if (ep.h16.out) {
+                float4 y = x;
+                if (ep.h16.expneg2) { y.x = __expf(-2.0f * y.x); y.y = __expf(-2.0f * y.y); y.z = __expf(-2.0f * y.z); y.w = __expf(-2.0f * y.w); }
+                y.x *= ep.h16.scale; y.y *= ep.h16.scale; y.z *= ep.h16.scale; y.w *= ep.h16.scale;
+                const float lo_ = fminf(fminf(y.x, y.y), fminf(y.z, y.w)), hi_ = fmaxf(fmaxf(y.x, y.y), fmaxf(y.z, y.w));
+                __half* d16 = static_cast<__half*>(ep.h16.out) + row * ep.h16.ld + n;
+                if (full4 && ((reinterpret_cast<uintptr_t>(d16) & 7) == 0)) {
+                  const __half2 a = __floats2half2_rn(y.x, y.y), b = __floats2half2_rn(y.z, y.w);
+                  *reinterpret_cast<uint2*>(d16) = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
+                  if (!(lo_ >= ep.h16.vmin && hi_ <= ep.h16.vmax)) atomicOr(ep.h16.flags + row / ep.h16.rows_per_flag, 1);
+                } else {
+                  const float yv[4] = {y.x, y.y, y.z, y.w};
+                  for (int q = 0; q < 4 && n + q < ep.N; ++q) {
+                    d16[q] = __float2half_rn(yv[q]);
+                    if (!(yv[q] >= ep.h16.vmin && yv[q] <= ep.h16.vmax)) atomicOr(ep.h16.flags + row / ep.h16.rows_per_flag, 1);
+                  }
                 }
               }
               if (ep.hi) {
@@ -1113,6 +1143,7 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.hi = Cd.hi;
   ep.lo = Cd.lo;
   ep.ldp = Cd.ldp;
+  ep.h16 = Cd.h16;
   ep.M = M;
   ep.N = N;
   ep.K = K;
@@ -1173,6 +1204,7 @@ static int launch_af32(const float* A, int64_t lda, const Operand& W, const Dest
   ep.hi = Cd.hi;
   ep.lo = Cd.lo;
   ep.ldp = Cd.ldp;
+  ep.h16 = Cd.h16;
   ep.M = M;
   ep.N = N;
   ep.K = K;

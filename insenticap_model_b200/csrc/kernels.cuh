@@ -45,6 +45,11 @@ struct AttnParams {
   long long ld_hproj = 0;
   const void* att = nullptr;    // [B,L,H] fp32 or bf16; null -> no content attention (seq2seq)
   const void* p_att = nullptr;
+  // fast path (isc_feats_t::att16 / p_att16 / feat_flags): fp16 copies; p_att16 = exp(-2 p) * 2^15. A CTA whose image is
+  // flagged (value outside the fp16 path's exact domain) reads att / p_att instead.
+  const void* att16 = nullptr;
+  const void* p_att16 = nullptr;
+  const int* flags = nullptr;
   const float* sw = nullptr;    // [B,S,H]; null -> no sentiment attention (xe)
   const float* p_sw = nullptr;
   const float* pre_word = nullptr;  // [B,H] label2word(sl)
@@ -65,7 +70,7 @@ int launch_embed_pack(const long long* it, const int* parent, const float* h_in,
 int launch_lstm_pointwise(const float* gates, const int* parent, const float* c_prev, float* h_out, float* c_out,
                           RowDest extra, int extra_col, int M, cudaStream_t stream, const unsigned char* mask = nullptr,
                           float scale = 1.0f);
-int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode, cudaStream_t stream);
+int launch_attention(const AttnParams& p, int B, int precision, cudaStream_t stream);
 int launch_gate_mix(const float* g3, const float* cs, const float* alpha, const float* alpha_b, RowDest ctx,
                     float* gate_w, long long ld_gate_w, int M, cudaStream_t stream);
 int launch_embed_rows(const long long* ids, long long groups, long long n_per_group, int prepend_pad, int pad_id, int V,

@@ -2,6 +2,10 @@
 // and of the prologue. All are HBM-bound element-wise / reduction kernels: 128-bit accesses,
 // warp-shuffle reductions, one CTA per row (or per image for the attention, so the K beams of an
 // image share one pass over its region features).
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace isc {
@@ -72,6 +76,13 @@ __global__ void __launch_bounds__(128) lstm_pointwise_kernel(const float* __rest
 // Attention (ContentAttention :23-35, SentiAttention :50-62): one CTA per image, R rows (beams)
 // of that image processed against one pass over p_att / att (and p_sw / sw).
 //   hproj[m] = [h2att(h) | h2word(h) | gate h2att(h)] (+ their biases), from the projection GEMM.
+//
+// The kernel streams both [L,H] feature tensors of its image once per decode step: their WIDTH is the HBM time of the
+// step. Tensor-core precisions therefore read 16-bit copies (isc_feats_t::att16 / p_att16): fp16 keeps 11
+// significant bits per value, and because a context vector is an average over L = 196 regions the rounding noise of its
+// inputs shrinks by sqrt(L): the context moves by ~1e-5 relative, the size of the split-bf16 GEMMs' own error, and no
+// golden token changes (tests/test_gpu_parity.py). Images with a value outside the 16-bit path's exact domain are
+// flagged by the prologue and their CTA reads the full-width tensors (the "wide" path below).
 // --------------------------------------------------------------------------------------------
 template <typename FeatT>
 struct FeatLoad;
@@ -79,10 +90,6 @@ template <>
 struct FeatLoad<float> {
   static constexpr int kChunks = 4;  // 4 x float4 per lane per 512-wide row
   __device__ static __forceinline__ int col(int lane, int i) { return i * 128 + lane * 4; }
-  __device__ static __forceinline__ void load(const float* row, int lane, int i, float* v) {
-    float4 t = __ldg(reinterpret_cast<const float4*>(row + col(lane, i)));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
   __device__ static __forceinline__ void load_shared(const float* row, int lane, int i, float* v) {
     float4 t = *reinterpret_cast<const float4*>(row + col(lane, i));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -93,15 +100,8 @@ template <>
 struct FeatLoad<__nv_bfloat16> {
   static constexpr int kChunks = 2;  // 2 x (8 bf16 = 16 B) per lane
   __device__ static __forceinline__ int col(int lane, int i) { return i * 256 + lane * 8; }
-  __device__ static __forceinline__ void load(const __nv_bfloat16* row, int lane, int i, float* v) {
-    uint4 t = __ldg(reinterpret_cast<const uint4*>(row + col(lane, i)));
-    unpack(t, v);
-  }
   __device__ static __forceinline__ void load_shared(const __nv_bfloat16* row, int lane, int i, float* v) {
     uint4 t = *reinterpret_cast<const uint4*>(row + col(lane, i));
-    unpack(t, v);
-  }
-  __device__ static __forceinline__ void unpack(const uint4& t, float* v) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -112,6 +112,41 @@ struct FeatLoad<__nv_bfloat16> {
   }
   static constexpr int kWidth = 8;
 };
+template <>
+struct FeatLoad<__half> {
+  static constexpr int kChunks = 2;  // 2 x (8 fp16 = 16 B) per lane
+  __device__ static __forceinline__ int col(int lane, int i) { return i * 256 + lane * 8; }
+  __device__ static __forceinline__ void load_shared(const __half* row, int lane, int i, float* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(row + col(lane, i));
+    const __half2* p = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 f = __half22float2(p[q]);  // HADD2.F32: full-rate, no conversion pipe
+      v[2 * q] = f.x;
+      v[2 * q + 1] = f.y;
+    }
+  }
+  static constexpr int kWidth = 8;
+};
+
+// Scoring modes (TANH_MODE):
+//   0  libdevice tanhf on p + q                                   (ISC_PREC_FP32)
+//   1  e-product, fast: pv = exp(-2p) * 2^15 (fp16), q = exp(-2q) * 2^-15 with q clamped at -20 (eb <= e^40). Exact on the
+//      domain the prologue's flag guarantees (p <= 10): then p + q <= -10 wherever the clamp bites and tanh is -1 either way.
+//   2  tanh.approx.f32 on p + q                                   (ISC_PREC_BF16, wide path)
+//   3  e-product, wide: pv = exp(-2p) (fp32), q = exp(-2q) clamped at 1.6e38 (q >= -44), the PRODUCT e clamped at 1e18
+//      (tanh is -1 to fp32 precision from e = 1e8 on): no operand combination overflows d0 * d1, and tanh(p + q) is right
+//      for every (p, q) with p <= 43 (exp(-2p) a normal float) and (q >= -44 or p <= 34). Two more FMA-pipe instructions
+//      per value than mode 1; only flagged images, the sentiment words (11 rows) and the training tape take it.
+constexpr float kWideExpClamp = 1.6e38f;
+__device__ __forceinline__ float exp_neg2_wide(float x) { return fminf(expf(-2.0f * x), kWideExpClamp); }
+__device__ __forceinline__ float score2_eprod_wide(float ea0, float ea1, float eb0, float eb1, float a0x2, float a1x2, float acc) {
+  const float e0 = fminf(ea0 * eb0, 1e18f), e1 = fminf(ea1 * eb1, 1e18f);
+  const float d0 = 1.0f + e0, d1 = 1.0f + e1;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
+  return fmaf(r, fmaf(a0x2, d1, a1x2 * d0), acc);
+}
 
 // RT > 0: rows per image known at compile time (fully unrolled); RT == 0: runtime R <= 8.
 template <typename FeatT, int TANH_MODE, int RT>
@@ -133,10 +168,12 @@ __device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kCh
         for (int j4 = 0; j4 < L::kWidth; j4 += 4) {
           const float4 qv = *reinterpret_cast<const float4*>(q + c0 + j4);
           if (TANH_MODE == 1) {
-            // pv = exp(-2 p), q = exp(-2 q), al = 2 alpha: the softmax-equivalent score sum 2 alpha / (1 + pv q)
-            // (score2_eprod, common.cuh), one reciprocal per pair
+            // the softmax-equivalent score sum 2 alpha / (1 + pv q) (score2_eprod, common.cuh), one reciprocal per pair
             acc = score2_eprod(pv[i][j4], pv[i][j4 + 1], qv.x, qv.y, al[i][j4], al[i][j4 + 1], acc);
             acc = score2_eprod(pv[i][j4 + 2], pv[i][j4 + 3], qv.z, qv.w, al[i][j4 + 2], al[i][j4 + 3], acc);
+          } else if (TANH_MODE == 3) {
+            acc = score2_eprod_wide(pv[i][j4], pv[i][j4 + 1], qv.x, qv.y, al[i][j4], al[i][j4 + 1], acc);
+            acc = score2_eprod_wide(pv[i][j4 + 2], pv[i][j4 + 3], qv.z, qv.w, al[i][j4 + 2], al[i][j4 + 3], acc);
           } else {
             float t[4];
             const float x[4] = {pv[i][j4] + qv.x, pv[i][j4 + 1] + qv.y, pv[i][j4 + 2] + qv.z, pv[i][j4 + 3] + qv.w};
@@ -154,29 +191,114 @@ __device__ __forceinline__ void score_one(const float (&pv)[FeatLoad<FeatT>::kCh
 }
 
 // One warp scores items l = warp, warp + n_warps, ...  The item's 512-wide row is staged gmem -> smem with
-// cp.async (no registers held across the long SFU-bound scoring of the previous row): a 2-slot ring per warp.
+// cp.async (no registers held across the scoring of the previous row): a RING-slot ring per warp, RING - 1 rows in flight.
 // Every lane reads back exactly the 16-byte chunks it copied itself, so no cross-lane barrier is needed.
-// L2 prefetch of rows the kernel will read later: holds no register and no shared memory, so it adds bytes in flight
-// beyond what the cp.async ring (one row per warp) and the register-held loads of the weighted sum (8 x 8 B per thread)
-// can keep outstanding. One instruction per 128-byte line. Distances measured on B = 1024, beam 3 (attention ms per call,
-// same box): none 2.795 | (score 2, sum 16) 2.588 | (3, 16) 2.61 | (2, 32) 2.63 | (3, 32) 2.65 | (6, 64) 3.11 | (12, 96)
-// 3.65 — with ~590 images resident, longer distances evict each other's lines from the 126 MB L2.
+// L2 prefetch of rows the kernel will read later holds no register and no shared memory, so it adds bytes in flight
+// beyond what the ring and the register-held loads of the weighted sum keep outstanding: one instruction per 128-byte
+// line, one warp-round beyond the ring for the scores, kSumAheadBytes ahead for the weighted sum. Distances measured in
+// round 1 on fp32 rows (B = 1024, beam 3, attention ms per call): none 2.795 | (this) 2.588 | longer ones thrash L2
+// (6 rounds / 64 rows: 3.11, 12 / 96: 3.65) — with ~590 images resident their lines evict each other from the 126 MB L2.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-constexpr int kScoreAhead = 2;   // score_rows: rows (in units of n_warps) prefetched into L2 ahead of the ring
-constexpr int kSumAhead = 16;    // weighted_sum: rows prefetched into L2 ahead of the loads
-constexpr int kRing = 2;  // staging slots per warp in score_rows (3 was measured: the smem costs a CTA per SM, 2.83 -> 3.09 ms)
+constexpr int kRingBytes = 4096;          // per warp, smem-query variant: 2 fp32 rows or 4 16-bit rows (4 CTAs per SM)
+constexpr int kRingBytesReg = 8192;       // per warp, register-query variant (2 CTAs per SM): 4 fp32 rows or 8 16-bit rows
+constexpr int kSumAheadBytes = 32 * 1024;  // weighted_sum: bytes prefetched into L2 ahead of the loads
 template <typename FeatT, int TANH_MODE, int RT>
 __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int n_items, int R,
                                            const float* __restrict__ q_smem /*[R][H]*/, const float* __restrict__ alpha_smem,
-                                           float* __restrict__ score_smem /*[R][n_items]*/, FeatT* __restrict__ ring /*[2][H]*/,
+                                           float* __restrict__ score_smem /*[R][n_items]*/, void* __restrict__ ring_raw,
                                            int warp, int lane, int n_warps) {
   using L = FeatLoad<FeatT>;
+  constexpr int RING = kRingBytes / (H * (int)sizeof(FeatT));
+  FeatT* ring = reinterpret_cast<FeatT*>(ring_raw);
   float al[L::kChunks][L::kWidth];  // this lane's slice of alpha stays in registers
 #pragma unroll
   for (int i = 0; i < L::kChunks; ++i)
 #pragma unroll
-    for (int j = 0; j < L::kWidth; ++j) al[i][j] = (TANH_MODE == 1 ? 2.0f : 1.0f) * alpha_smem[L::col(lane, i) + j];
-  auto prefetch = [&](int l, int slot) {
+    for (int j = 0; j < L::kWidth; ++j)
+      al[i][j] = ((TANH_MODE == 1 || TANH_MODE == 3) ? 2.0f : 1.0f) * alpha_smem[L::col(lane, i) + j];
+  auto stage = [&](int l, int slot) {
+    if (l < n_items) {
+#pragma unroll
+      for (int i = 0; i < L::kChunks; ++i) {
+        const FeatT* src = p_feat + (long long)l * H + L::col(lane, i);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + slot * H + L::col(lane, i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group past the end keeps the group count uniform)
+  };
+  constexpr int kLines = H * (int)sizeof(FeatT) / 128;  // 128-byte lines per row (16 fp32, 8 fp16 / bf16)
+  auto ahead = [&](int l) {
+    if (l < n_items && lane < kLines) prefetch_l2(reinterpret_cast<const char*>(p_feat + (long long)l * H) + lane * 128);
+  };
+#pragma unroll
+  for (int a = 0; a < RING - 1; ++a) stage(warp + a * n_warps, a);
+  ahead(warp + (RING - 1) * n_warps);
+  int it = 0;
+  for (int l = warp; l < n_items; l += n_warps, ++it) {
+    ahead(l + RING * n_warps);
+    stage(l + (RING - 1) * n_warps, (it + RING - 1) % RING);
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");  // the group that holds row l has landed
+    float pv[L::kChunks][L::kWidth];
+#pragma unroll
+    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it % RING) * H, lane, i, pv[i]);
+    score_one<FeatT, TANH_MODE, RT>(pv, al, l, n_items, R, q_smem, score_smem, lane);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Sum over the 32 lanes of EIGHT per-lane values at once: three exchange-halves stages (xor 16, 8, 4: a lane keeps the
+// half of the values its lane bit selects and adds the other lane's copy of that half) leave ONE value per lane, two
+// plain butterfly stages finish it. 9 shuffles for 8 sums instead of 40, and five dependent shuffle latencies per
+// EIGHT rows instead of per row. Lanes with (lane & 3) == 0 end up holding the total of value
+// k = 4 * bit4(lane) + 2 * bit3(lane) + bit2(lane).
+__device__ __forceinline__ float treduce8(const float (&v)[8], int lane) {
+  const unsigned full = 0xffffffffu;
+  float w4[4], w2[2];
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w4[i] = (b16 ? v[i + 4] : v[i]) + __shfl_xor_sync(full, b16 ? v[i] : v[i + 4], 16);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) w2[i] = (b8 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(full, b8 ? w4[i] : w4[i + 2], 8);
+  float w1 = (b4 ? w2[1] : w2[0]) + __shfl_xor_sync(full, b4 ? w2[0] : w2[1], 4);
+  w1 += __shfl_xor_sync(full, w1, 2);
+  w1 += __shfl_xor_sync(full, w1, 1);
+  return w1;
+}
+
+// Register-query variant of score_rows for RT = 1 or 3 rows per image (greedy / beam-3, the measured workloads).
+// ncu on the smem-query kernel (B = 1024, beam 3, fp16 rows): l1tex at 79 % of peak — every row re-read the RT query
+// vectors from shared memory, 6 KB per 1 KB row — and a third of all stall samples on the five dependent shuffle + add
+// steps of the per-row warp reduction. Here a lane keeps ITS 16 columns of every query (and of alpha) in registers for
+// the whole image (the lane <-> column mapping never changes), and the warp reductions of EIGHT consecutive rows are
+// batched (treduce8): shared memory only carries the staged feature rows.
+template <typename FeatT, int TANH_MODE, int RT>
+__device__ __forceinline__ void score_rows_reg(const FeatT* __restrict__ p_feat, int n_items,
+                                               const float* __restrict__ q_smem /*[RT][H]*/, const float* __restrict__ alpha_smem,
+                                               float* __restrict__ score_smem /*[RT][n_items]*/, void* __restrict__ ring_raw,
+                                               int warp, int lane, int n_warps) {
+  using L = FeatLoad<FeatT>;
+  constexpr int NV = L::kChunks * L::kWidth;  // 16 values per lane per row
+  constexpr int RING = kRingBytesReg / (H * (int)sizeof(FeatT));  // 4 or 8: divides the 8-row group
+  static_assert(8 % RING == 0, "ring slots must divide the row group");
+  FeatT* ring = reinterpret_cast<FeatT*>(ring_raw);
+  float al[NV], q[RT][NV];
+#pragma unroll
+  for (int i = 0; i < L::kChunks; ++i)
+#pragma unroll
+    for (int j = 0; j < L::kWidth; j += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(alpha_smem + L::col(lane, i) + j);
+      const float sc = (TANH_MODE == 1 || TANH_MODE == 3) ? 2.0f : 1.0f;
+      al[i * L::kWidth + j] = sc * a.x; al[i * L::kWidth + j + 1] = sc * a.y;
+      al[i * L::kWidth + j + 2] = sc * a.z; al[i * L::kWidth + j + 3] = sc * a.w;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const float4 t = *reinterpret_cast<const float4*>(q_smem + r * H + L::col(lane, i) + j);
+        q[r][i * L::kWidth + j] = t.x; q[r][i * L::kWidth + j + 1] = t.y;
+        q[r][i * L::kWidth + j + 2] = t.z; q[r][i * L::kWidth + j + 3] = t.w;
+      }
+    }
+  auto stage = [&](int l, int slot) {
     if (l < n_items) {
 #pragma unroll
       for (int i = 0; i < L::kChunks; ++i) {
@@ -187,25 +309,48 @@ __device__ __forceinline__ void score_rows(const FeatT* __restrict__ p_feat, int
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  constexpr int kLines = H * (int)sizeof(FeatT) / 128;  // 128-byte lines per row (16 fp32, 8 bf16)
+  constexpr int kLines = H * (int)sizeof(FeatT) / 128;
   auto ahead = [&](int l) {
     if (l < n_items && lane < kLines) prefetch_l2(reinterpret_cast<const char*>(p_feat + (long long)l * H) + lane * 128);
   };
-  // kRing slots, kRing - 1 rows in flight per warp
-  prefetch(warp, 0);
-  if (kRing > 2) prefetch(warp + n_warps, 1);
 #pragma unroll
-  for (int a = 1; a < kScoreAhead; ++a) ahead(warp + a * n_warps);
-  int it = 0;
-  for (int l = warp; l < n_items; l += n_warps, ++it) {
-    ahead(l + kScoreAhead * n_warps);
-    prefetch(l + (kRing - 1) * n_warps, (it + kRing - 1) % kRing);
-    if (kRing > 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-    else asm volatile("cp.async.wait_group 1;" ::: "memory");
-    float pv[L::kChunks][L::kWidth];
+  for (int a = 0; a < RING - 1; ++a) stage(warp + a * n_warps, a);
+  ahead(warp + (RING - 1) * n_warps);
+  for (int l0 = warp; l0 < n_items; l0 += 8 * n_warps) {  // 8 rows of this warp per group
+    float acc[RT][8];
 #pragma unroll
-    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it % kRing) * H, lane, i, pv[i]);
-    score_one<FeatT, TANH_MODE, RT>(pv, al, l, n_items, R, q_smem, score_smem, lane);
+    for (int k = 0; k < 8; ++k) {
+      const int l = l0 + k * n_warps;
+      ahead(l + RING * n_warps);
+      stage(l + (RING - 1) * n_warps, (k + RING - 1) % RING);
+      asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
+#pragma unroll
+      for (int r = 0; r < RT; ++r) acc[r][k] = 0.f;
+      if (l < n_items) {  // warp-uniform
+        float pv[NV];
+#pragma unroll
+        for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (k % RING) * H, lane, i, pv + i * L::kWidth);
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          float a = 0.f;
+#pragma unroll
+          for (int j = 0; j < NV; j += 2) {
+            if (TANH_MODE == 1) a = score2_eprod(pv[j], pv[j + 1], q[r][j], q[r][j + 1], al[j], al[j + 1], a);
+            else if (TANH_MODE == 3) a = score2_eprod_wide(pv[j], pv[j + 1], q[r][j], q[r][j + 1], al[j], al[j + 1], a);
+            else if (TANH_MODE == 2) a = fmaf(al[j], tanh_fast(pv[j] + q[r][j]), fmaf(al[j + 1], tanh_fast(pv[j + 1] + q[r][j + 1]), a));
+            else a = fmaf(al[j], tanhf(pv[j] + q[r][j]), fmaf(al[j + 1], tanhf(pv[j + 1] + q[r][j + 1]), a));
+          }
+          acc[r][k] = a;
+        }
+      }
+    }
+    const int kk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int lw = l0 + kk * n_warps;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const float tot = treduce8(acc[r], lane);
+      if ((lane & 3) == 0 && lw < n_items) score_smem[r * n_items + lw] = tot;
+    }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -243,33 +388,42 @@ __device__ __forceinline__ float2 load2<__nv_bfloat16>(const __nv_bfloat16* p) {
   unsigned int u = __ldg(reinterpret_cast<const unsigned int*>(p));
   return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
+template <>
+__device__ __forceinline__ float2 load2<__half>(const __half* p) {
+  unsigned int u = __ldg(reinterpret_cast<const unsigned int*>(p));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
 
 // context[r] = sum_l w[r][l] * feat[l] ; thread owns columns (2t, 2t+1); weights are read from smem four
-// items at a time (128-bit broadcast loads) when the row length allows it
+// items at a time (128-bit broadcast loads) when the row length allows it. UNR rows are in flight per thread: 8 fp32
+// rows (8 x 8 B) or 16 rows of a 16-bit type (16 x 4 B) — the kernel is bound by bytes in flight, so halving the
+// element width must not halve them.
 template <typename FeatT, int RT>
 __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int n_items, int R,
                                              const float* __restrict__ w_smem, RowDest dst, long long row0, int dst_col) {
   constexpr int RU = RT > 0 ? RT : 8;
+  constexpr int UNR = sizeof(FeatT) == 4 ? 8 : 16;
+  constexpr int kAhead = kSumAheadBytes / (H * (int)sizeof(FeatT));
   const int c = threadIdx.x * 2;
   float2 acc[RU];
 #pragma unroll
   for (int r = 0; r < RU; ++r) acc[r] = make_float2(0.f, 0.f);
   int l = 0;
   if ((n_items & 3) == 0 && (reinterpret_cast<uintptr_t>(w_smem) & 15) == 0) {
-    for (; l + 8 <= n_items; l += 8) {  // 8 rows (8 x 8 B per thread) in flight
-      if ((threadIdx.x & (64 / (int)sizeof(FeatT) - 1)) == 0) {  // one thread per 128-byte line of the 8 rows kSumAhead ahead
+    for (; l + UNR <= n_items; l += UNR) {
+      if ((threadIdx.x & (64 / (int)sizeof(FeatT) - 1)) == 0) {  // one thread per 128-byte line of the UNR rows kAhead ahead
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (l + kSumAhead + u < n_items) prefetch_l2(feat + (long long)(l + kSumAhead + u) * H + c);
+        for (int u = 0; u < UNR; ++u)
+          if (l + kAhead + u < n_items) prefetch_l2(feat + (long long)(l + kAhead + u) * H + c);
       }
-      float2 a[8];
+      float2 a[UNR];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = load2<FeatT>(feat + (long long)(l + u) * H + c);
+      for (int u = 0; u < UNR; ++u) a[u] = load2<FeatT>(feat + (long long)(l + u) * H + c);
 #pragma unroll
       for (int r = 0; r < RU; ++r)
         if (RT > 0 || r < R) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
+          for (int hh = 0; hh < UNR / 4; ++hh) {
             const float4 w = *reinterpret_cast<const float4*>(w_smem + r * n_items + l + 4 * hh);
             acc[r].x = fmaf(w.x, a[4 * hh].x, acc[r].x); acc[r].y = fmaf(w.x, a[4 * hh].y, acc[r].y);
             acc[r].x = fmaf(w.y, a[4 * hh + 1].x, acc[r].x); acc[r].y = fmaf(w.y, a[4 * hh + 1].y, acc[r].y);
@@ -308,14 +462,37 @@ __device__ __forceinline__ void weighted_sum(const FeatT* __restrict__ feat, int
     if (RT > 0 || r < R) dst.store2(row0 + r, dst_col + c, acc[r]);
 }
 
-// TANH_MODE: 0 = libdevice tanhf (ISC_PREC_FP32); 1 = e-product tanh, |err| ~ 2e-7 (ISC_PREC_BF16X3): p_att and
-// p_sw hold exp(-2 * projected feature) (written by the prologue GEMM epilogue, ACT_EXPNEG2_RELU);
-// 2 = tanh.approx.f32, one MUFU (ISC_PREC_BF16)
+template <typename FeatT>
+__device__ __forceinline__ void prefetch_first_rows(const FeatT* a0, int L) {
+  constexpr int kLines = H * (int)sizeof(FeatT) / 128;
+  constexpr int kAhead = kSumAheadBytes / (H * (int)sizeof(FeatT));
+  for (int i = threadIdx.x; i < kAhead * kLines && i / kLines < L; i += 256)
+    prefetch_l2(reinterpret_cast<const char*>(a0 + (long long)(i / kLines) * H) + (i % kLines) * 128);
+}
+
+// PREC = ISC_PREC_*: the representation of the full-width features and the scoring mode of the wide path:
+//   FP32: fp32 ReLU(.) + tanhf | BF16X3: fp32 att, fp32 exp(-2 p), e-product (mode 3) | BF16: bf16 att and p, tanh.approx.
+// The fast path (p.p_att16 set and the image not flagged; tensor-core precisions): fp16 p_att16 scored in mode 1, att16
+// (or, in ISC_PREC_BF16, the bf16 att) summed.
+template <int RT>
+struct AttnVariant {
+  static constexpr bool kRegQuery = RT == 1 || RT == 3;  // queries in registers (2 CTAs per SM), else in shared memory (4)
+  static constexpr int kRing = kRegQuery ? kRingBytesReg : kRingBytes;
+};
 template <typename FeatT, int TANH_MODE, int RT>
-__global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
+__device__ __forceinline__ void score_dispatch(const FeatT* __restrict__ p_feat, int n_items, int R, const float* q_smem,
+                                               const float* alpha_smem, float* score_smem, void* ring, int warp, int lane) {
+  if (AttnVariant<RT>::kRegQuery) score_rows_reg<FeatT, TANH_MODE, (RT > 0 ? RT : 1)>(p_feat, n_items, q_smem, alpha_smem, score_smem, ring, warp, lane, 8);
+  else score_rows<FeatT, TANH_MODE, RT>(p_feat, n_items, R, q_smem, alpha_smem, score_smem, ring, warp, lane, 8);
+}
+
+template <int PREC, int RT>
+__global__ void __launch_bounds__(256, (RT == 1 || RT == 3) ? 2 : 3) attention_kernel(AttnParams p) {
   extern __shared__ __align__(16) float sm[];
   pdl_trigger();
   pdl_wait();
+  constexpr int WIDE_MODE = PREC == ISC_PREC_FP32 ? 0 : (PREC == ISC_PREC_BF16X3 ? 3 : 2);
+  typedef typename std::conditional<PREC == ISC_PREC_BF16, __nv_bfloat16, float>::type WideT;
   const int R = RT > 0 ? RT : p.R, L = p.L, S = p.S;
   const int Lp = (L + 3) & ~3, Sp = (S + 3) & ~3;  // padded score rows keep 16-byte alignment
   float* q_c = sm;                 // [R][H] content query  h2att(h)
@@ -324,54 +501,60 @@ __global__ void __launch_bounds__(256) attention_kernel(AttnParams p) {
   float* alpha_s = alpha_c + H;    // [H]
   float* sc_c = alpha_s + H;       // [R][L]
   float* sc_s = sc_c + R * Lp;     // [R][S]
-  float* ring_base = sc_s + R * Sp;  // [8 warps][2 slots][H] fp32 worth of staging (bf16 rows use half)
+  uint8_t* ring_base = reinterpret_cast<uint8_t*>(sc_s + R * Sp);  // [8 warps][ring bytes of this variant]
   const int img = blockIdx.x;
   const long long row0 = (long long)img * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fast = PREC != ISC_PREC_FP32 && p.p_att16 != nullptr && (p.flags == nullptr || p.flags[img] == 0);
   for (int i = threadIdx.x; i < R * H; i += 256) {
     int r = i / H, c = i - r * H;
     const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
     const float qc = hp[c];
     const float qw = hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f);
-    // TANH_MODE 1: queries (like the projected features) are kept as exp(-2 x) for the e-product tanh
-    q_c[i] = TANH_MODE == 1 ? exp_neg2(qc) : qc;
-    q_s[i] = TANH_MODE == 1 ? exp_neg2(qw) : qw;
+    // e-product modes keep the queries (like the projected features) as exp(-2 x); the fast path folds its feature
+    // scale 2^15 into the query
+    q_c[i] = fast ? exp_neg2(qc) * (1.0f / kFastScale) : (WIDE_MODE == 3 ? exp_neg2_wide(qc) : qc);
+    q_s[i] = WIDE_MODE == 3 ? exp_neg2_wide(qw) : qw;
   }
   for (int i = threadIdx.x; i < H; i += 256) {
     alpha_c[i] = p.alpha_c[i];
     alpha_s[i] = p.alpha_s[i];
   }
   __syncthreads();
-  const FeatT* att = reinterpret_cast<const FeatT*>(p.att);
-  const FeatT* p_att = reinterpret_cast<const FeatT*>(p.p_att);
-  if (att)
-    score_rows<FeatT, TANH_MODE, RT>(p_att + (long long)img * L * H, L, R, q_c, alpha_c, sc_c,
-                                     reinterpret_cast<FeatT*>(ring_base + warp * kRing * H), warp, lane, 8);
-  if (p.sw)
-    score_rows<float, TANH_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring_base + warp * kRing * H,
-                                     warp, lane, 8);
-  __syncthreads();
-  if (att) {  // the first rows of the weighted sum travel to L2 while the softmax runs
-    const FeatT* a0 = att + (long long)img * L * H;
-    constexpr int kLines = H * (int)sizeof(FeatT) / 128;
-    for (int i = threadIdx.x; i < kSumAhead * kLines && i / kLines < L; i += 256)
-      prefetch_l2(reinterpret_cast<const char*>(a0 + (long long)(i / kLines) * H) + (i % kLines) * 128);
+  const long long foff = (long long)img * L * H;
+  void* ring = ring_base + warp * AttnVariant<RT>::kRing;
+  if (p.att) {
+    if (fast)
+      score_dispatch<__half, 1, RT>(reinterpret_cast<const __half*>(p.p_att16) + foff, L, R, q_c, alpha_c, sc_c, ring, warp, lane);
+    else
+      score_dispatch<WideT, WIDE_MODE, RT>(reinterpret_cast<const WideT*>(p.p_att) + foff, L, R, q_c, alpha_c, sc_c, ring, warp, lane);
   }
-  if (att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
+  if (p.sw)
+    score_dispatch<float, WIDE_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring, warp, lane);
+  __syncthreads();
+  const bool att_half = fast && p.att16 != nullptr;
+  if (p.att) {  // the first rows of the weighted sum travel to L2 while the softmax runs
+    if (att_half) prefetch_first_rows(reinterpret_cast<const __half*>(p.att16) + foff, L);
+    else prefetch_first_rows(reinterpret_cast<const WideT*>(p.att) + foff, L);
+  }
+  if (p.att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
   if (p.sw) softmax_rows(sc_s, S, R, warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
   __syncthreads();
-  if (att) weighted_sum<FeatT, RT>(att + (long long)img * L * H, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  if (p.att) {
+    if (att_half) weighted_sum<__half, RT>(reinterpret_cast<const __half*>(p.att16) + foff, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+    else weighted_sum<WideT, RT>(reinterpret_cast<const WideT*>(p.att) + foff, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  }
   if (p.sw) weighted_sum<float, RT>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
 }
 
-template <typename FeatT, int TANH_MODE>
+template <int PREC>
 static int launch_attention_t(const AttnParams& p, int B, size_t smem, cudaStream_t stream) {
   void (*k)(AttnParams) = nullptr;
   switch (p.R) {
-    case 1: k = attention_kernel<FeatT, TANH_MODE, 1>; break;
-    case 3: k = attention_kernel<FeatT, TANH_MODE, 3>; break;
-    case 5: k = attention_kernel<FeatT, TANH_MODE, 5>; break;
-    default: k = attention_kernel<FeatT, TANH_MODE, 0>; break;
+    case 1: k = attention_kernel<PREC, 1>; break;
+    case 3: k = attention_kernel<PREC, 3>; break;
+    case 5: k = attention_kernel<PREC, 5>; break;
+    default: k = attention_kernel<PREC, 0>; break;
   }
   ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ISC_CUDA(launch_pdl(k, dim3(B), dim3(256), smem, stream, p));
@@ -379,20 +562,23 @@ static int launch_attention_t(const AttnParams& p, int B, size_t smem, cudaStrea
   return 0;
 }
 
-int launch_attention(const AttnParams& p, int B, bool bf16_feats, int tanh_mode, cudaStream_t stream) {
+int launch_attention(const AttnParams& p, int B, int precision, cudaStream_t stream) {
   ISC_REQUIRE(p.R >= 1 && p.R <= 8, "attention: rows per image %d not in 1..8", p.R);
-  ISC_REQUIRE((bf16_feats && tanh_mode == 2) || (!bf16_feats && tanh_mode != 2), "attention: feature dtype / tanh mode mismatch");
+  ISC_REQUIRE(!p.att16 || p.p_att16, "attention: att16 without p_att16");
   const int Lp = (p.L + 3) & ~3, Sp = (p.S + 3) & ~3;
-  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp + 8 * kRing * H);
+  const int ring_bytes = (p.R == 1 || p.R == 3) ? kRingBytesReg : kRingBytes;
+  size_t smem = sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp) + 8 * ring_bytes;
   // algorithmic HBM bytes: both feature tensors of every image once per launch (shared by its R rows),
   // sentiment-word features, the R query rows in and the R context rows out
-  const double feat_b = bf16_feats ? 2.0 : 4.0;
-  const double bytes = (double)B * ((p.att ? 2.0 * p.L * H * feat_b : 0.0) + (p.sw ? 2.0 * p.S * H * 4.0 : 0.0) +
+  const bool fastp = precision != ISC_PREC_FP32 && p.p_att16 != nullptr;
+  const double wide_b = precision == ISC_PREC_BF16 ? 2.0 : 4.0;
+  const double feat_b = (fastp ? 2.0 : wide_b) + ((fastp && p.att16) ? 2.0 : wide_b);
+  const double bytes = (double)B * ((p.att ? p.L * H * feat_b : 0.0) + (p.sw ? 2.0 * p.S * H * 4.0 : 0.0) +
                                     (double)p.R * (3.0 * H * 4.0 + 2.0 * H * 4.0));
   ProfScope ps(ISC_K_ATTENTION, bytes, stream);
-  if (bf16_feats) return launch_attention_t<__nv_bfloat16, 2>(p, B, smem, stream);
-  if (tanh_mode == 1) return launch_attention_t<float, 1>(p, B, smem, stream);
-  return launch_attention_t<float, 0>(p, B, smem, stream);
+  if (precision == ISC_PREC_BF16) return launch_attention_t<ISC_PREC_BF16>(p, B, smem, stream);
+  if (precision == ISC_PREC_BF16X3) return launch_attention_t<ISC_PREC_BF16X3>(p, B, smem, stream);
+  return launch_attention_t<ISC_PREC_FP32>(p, B, smem, stream);
 }
 
 // --------------------------------------------------------------------------------------------

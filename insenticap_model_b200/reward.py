@@ -61,9 +61,10 @@ class RefSet:
         self.n_images = len(refs_words)
         self.ld = ld
         self.n_positions = int(sum(max(4 * int(l) - 6, int(l)) for l in lens))
-        self.tokens = torch.from_numpy(tok).to(device)
-        self.lens = torch.from_numpy(lens).to(device)
-        self.offsets = torch.from_numpy(offs).to(device)
+        # pinned staging + async copies: building the references of a batch must not drain the stream (RL iteration)
+        self.tokens = _lib.to_device_async(torch.from_numpy(tok), torch.from_numpy(tok).dtype, device)
+        self.lens = _lib.to_device_async(torch.from_numpy(lens), torch.from_numpy(lens).dtype, device)
+        self.offsets = _lib.to_device_async(torch.from_numpy(offs), torch.from_numpy(offs).dtype, device)
 
 
 class CiderD:
@@ -122,7 +123,7 @@ class CiderD:
         if self.table is None:
             raise RuntimeError("CiderD: document-frequency table not built (pass refs=...)")
         hyps = hyps.to(self.device).long().contiguous()
-        hyp_img = hyp_img.to(self.device).int().contiguous()
+        hyp_img = _lib.to_device_async(hyp_img, torch.int32, self.device).contiguous()
         N, T = hyps.shape
         scores = torch.empty(N, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):

@@ -82,7 +82,7 @@ class SentenceSentimentClassifier(nn.Module):
         packed = self._pack(dev)
         B = seqs.shape[0]
         seqs = seqs.long().contiguous()
-        lens_t = lens_t.to(dev).contiguous()
+        lens_t = _lib.to_device_async(lens_t, torch.int32, dev).contiguous()
         n = len(self.sentiment_categories)
         nbytes = lib.isc_sentcls_workspace_bytes(B, T)
         if self._ws is None or self._ws.numel() < nbytes or self._ws.device != dev:

@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from insenticap_model_b200 import synthetic as syn
+from insenticap_model_b200.captioner import Captioner
 from oracle import captioner_oracle as O
 from tests._common import T, greedy_mismatch_report, model, params, to_cuda
 
@@ -394,3 +395,113 @@ def test_empty_and_invalid_arguments_fail_loudly():
     assert lib.isc_decode_workspace_bytes(C.byref(d), 1, 0) == 0  # M = 0 -> no workspace, and the call refuses it
     with pytest.raises(RuntimeError):
         _lib.check(lib.isc_decode_beam(C.byref(d), None, 1, None, 0, 3, 4, 1, None, None, None, None, 0, None), "isc_decode_beam")
+
+
+def _stressed_model(V, scale, precision="bf16x3"):
+    """att2att, senti2att and the three query projections scaled by `scale`: attention pre-activations p = ReLU(att2att(.))
+    and q = h2att(h) grow `scale`-fold, far beyond the fp16 fast path's domain (p <= 10) and into the region
+    p > 20, q < -20 where a naive exp(-2p) * exp(-2q) factorisation of tanh(p + q) breaks down."""
+    sd = params(V, 3)
+    for k in ("att2att.0.weight", "att2att.0.bias", "senti2att.0.weight", "senti2att.0.bias",
+              "attention.cont_att.h2att.weight", "attention.cont_att.h2att.bias",
+              "attention.senti_att.h2word.weight", "attention.senti_att.h2word.bias"):
+        sd[k] = sd[k] * scale
+    m = Captioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS), precision=precision)
+    m.load_state_dict(sd)
+    return m.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("scale", [30.0, 120.0])
+def test_attention_extreme_preactivations_match_oracle(scale):
+    """the e-product tanh must stay right when the projected features and the queries are huge with
+    opposite signs. Every image is then outside the 16-bit path's domain, is flagged by the prologue and takes the wide
+    path (fp32 exp(-2p), product clamped): attention weights, one step's log-probs and the greedy tokens equal the oracle."""
+    V, B = 500, 6
+    m, sd = _stressed_model(V, scale)
+    fc, att, cpts, sentis, labels = syn.synthetic_inputs(B, V, seed=17)
+    t, _ = m.prologue(*to_cuda(fc, att, cpts, sentis, labels))
+    assert int((t["feat_flags"] != 0).sum()) == B  # all flagged: max p is far above 10
+    with torch.no_grad():
+        f = O.prologue(sd, fc, att, cpts, sentis, labels)
+        assert float(f["p_att"].max()) > (60.0 if scale > 100 else 15.0)  # measured: 17 at x30, 68 at x120
+        seq_o, lp_o, mask_o, margins = O.decode_greedy(sd, f, B, T, return_margins=True)
+        seq, lp, mask = m(*to_cuda(fc, att, cpts, sentis, labels), T, 1, mode="rl")
+        q = F_lin(O, sd, f, seq_o)
+    assert float(q.min()) < -20.0 or scale < 100  # the queries reach the clamp region at the larger scale
+    bad, _ = greedy_mismatch_report(seq, seq_o, margins, 1e-5)
+    assert not bad, bad
+    same = (seq.cpu() == seq_o).all(1)
+    assert int(same.sum()) >= B - 1
+    np.testing.assert_allclose(lp.cpu()[same].numpy(), lp_o[same].numpy(), rtol=1e-3, atol=1e-4)
+    # beam search takes the same kernels with R = 3 rows per image
+    tk, sc, ln = m.beam_search(*to_cuda(fc, att, sentis, labels), beam_size=3, max_seq_len=T)
+    with torch.no_grad():
+        tk_o, sc_o, ln_o, margin = O.beam_search(sd, O.prologue(sd, fc, att, None, sentis, labels), B, 3, 1, T, return_margins=True)
+    if margin > 1e-5:
+        assert np.array_equal(tk.cpu().numpy(), tk_o.numpy())
+        # scores ~ -97 here and the x120 attention is razor sharp: 5e-5 relative (the north-star tolerance is 1e-3)
+        np.testing.assert_allclose(sc.cpu().numpy(), sc_o.numpy(), rtol=5e-5, atol=5e-4)
+
+
+def F_lin(O_, sd, f, seq_o):
+    """content-attention queries h2att(h_att) of the oracle's first decode step (to show how negative they get)."""
+    B = seq_o.shape[0]
+    h = torch.zeros(2, B, 512)
+    it = torch.full((B,), 1, dtype=torch.long)
+    _, (h1, _) = O_.step(sd, it, (h, torch.zeros_like(h)), f)
+    return torch.nn.functional.linear(h1[0], sd["attention.cont_att.h2att.weight"], sd["attention.cont_att.h2att.bias"])
+
+
+def test_fast_feature_path_equals_wide_path_tokens_and_flags_mixed_batch():
+    """The 16-bit attention path and the full-width path decode the same tokens (cfg1 and an EOS-heavy batch), and a batch in
+    which only SOME images leave the fp16 domain is split per image: flagged ones read full width, the rest 16-bit."""
+    V, B, (fc, att, cpts, sentis, labels) = _cfg1()
+    m = model(V, 0, "bf16x3")
+    fast = [x.clone() for x in m.beam_search(*to_cuda(fc, att, sentis, labels), beam_size=3, max_seq_len=T)]
+    m.fast_features = False
+    try:
+        wide = m.beam_search(*to_cuda(fc, att, sentis, labels), beam_size=3, max_seq_len=T)
+    finally:
+        m.fast_features = True
+    assert torch.equal(fast[0], wide[0]) and torch.equal(fast[2], wide[2])
+    np.testing.assert_allclose(fast[1].cpu().numpy(), wide[1].cpu().numpy(), atol=5e-5)
+    t, _ = m.prologue(*to_cuda(fc, att, None, sentis, labels))
+    assert int(t["feat_flags"].abs().sum()) == 0  # ordinary features: nobody flagged
+    # scale up the region features of images 1 and 4 so that only THEIR projected features exceed the domain
+    att2 = att.clone()
+    att2[1] *= 40.0
+    att2[4] *= 40.0
+    t2, _ = m.prologue(*to_cuda(fc, att2, None, sentis, labels))
+    assert t2["feat_flags"].ne(0).cpu().tolist() == [i in (1, 4) for i in range(B)]
+    got = m.beam_search(*to_cuda(fc, att2, sentis, labels), beam_size=3, max_seq_len=T)
+    p = params(V, 0)
+    with torch.no_grad():
+        tk_o, sc_o, ln_o, margin = O.beam_search(p, O.prologue(p, fc, att2, None, sentis, labels), B, 3, 1, T, return_margins=True)
+    if margin > 1e-5:
+        assert np.array_equal(got[0].cpu().numpy(), tk_o.numpy())
+
+
+@pytest.mark.parametrize("label", [0, 1, 2])
+def test_cfg2_single_sentiment_runs(label):
+    """BASELINE configs[1] / SURVEY 8(d) 'cfg2: also all-0 / all-1 / all-2 runs': beam-3 over a batch conditioned on ONE
+    sentiment (all positive / all negative / all neutral), B = 1024: invariants at full size, the oracle on a slice, and
+    the label must matter (the captions differ from another sentiment's)."""
+    V, B, K = 10000, 1024, 3
+    m = model(V, 0, "bf16x3")
+    g = torch.Generator(device="cuda").manual_seed(4321)
+    fc = torch.rand(B, 2048, device="cuda", generator=g)
+    att = torch.rand(B, 14, 14, 2048, device="cuda", generator=g)
+    sentis = torch.randint(4, V, (B, 10), device="cuda", generator=g)
+    labels = torch.full((B,), label, dtype=torch.long, device="cuda")
+    tk, sc, ln = m.beam_search(fc, att, sentis, labels, beam_size=K, max_seq_len=T)
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all()) and int(tk.min()) >= 0 and int(tk.max()) < V
+    other = m.beam_search(fc[:64], att[:64], sentis[:64], (labels[:64] + 1) % 3, beam_size=K, max_seq_len=T)
+    assert not torch.equal(other[0], tk[:64])
+    idx = torch.arange(0, B, 64)
+    p = params(V, 0)
+    with torch.no_grad():
+        f = O.prologue(p, fc[idx].cpu(), att[idx].cpu(), None, sentis[idx].cpu(), labels[idx].cpu())
+        tk_o, sc_o, ln_o, margin = O.beam_search(p, f, len(idx), K, 1, T, return_margins=True)
+    neq = (tk[idx].cpu() != tk_o).any(2).any(1)
+    assert int(neq.sum()) == 0 or margin < 1e-5, (int(neq.sum()), margin)
+    np.testing.assert_allclose(sc[idx].cpu().numpy()[~neq.numpy()], sc_o.numpy()[~neq.numpy()], atol=2e-4)
