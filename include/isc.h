@@ -162,6 +162,9 @@ int isc_prologue_bf16in(const isc_dims_t* dims, const void* packed, int precisio
  * what the attention kernel's tanh reads there; everything else is a copy. n elements. */
 int isc_convert_features(int precision, int projected, const float* src, void* dst, int64_t n,
                          isc_stream_t stream);
+/* fp16 features (a fp16 feature shard, isc_shard_* below; half the host->device bytes of fp32) -> the fp32 tensors
+ * isc_prologue reads. Exact: every fp16 value is an fp32 value. n elements, 16-byte aligned buffers. */
+int isc_expand_f16(const void* src_f16, float* dst, int64_t n, isc_stream_t stream);
 
 /* Recompute only the hoisted terms (pre_gates, pre_word) from feats->fc / feats->sl:
  * used when the caller supplies already-embedded features (Captioner.forward_step API). */
@@ -269,6 +272,12 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
                        const float* logprobs, const float* dlogprobs, const int64_t* targets,
                        int64_t ld_targets, const float* coef, const float* d_cpt_feats,
                        const isc_grads_t* grads, void* workspace, size_t workspace_bytes, isc_stream_t stream);
+/* Arms up to two CUDA events (cudaEvent_t, or NULL) for the NEXT isc_train_backward call of this host thread. The call
+ * records event0 on its stream once the gradients of classifier.*, lang_lstm.* and attention.{h2att, cont2att,
+ * senti2att, att_alpha} are final, and event1 once att_lstm.* is final — before the hoisted terms and the prologue
+ * layers are differentiated — so that the caller can all-reduce those gradients (the path's one collective,
+ * bucketed in reverse layer order) under the rest of the backward. Both are recorded at the latest when the call ends. */
+int isc_train_backward_marks(void* event0, void* event1);
 /* Element-wise clamp to +-clip (train_xe.py:19-23; clip <= 0 disables) then torch.optim.Adam's update, fused over a
  * flat fp32 buffer; grads are first multiplied by grad_scale (1 / world_size after a summing all-reduce). */
 int isc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
@@ -317,6 +326,7 @@ int isc_sentcls_forward(int vocab, int n_cls, const void* packed, const int64_t*
  * u64 record_bytes}, n NUL-terminated names in record order, zero padding to data_offset, records. */
 #define ISC_SHARD_F32 0
 #define ISC_SHARD_BF16 1
+#define ISC_SHARD_F16 2 /* IEEE half, round-to-nearest-even: 11 significant bits, exactly representable by the split-bf16 GEMM operands */
 typedef void* isc_shard_t;
 int isc_shard_write(const char* path, int dtype, int feat_dim, int n_regions, int64_t n_images,
                     const char* const* names, const float* fc_feats, const float* att_feats);

@@ -118,13 +118,25 @@ class _TeacherForced(torch.autograd.Function):
         (logprobs,) = ctx.saved_tensors
         B, n_steps = call["inputs"].shape[0], call["inputs"].shape[1] - 1
         sizes = [int(torch.Size(sh).numel()) for sh in ctx.param_shapes]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        # A gradient sink (train.FusedClampAdam registers itself as model._grad_sink) owns ONE flat fp32 gradient buffer
+        # whose slices are the parameters' .grad: isc_train_backward ACCUMULATES, so it adds straight into those slices and
+        # autograd gets None for the parameters — no per-node 88 MB scratch, no AccumulateGrad pass, and the sink knows
+        # when slices are final (gradient-ready marks -> bucketed all-reduce under the rest of the backward).
+        sink = getattr(model, "_grad_sink", None)
+        if sink is not None and not sink.accepts(dev, ctx.param_shapes):
+            sink = None
         views, g, off = [], _lib.Grads(), 0
-        for (field, _), n, sh in zip(_lib.WEIGHT_FIELDS, sizes, ctx.param_shapes):
-            v = flat[off:off + n].view(sh)
-            views.append(v)
-            setattr(g, field, v.data_ptr())
-            off += n
+        if sink is not None:
+            for field, name in _lib.WEIGHT_FIELDS:
+                setattr(g, field, sink.grad_slice(name).data_ptr())
+        else:
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            for (field, _), n, sh in zip(_lib.WEIGHT_FIELDS, sizes, ctx.param_shapes):
+                v = flat[off:off + n].view(sh)
+                views.append(v)
+                setattr(g, field, v.data_ptr())
+                off += n
+        no_param_grads = (None,) * len(sizes)
         targets = coef = None
         if call.get("fused") is not None:
             targets, coef = call["fused"]
@@ -136,9 +148,15 @@ class _TeacherForced(torch.autograd.Function):
             dlogp = dlogp.contiguous() if dlogp is not None else None
         dcpt = dcpt.contiguous() if (dcpt is not None and call["cpt"] is not None) else None
         if dlogp is None and coef is None and dcpt is None:
+            if sink is not None:
+                sink.node_done(None)
+                return (None, None, None) + no_param_grads
             return (None, None, None) + tuple(views)
         drop = model._dropout_struct(call["dropout"])
+        marks = sink.node_starting() if sink is not None else None  # events, if this is the iteration's last backward node
         with torch.cuda.device(dev):
+            if marks is not None:
+                _lib.check(lib.isc_train_backward_marks(marks[0].cuda_event, marks[1].cuda_event), "isc_train_backward_marks")
             _lib.check(lib.isc_train_backward(
                 C.byref(d), _lib.ptr(ctx.packed), model._prec, ctx.mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
                 _lib.ptr(call["cpt"]), call["cpt"].shape[1] if call["cpt"] is not None else 0, _lib.ptr(call["sw"]),
@@ -147,6 +165,9 @@ class _TeacherForced(torch.autograd.Function):
                 targets.shape[1] if targets is not None else 0, _lib.ptr(coef), _lib.ptr(dcpt), C.byref(g), _lib.ptr(ctx.ws),
                 ctx.ws.numel(), _lib.stream_ptr(dev)), "isc_train_backward")
         ctx.ws = None
+        if sink is not None:
+            sink.node_done(marks)
+            return (None, None, None) + no_param_grads
         return (None, None, None) + tuple(views)
 
 
@@ -283,6 +304,17 @@ class Captioner(nn.Module):
                                                         x.numel(), _lib.stream_ptr(dev)), "isc_convert_features")
         return out
 
+    def _expand_f16(self, x):
+        """fp16 device tensor -> fp32 (isc_expand_f16); other dtypes pass through."""
+        if x.dtype != torch.float16:
+            return x
+        dev = self._device()
+        x = x.contiguous()
+        out = torch.empty(x.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().isc_expand_f16(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr(dev)), "isc_expand_f16")
+        return out
+
     # ------------------------------------------------------------------ training plumbing
     def _dropout_masks(self, shapes, n_steps, B):
         """uint8 keep masks for the tensors nn.Dropout touches in the reference (captioner.py:182, :200-214,
@@ -358,6 +390,10 @@ class Captioner(nn.Module):
         if not seq2seq:
             # bf16 features (a bf16 feature shard, dataloader.FeatureShard): precision="bf16" rounds its inputs to bf16
             # anyway, so they go in as they are; every other mode computes on fp32 inputs
+            if fc_feats.dtype == torch.float16 or att_feats.dtype == torch.float16:
+                # fp16 features (a fp16 feature shard): half the host->device bytes; every fp16 value is an fp32 value and
+                # is represented exactly by the split-bf16 operands, so this is the fp32 computation on these inputs
+                fc_feats, att_feats = self._expand_f16(fc_feats), self._expand_f16(att_feats)
             bf16_in = (fc_feats.dtype == torch.bfloat16 and att_feats.dtype == torch.bfloat16
                        and self._prec == _lib.PREC_BF16 and not dropout)
             keep = (lambda x: x.contiguous()) if bf16_in else (lambda x: x.float().contiguous())

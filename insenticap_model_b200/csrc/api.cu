@@ -503,6 +503,22 @@ int isc_convert_features(int precision, int projected, const float* src, void* d
   return 0;
 }
 
+int isc_expand_f16(const void* src_f16, float* dst, int64_t n, isc_stream_t stream) {
+  ISC_TRY(check_device());
+  ISC_REQUIRE(src_f16 && dst && n >= 0, "bad expand_f16 arguments");
+  ISC_REQUIRE((reinterpret_cast<uintptr_t>(src_f16) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+              "expand_f16: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const long long n8 = (n + 7) / 8;
+  int blocks = (int)((n8 + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  ProfScope ps(ISC_K_POINTWISE, (double)n * 6.0, s);
+  expand_f16_kernel<<<blocks, 256, 0, s>>>(static_cast<const __half*>(src_f16), dst, n);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+
 size_t isc_gemm_workspace_bytes(int precision, int M, int N, int K) {
   if (precision == ISC_PREC_FP32) return 256;
   size_t planes = precision == ISC_PREC_BF16X3 ? 2 : 1;

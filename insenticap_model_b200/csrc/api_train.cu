@@ -269,6 +269,18 @@ DecodeWs tape_view(const TrainWs& w, int t, int B) {
   return v;
 }
 
+// Optional events recorded inside isc_train_backward at the points where a group of parameter gradients is final
+// (isc_train_backward_marks): lets the caller start the data-parallel all-reduce of those gradients while the rest of the
+// backward (hoisted terms, prologue layers) still runs. Armed per call, per host thread.
+thread_local cudaEvent_t g_marks[2] = {nullptr, nullptr};
+int record_mark(int i, cudaStream_t s) {
+  if (g_marks[i]) {
+    ISC_CUDA(cudaEventRecord(g_marks[i], s));
+    g_marks[i] = nullptr;
+  }
+  return 0;
+}
+
 }  // namespace
 }  // namespace isc
 
@@ -351,6 +363,12 @@ int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision,
     ISC_TRY(run_step(c, v, B, 1, io));
     ISC_TRY(launch_log_softmax(io.logits, io.ld_logits, B, (int)V, c.s));
   }
+  return 0;
+}
+
+int isc_train_backward_marks(void* event0, void* event1) {
+  g_marks[0] = static_cast<cudaEvent_t>(event0);
+  g_marks[1] = static_cast<cudaEvent_t>(event1);
   return 0;
 }
 
@@ -546,6 +564,9 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       ISC_TRY(pgemm(precision, op_of(w.dhprojT, 2 * H), op_of(w.csT, 0), g->g_cont2att_w, H, H, H, TMk, true, s));
       ISC_TRY(pgemm(precision, op_of(w.dhprojT, 2 * H), op_of(w.csT, H), g->g_senti2att_w, H, H, H, TMk, true, s));
     }
+    // gradients of classifier.*, lang_lstm.* and attention.{h2att, cont2att, senti2att, att_alpha} are final from here
+    // on: the data-parallel all-reduce of that (contiguous) tail of the flat gradient may start (isc_train_backward_marks)
+    ISC_TRY(record_mark(0, s));
 
     // ---- hoisted step-invariant terms: pre_gates = [fc | sl] Wpre^T (+ biases, already covered by colsum(dg1))
     ISC_TRY(split_planes(w.dpre_gates, G4, w.pB4.hi, w.pB4.lo, G4, M, G4, s));
@@ -558,6 +579,7 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     ISC_TRY(to_T(f.sl, H, M, H, w.slT, 0, s));
     ISC_TRY(pgemm(precision, op_of(w.B4T), op_of(w.fcT), g->att_lstm_w_ih + H, 3 * H, G4, H, Bk, true, s));
     ISC_TRY(pgemm(precision, op_of(w.B4T), op_of(w.slT), g->att_lstm_w_ih + 2 * H, 3 * H, G4, H, Bk, true, s));
+    ISC_TRY(record_mark(1, s));  // att_lstm.{weight_ih, weight_hh, bias_ih, bias_hh} final
     const float* dsl_extra = nullptr;
     if (tm.sw) {  // label2word(sl), the label term of the sentiment-attention query
       ISC_TRY(launch_colsum_add(w.dpre_word, H, M, H, g->sa_label2word_b, nullptr, s));
@@ -642,6 +664,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     ISC_TRY(launch_embed_bwd(reinterpret_cast<const long long*>(cpt_words), n_cpt, M, n_cpt, 0, dims->pad_id, 1, (int)V, pk.emb, w.tB1,
                              H, 1, nullptr, 1.f, 1.0f / (float)n_cpt, g->word_embed, s));
   }
+  ISC_TRY(record_mark(0, s));  // marks a call without sequence gradients never reached: everything is final here
+  ISC_TRY(record_mark(1, s));
   return 0;
 }
 

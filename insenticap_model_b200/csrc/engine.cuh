@@ -53,6 +53,19 @@ __global__ void proj_convert_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// fp16 -> fp32, 8 elements (one 16-byte load, two 16-byte stores) per thread and iteration
+__global__ void expand_f16_kernel(const __half* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n8 = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&t);
+    const float2 a = __half22float2(h[0]), b = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+    reinterpret_cast<float4*>(dst)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - n8 * 8)) dst[n8 * 8 + threadIdx.x] = __half2float(src[n8 * 8 + threadIdx.x]);
+}
+
 // ------------------------------------------------------------------ bump allocator
 struct Bump {
   uint8_t* base;

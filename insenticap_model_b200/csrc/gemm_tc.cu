@@ -324,7 +324,9 @@ __device__ __forceinline__ void trace_stamp(int slot) {
 #define ISC_TRACE(cond, slot) do { } while (0)
 #endif
 
-template <int PASSES, int BN, int ACT, int EPI, int CG, int AF>
+// H16: the standard epilogue also writes the fp16 copy described by EpiParams::h16 (a compile-time switch: as a run-time
+// test inside the store loop it cost every plain GEMM of the decode step ~4 us)
+template <int PASSES, int BN, int ACT, int EPI, int CG, int AF, int H16 = 0>
 __global__ void __launch_bounds__(NUM_THREADS + (AF ? CONV_WARPS * 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -686,6 +688,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (EPI == EPI_LSTM) {
     // ===================== epilogue: LSTM cell on the gate pre-activations (tile columns = [i f g o] x 16 units per group) =====
+    // (Measured and dropped in round 2: routing c_prev, the addend rows and the results through a per-warp shared-memory
+    // tile so that the warp's global accesses are coalesced — 4x fewer L1 wavefronts, but the shuffles, warp barriers and
+    // smem round trips cost more: attention-LSTM GEMM 48 -> 59 us, language-LSTM GEMM 52 -> 56 us.)
     const int ew = warp - 2;
     const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
     const int half = ew >> 2;      // which half of the tile's 16-unit groups
@@ -918,7 +923,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                   if (n + 3 < ep.N) dst[3] = x.w;
                 }
               }
-              if (ep.h16.out) {
+              if (H16) {
                 float4 y = x;
                 if (ep.h16.expneg2) { y.x = __expf(-2.0f * y.x); y.y = __expf(-2.0f * y.y); y.z = __expf(-2.0f * y.z); y.w = __expf(-2.0f * y.w); }
                 y.x *= ep.h16.scale; y.y *= ep.h16.scale; y.z *= ep.h16.scale; y.w *= ep.h16.scale;
@@ -927,12 +932,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 if (full4 && ((reinterpret_cast<uintptr_t>(d16) & 7) == 0)) {
                   const __half2 a = __floats2half2_rn(y.x, y.y), b = __floats2half2_rn(y.z, y.w);
                   *reinterpret_cast<uint2*>(d16) = make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b));
-                  if (!(lo_ >= ep.h16.vmin && hi_ <= ep.h16.vmax)) atomicOr(ep.h16.flags + row / ep.h16.rows_per_flag, 1);
+                  if (!(lo_ >= ep.h16.vmin && hi_ <= ep.h16.vmax)) atomicOr(ep.h16.flags + (unsigned)row / (unsigned)ep.h16.rows_per_flag, 1);
                 } else {
                   const float yv[4] = {y.x, y.y, y.z, y.w};
                   for (int q = 0; q < 4 && n + q < ep.N; ++q) {
                     d16[q] = __float2half_rn(yv[q]);
-                    if (!(yv[q] >= ep.h16.vmin && yv[q] <= ep.h16.vmax)) atomicOr(ep.h16.flags + row / ep.h16.rows_per_flag, 1);
+                    if (!(yv[q] >= ep.h16.vmin && yv[q] <= ep.h16.vmax)) atomicOr(ep.h16.flags + (unsigned)row / (unsigned)ep.h16.rows_per_flag, 1);
                   }
                 }
               }
@@ -1072,9 +1077,9 @@ static int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64
   return 0;
 }
 
-template <int PASSES, int BN, int ACT, int EPI, int CG, int AF = 0>
+template <int PASSES, int BN, int ACT, int EPI, int CG, int AF = 0, int H16 = 0>
 static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG, AF>;
+  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG, AF, H16>;
   constexpr int smem = Cfg<PASSES, BN, CG, AF>::kSmemBytes;
   constexpr int NUM_THREADS = Cfg<PASSES, BN, CG, AF>::kThreads;
   ISC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1149,6 +1154,12 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.K = K;
   const int grid = persistent_grid<BN, CG>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  if (ep.h16.out) {  // fp16 copy of the result (the prologue's projected features): only the two activations it is used with
+    if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG, 0, 1>(m, ep, grid, stream);
+    if (e.act == ACT_EXPNEG2_RELU) return launch_kernel<PASSES, BN, ACT_EXPNEG2_RELU, EPI_STD, CG, 0, 1>(m, ep, grid, stream);
+    set_error("gemm_tc: fp16 output is only built for the ReLU / exp(-2 ReLU) epilogues");
+    return ISC_ERR_ARG;
+  }
   switch (e.act) {
     case ACT_RELU: return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG>(m, ep, grid, stream);
     case ACT_TANH: return launch_kernel<PASSES, BN, ACT_TANH, EPI_STD, CG>(m, ep, grid, stream);
@@ -1210,6 +1221,11 @@ static int launch_af32(const float* A, int64_t lda, const Operand& W, const Dest
   ep.K = K;
   const int grid = persistent_grid<BN, 1>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  if (ep.h16.out) {
+    if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, 1, 1>(m, ep, grid, stream);
+    set_error("gemm_tc_af32: fp16 output is only built for the ReLU epilogue");
+    return ISC_ERR_ARG;
+  }
   if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, 1>(m, ep, grid, stream);
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, 1, 1>(m, ep, grid, stream);
 }

@@ -4,6 +4,9 @@
 // image share one pass over its region features).
 #include <cuda_fp16.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -276,7 +279,7 @@ template <typename FeatT, int TANH_MODE, int RT>
 __device__ __forceinline__ void score_rows_reg(const FeatT* __restrict__ p_feat, int n_items,
                                                const float* __restrict__ q_smem /*[RT][H]*/, const float* __restrict__ alpha_smem,
                                                float* __restrict__ score_smem /*[RT][n_items]*/, void* __restrict__ ring_raw,
-                                               int warp, int lane, int n_warps) {
+                                               int warp, int lane, int n_warps, bool primed = false) {
   using L = FeatLoad<FeatT>;
   constexpr int NV = L::kChunks * L::kWidth;  // 16 values per lane per row
   constexpr int RING = kRingBytesReg / (H * (int)sizeof(FeatT));  // 4 or 8: divides the 8-row group
@@ -313,9 +316,11 @@ __device__ __forceinline__ void score_rows_reg(const FeatT* __restrict__ p_feat,
   auto ahead = [&](int l) {
     if (l < n_items && lane < kLines) prefetch_l2(reinterpret_cast<const char*>(p_feat + (long long)l * H) + lane * 128);
   };
+  if (!primed) {
 #pragma unroll
-  for (int a = 0; a < RING - 1; ++a) stage(warp + a * n_warps, a);
-  ahead(warp + (RING - 1) * n_warps);
+    for (int a = 0; a < RING - 1; ++a) stage(warp + a * n_warps, a);
+    ahead(warp + (RING - 1) * n_warps);
+  }
   for (int l0 = warp; l0 < n_items; l0 += 8 * n_warps) {  // 8 rows of this warp per group
     float acc[RT][8];
 #pragma unroll
@@ -355,6 +360,94 @@ __device__ __forceinline__ void score_rows_reg(const FeatT* __restrict__ p_feat,
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// The first RING - 1 rows of a warp's stream (rows warp, warp + n_warps, ...) requested into its ring, plus the L2
+// prefetch of the next one: what score_rows_reg / wsum_rows_reg do before their loops, callable EARLY — before the queries
+// are prepared, or right after the scoring pass — so that HBM works through the kernel's set-up and its softmax.
+template <typename FeatT>
+__device__ __forceinline__ void ring_prime(const FeatT* __restrict__ feat, int n_items, void* __restrict__ ring_raw, int warp,
+                                           int lane, int n_warps) {
+  using L = FeatLoad<FeatT>;
+  constexpr int RING = kRingBytesReg / (H * (int)sizeof(FeatT));
+  FeatT* ring = reinterpret_cast<FeatT*>(ring_raw);
+#pragma unroll
+  for (int a = 0; a < RING - 1; ++a) {
+    const int l = warp + a * n_warps;
+    if (l < n_items) {
+#pragma unroll
+      for (int i = 0; i < L::kChunks; ++i) {
+        const FeatT* src = feat + (long long)l * H + L::col(lane, i);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + a * H + L::col(lane, i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  constexpr int kLines = H * (int)sizeof(FeatT) / 128;
+  const int la = warp + (RING - 1) * n_warps;
+  if (la < n_items && lane < kLines) prefetch_l2(reinterpret_cast<const char*>(feat + (long long)la * H) + lane * 128);
+}
+
+// Weighted sum with the scoring pass's structure: warp w streams rows w, w + 8, ... through its cp.async ring (RING - 1
+// rows in flight, nothing held in registers), a lane accumulates ITS 16 columns of the RT context vectors, and the eight
+// per-warp partial sums meet in shared memory at the end (each warp parks its partial in its own ring area). The
+// register-held global loads of weighted_sum (32 KB in flight per SM at two CTAs) sat on the long scoreboard for 30 % of
+// the kernel (ncu, B = 1024, beam 3); this keeps 7 KB per warp in flight like the scores.
+// Expects ring_prime<FeatT>() to have been called for `feat`. Leaves this warp's partial [RT][H] floats at ring_raw.
+template <typename FeatT, int RT>
+__device__ __forceinline__ void wsum_rows_reg(const FeatT* __restrict__ feat, int n_items, const float* __restrict__ w_smem,
+                                              void* __restrict__ ring_raw, int warp, int lane, int n_warps) {
+  using L = FeatLoad<FeatT>;
+  constexpr int NV = L::kChunks * L::kWidth;
+  constexpr int RING = kRingBytesReg / (H * (int)sizeof(FeatT));
+  FeatT* ring = reinterpret_cast<FeatT*>(ring_raw);
+  float ctx[RT][NV];
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) ctx[r][j] = 0.f;
+  constexpr int kLines = H * (int)sizeof(FeatT) / 128;
+  int it = 0;
+  for (int l = warp; l < n_items; l += n_warps, ++it) {
+    const int la = l + RING * n_warps, ls = l + (RING - 1) * n_warps;
+    if (la < n_items && lane < kLines) prefetch_l2(reinterpret_cast<const char*>(feat + (long long)la * H) + lane * 128);
+    if (ls < n_items) {
+      const int slot = (it + RING - 1) % RING;
+#pragma unroll
+      for (int i = 0; i < L::kChunks; ++i) {
+        const FeatT* src = feat + (long long)ls * H + L::col(lane, i);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(ring + slot * H + L::col(lane, i));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
+    float pv[NV];
+#pragma unroll
+    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it % RING) * H, lane, i, pv + i * L::kWidth);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const float w = w_smem[r * n_items + l];  // broadcast
+#pragma unroll
+      for (int j = 0; j < NV; ++j) ctx[r][j] = fmaf(w, pv[j], ctx[r][j]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();  // every lane has read its last staged row: the ring area now holds this warp's partial sums
+  float* part = reinterpret_cast<float*>(ring_raw);
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int i = 0; i < L::kChunks; ++i)
+#pragma unroll
+      for (int j = 0; j < L::kWidth; j += 4)
+        *reinterpret_cast<float4*>(part + r * H + L::col(lane, i) + j) =
+            make_float4(ctx[r][i * L::kWidth + j], ctx[r][i * L::kWidth + j + 1], ctx[r][i * L::kWidth + j + 2],
+                        ctx[r][i * L::kWidth + j + 3]);
+}
+
+// FAST: exp through the raw MUFU op and one reciprocal per row (weights differ from expf / true division by ~3e-7
+// relative; a row's softmax was three serial warps of ~30-instruction expf + division chains while five warps waited).
+template <bool FAST = false>
 __device__ __forceinline__ void softmax_rows(float* score_smem, int n_items, int R, int warp, int lane, int n_warps,
                                              float* w_out, long long ld_w, long long row0) {
   for (int r = warp; r < R; r += n_warps) {
@@ -364,13 +457,16 @@ __device__ __forceinline__ void softmax_rows(float* score_smem, int n_items, int
     mx = warp_max(mx);
     float sum = 0.f;
     for (int l = lane; l < n_items; l += 32) {
-      float e = expf(s[l] - mx);
+      float e;
+      if (FAST) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((s[l] - mx) * 1.4426950408889634f));
+      else e = expf(s[l] - mx);
       s[l] = e;
       sum += e;
     }
     sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
     for (int l = lane; l < n_items; l += 32) {
-      float w = s[l] / sum;
+      float w = FAST ? s[l] * inv : s[l] / sum;
       s[l] = w;
       if (w_out) w_out[(row0 + r) * ld_w + l] = w;
     }
@@ -474,6 +570,27 @@ __device__ __forceinline__ void prefetch_first_rows(const FeatT* a0, int L) {
 //   FP32: fp32 ReLU(.) + tanhf | BF16X3: fp32 att, fp32 exp(-2 p), e-product (mode 3) | BF16: bf16 att and p, tanh.approx.
 // The fast path (p.p_att16 set and the image not flagged; tensor-core precisions): fp16 p_att16 scored in mode 1, att16
 // (or, in ISC_PREC_BF16, the bf16 att) summed.
+constexpr int kSentiDirectMax = 16;                               // sentiment rows held in registers by the direct path
+
+// sentiment-word scores by direct global loads (S ~ 11 fp32 rows per image: no staging); queries from shared memory
+template <int MODE, int RT>
+__device__ __forceinline__ void score_senti_direct(const float* __restrict__ p_sw, int S, const float* __restrict__ q_smem,
+                                                   const float* __restrict__ alpha_smem, float* __restrict__ score_smem, int warp,
+                                                   int lane) {
+  for (int l = warp; l < S; l += 8) {
+    float pv[4][4], al[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p_sw + (long long)l * H + i * 128 + lane * 4));
+      pv[i][0] = t.x; pv[i][1] = t.y; pv[i][2] = t.z; pv[i][3] = t.w;
+      const float4 a = *reinterpret_cast<const float4*>(alpha_smem + i * 128 + lane * 4);
+      const float sc = (MODE == 1 || MODE == 3) ? 2.0f : 1.0f;
+      al[i][0] = sc * a.x; al[i][1] = sc * a.y; al[i][2] = sc * a.z; al[i][3] = sc * a.w;
+    }
+    score_one<float, MODE, RT>(pv, al, l, S, RT, q_smem, score_smem, lane);
+  }
+}
+
 template <int RT>
 struct AttnVariant {
   static constexpr bool kRegQuery = RT == 1 || RT == 3;  // queries in registers (2 CTAs per SM), else in shared memory (4)
@@ -492,6 +609,7 @@ __global__ void __launch_bounds__(256, (RT == 1 || RT == 3) ? 2 : 3) attention_k
   pdl_trigger();
   pdl_wait();
   constexpr int WIDE_MODE = PREC == ISC_PREC_FP32 ? 0 : (PREC == ISC_PREC_BF16X3 ? 3 : 2);
+  constexpr bool kReg = AttnVariant<RT>::kRegQuery;
   typedef typename std::conditional<PREC == ISC_PREC_BF16, __nv_bfloat16, float>::type WideT;
   const int R = RT > 0 ? RT : p.R, L = p.L, S = p.S;
   const int Lp = (L + 3) & ~3, Sp = (S + 3) & ~3;  // padded score rows keep 16-byte alignment
@@ -506,13 +624,274 @@ __global__ void __launch_bounds__(256, (RT == 1 || RT == 3) ? 2 : 3) attention_k
   const long long row0 = (long long)img * R;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool fast = PREC != ISC_PREC_FP32 && p.p_att16 != nullptr && (p.flags == nullptr || p.flags[img] == 0);
+  const bool att_half = fast && p.att16 != nullptr;
+  const long long foff = (long long)img * L * H;
+  void* ring = ring_base + warp * AttnVariant<RT>::kRing;
+  const __half* p16 = reinterpret_cast<const __half*>(p.p_att16) + foff;
+  const __half* a16 = reinterpret_cast<const __half*>(p.att16) + foff;
+  const WideT* pw = reinterpret_cast<const WideT*>(p.p_att) + foff;
+  const WideT* aw = reinterpret_cast<const WideT*>(p.att) + foff;
+  if (kReg && p.sw) {  // the image's 2 x S sentiment-word rows (fp32): on their way to L2 before anything needs them
+    const int lines = S * H * 4 / 128;
+    for (int i = threadIdx.x; i < 2 * lines; i += 256) {
+      const float* base = (i < lines ? p.p_sw : p.sw) + (long long)img * S * H;
+      prefetch_l2(reinterpret_cast<const char*>(base) + (i < lines ? i : i - lines) * 128);
+    }
+  }
+  if (kReg && p.att) {  // the projected rows start streaming before the queries exist
+    if (fast) ring_prime<__half>(p16, L, ring, warp, lane, 8);
+    else ring_prime<WideT>(pw, L, ring, warp, lane, 8);
+  }
+  // e-product modes keep the queries (like the projected features) as exp(-2 x); the fast path folds its feature scale
+  // 2^15 into the query
+  auto to_qc = [&](float qc) { return fast ? exp_neg2(qc) * (1.0f / kFastScale) : (WIDE_MODE == 3 ? exp_neg2_wide(qc) : qc); };
+  auto to_qs = [&](float qw) { return WIDE_MODE == 3 ? exp_neg2_wide(qw) : qw; };
+  if (kReg) {
+    // every global load of the set-up is requested before the first one is used (ncu: with the loop rolled, its six
+    // dependent load -> exp -> store rounds per thread were 21 % of the kernel, HBM idle)
+    constexpr int NQ = (RT > 0 ? RT : 1) * H / 256;
+    float qc[NQ], qw[NQ], pwd[NQ], ac[2], as_[2];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      const int i = threadIdx.x + k * 256, r = i / H, c = i - r * H;
+      const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
+      qc[k] = __ldg(hp + c);
+      qw[k] = __ldg(hp + H + c);
+      pwd[k] = p.pre_word ? __ldg(p.pre_word + (long long)img * H + c) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      ac[k] = __ldg(p.alpha_c + threadIdx.x + k * 256);
+      as_[k] = __ldg(p.alpha_s + threadIdx.x + k * 256);
+    }
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+      q_c[threadIdx.x + k * 256] = to_qc(qc[k]);
+      q_s[threadIdx.x + k * 256] = to_qs(qw[k] + pwd[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      alpha_c[threadIdx.x + k * 256] = ac[k];
+      alpha_s[threadIdx.x + k * 256] = as_[k];
+    }
+  } else {
+    for (int i = threadIdx.x; i < R * H; i += 256) {
+      int r = i / H, c = i - r * H;
+      const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
+      q_c[i] = to_qc(hp[c]);
+      q_s[i] = to_qs(hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f));
+    }
+    for (int i = threadIdx.x; i < H; i += 256) {
+      alpha_c[i] = p.alpha_c[i];
+      alpha_s[i] = p.alpha_s[i];
+    }
+  }
+  __syncthreads();
+  if (kReg) {
+    // ---- register-query variant: one stream per warp through both passes
+    constexpr int RQ = RT > 0 ? RT : 1;
+    if (p.att) {
+      if (fast) score_rows_reg<__half, 1, RQ>(p16, L, q_c, alpha_c, sc_c, ring, warp, lane, 8, true);
+      else score_rows_reg<WideT, WIDE_MODE, RQ>(pw, L, q_c, alpha_c, sc_c, ring, warp, lane, 8, true);
+      // this warp's feature rows start streaming now: they travel through the sentiment scores and the softmax
+      if (att_half) ring_prime<__half>(a16, L, ring, warp, lane, 8);
+      else ring_prime<WideT>(aw, L, ring, warp, lane, 8);
+    }
+    if (p.sw) score_senti_direct<WIDE_MODE, RQ>(p.p_sw + (long long)img * S * H, S, q_s, alpha_s, sc_s, warp, lane);
+    __syncthreads();
+    // the content rows' softmax on warps 0..R-1, the sentiment rows' on warps 7, 6, ...: both at once. (Measured and
+    // dropped: no softmax pass, every warp deriving (max, 1 / sum) itself and forming the weights of its rows inside the
+    // weighted-sum loop — one barrier and the idle warps less, but 15 us MORE per launch: the ex2 -> multiply in front of
+    // each row's 48 FMAs lengthens the loop's dependent chain.)
+    if (p.att) softmax_rows<PREC != ISC_PREC_FP32>(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
+    if (p.sw) softmax_rows<PREC != ISC_PREC_FP32>(sc_s, S, R, 7 - warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
+    // the sentiment rows of this thread's two columns: requested now, used after the content pass
+    const int c2 = threadIdx.x * 2;
+    float2 sv[kSentiDirectMax];
+    const bool senti_direct = p.sw != nullptr && S <= kSentiDirectMax;
+    if (senti_direct) {
+#pragma unroll
+      for (int l = 0; l < kSentiDirectMax; ++l)
+        sv[l] = l < S ? __ldg(reinterpret_cast<const float2*>(p.sw + ((long long)img * S + l) * H + c2)) : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    if (p.att) {
+      if (att_half) wsum_rows_reg<__half, RQ>(a16, L, sc_c, ring, warp, lane, 8);
+      else wsum_rows_reg<WideT, RQ>(aw, L, sc_c, ring, warp, lane, 8);
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < RQ; ++r) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float2 t = *reinterpret_cast<const float2*>(ring_base + w * AttnVariant<RT>::kRing + (r * H + c2) * sizeof(float));
+          acc.x += t.x;
+          acc.y += t.y;
+        }
+        p.cont_dst.store2(row0 + r, p.cont_col + c2, acc);
+      }
+    }
+    if (senti_direct) {
+#pragma unroll
+      for (int r = 0; r < RQ; ++r) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int l = 0; l < kSentiDirectMax; ++l)
+          if (l < S) {
+            const float w = sc_s[r * S + l];
+            acc.x = fmaf(w, sv[l].x, acc.x);
+            acc.y = fmaf(w, sv[l].y, acc.y);
+          }
+        p.senti_dst.store2(row0 + r, p.senti_col + c2, acc);
+      }
+    } else if (p.sw) {
+      weighted_sum<float, RT>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+    }
+    return;
+  }
+  // ---- shared-memory-query variant (other beam sizes)
+  if (p.att) {
+    if (fast) score_rows<__half, 1, RT>(p16, L, R, q_c, alpha_c, sc_c, ring, warp, lane, 8);
+    else score_rows<WideT, WIDE_MODE, RT>(pw, L, R, q_c, alpha_c, sc_c, ring, warp, lane, 8);
+  }
+  if (p.sw) score_rows<float, WIDE_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring, warp, lane, 8);
+  __syncthreads();
+  if (p.att) {  // the first rows of the weighted sum travel to L2 while the softmax runs
+    if (att_half) prefetch_first_rows(a16, L);
+    else prefetch_first_rows(aw, L);
+  }
+  if (p.att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
+  if (p.sw) softmax_rows(sc_s, S, R, warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
+  __syncthreads();
+  if (p.att) {
+    if (att_half) weighted_sum<__half, RT>(a16, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+    else weighted_sum<WideT, RT>(aw, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  }
+  if (p.sw) weighted_sum<float, RT>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (the 16-bit path, RT = 1 or 3 rows per image): the image's projected rows and then its feature rows
+// — two contiguous 196 KB blocks — are streamed through ONE 64 KB shared-memory ring of 8 KB chunks (8 rows) by bulk
+// asynchronous copies (cp.async.bulk ... mbarrier::complete_tx), issued by a single elected thread: no per-lane copy
+// instructions, no address arithmetic, no registers held, 56 KB in flight per CTA from the first instruction of the
+// kernel on — the stream starts BEFORE the queries are prepared and runs through the softmax between the two passes.
+// ncu on the per-warp cp.async version (B = 1024, beam 3): 16 % of the kernel's time went to the query set-up with HBM
+// idle, 39 % to the weighted sums, whose register-held global loads (32 KB in flight per SM) stalled on the long
+// scoreboard. Consumers: scoring, warp w takes row 8c + w of chunk c (register-resident queries, treduce8 over the
+// 8 chunks of a group); weighted sum, thread t owns columns 2t, 2t + 1 of all 8 rows of a chunk. full[slot] / empty[slot]
+// mbarriers; the producer thread (warp 0, lane 0) tops the ring up opportunistically (try_wait) and blocks only for the
+// chunk its own warp is about to consume. The sentiment words (11 fp32 rows) are read directly.
+// ---------------------------------------------------------------------------------------------------------------
+namespace bulk {
+__device__ __forceinline__ uint32_t s32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(s32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {  // bounded: a protocol bug traps, never hangs
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("isc attention: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(s32(bar))
+               : "memory");
+}
+}  // namespace bulk
+
+constexpr int kTmaSlots = 8;
+constexpr int kTmaChunkRows = 8;
+constexpr int kTmaRowBytes = H * 2;                               // 16-bit rows
+constexpr int kTmaChunkBytes = kTmaChunkRows * kTmaRowBytes;      // 8 KB
+constexpr int kTmaRingBytes = kTmaSlots * kTmaChunkBytes;         // 64 KB
+
+template <int PREC, int RT>
+__global__ void __launch_bounds__(256, 2) attention_tma_kernel(AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smraw[];
+  static_assert(RT == 1 || RT == 3, "register-resident queries: 1 or 3 rows per image");
+  constexpr int WIDE_MODE = PREC == ISC_PREC_BF16X3 ? 3 : 2;
+  typedef typename std::conditional<PREC == ISC_PREC_BF16, __nv_bfloat16, float>::type WideT;
+  typedef typename std::conditional<PREC == ISC_PREC_BF16, __nv_bfloat16, __half>::type AttT;  // 16-bit feature rows
+  constexpr int R = RT;
+  const int L = p.L, S = p.S;
+  const int Lp = (L + 3) & ~3, Sp = (S + 3) & ~3;
+  uint8_t* ring = smraw;                                      // [kTmaSlots][8 KB]; the wide path's per-warp rings otherwise
+  float* q_c = reinterpret_cast<float*>(smraw + kTmaRingBytes);  // [R][H]
+  float* q_s = q_c + R * H;
+  float* alpha_c = q_s + R * H;
+  float* alpha_s = alpha_c + H;
+  float* sc_c = alpha_s + H;       // [R][L]
+  float* sc_s = sc_c + R * Lp;     // [R][S]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sc_s + R * Sp + ((R * Sp) & 1));  // 8-byte aligned
+  uint64_t* empty = full + kTmaSlots;
+  const int img = blockIdx.x;
+  const long long row0 = (long long)img * R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTmaSlots; ++i) {
+      bulk::mbar_init(&full[i], 1);
+      bulk::mbar_init(&empty[i], 8);  // one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  const bool fast = p.flags == nullptr || p.flags[img] == 0;
+  const long long foff = (long long)img * L * H;
+  const uint8_t* src_p = reinterpret_cast<const uint8_t*>(p.p_att16) + foff * 2;
+  const uint8_t* src_a = (PREC == ISC_PREC_BF16 ? reinterpret_cast<const uint8_t*>(p.att) : reinterpret_cast<const uint8_t*>(p.att16)) + foff * 2;
+  const int n_ca = (L + kTmaChunkRows - 1) / kTmaChunkRows;  // chunks per tensor
+  const int n_chunks = (fast && p.att) ? 2 * n_ca : 0;
+  int next_issue = 0;  // producer state (warp 0, lane 0)
+  // issue every chunk up to `need` (blocking on a free slot) and, while slots are free, up to `want`
+  auto pump = [&](int need, int want) {
+    while (next_issue < n_chunks && next_issue <= want) {
+      const int c = next_issue, slot = c % kTmaSlots, round = c / kTmaSlots;
+      if (round > 0) {
+        const uint32_t par = (round - 1) & 1;
+        if (c <= need) bulk::mbar_wait(&empty[slot], par);
+        else if (!bulk::mbar_try_wait(&empty[slot], par)) break;
+      }
+      const int cc = c < n_ca ? c : c - n_ca;
+      const int rows = min(kTmaChunkRows, L - cc * kTmaChunkRows);
+      const uint8_t* src = (c < n_ca ? src_p : src_a) + (long long)cc * kTmaChunkBytes;
+      bulk::mbar_expect_tx(&full[slot], rows * kTmaRowBytes);
+      bulk::copy_g2s(ring + slot * kTmaChunkBytes, src, rows * kTmaRowBytes, &full[slot]);
+      ++next_issue;
+    }
+  };
+  const bool producer = warp == 0 && lane == 0;
+  if (producer) pump(-1, kTmaSlots - 1);  // the stream starts before the queries exist
+
   for (int i = threadIdx.x; i < R * H; i += 256) {
     int r = i / H, c = i - r * H;
     const float* hp = p.hproj + (row0 + r) * p.ld_hproj;
     const float qc = hp[c];
     const float qw = hp[H + c] + (p.pre_word ? p.pre_word[(long long)img * H + c] : 0.f);
-    // e-product modes keep the queries (like the projected features) as exp(-2 x); the fast path folds its feature
-    // scale 2^15 into the query
     q_c[i] = fast ? exp_neg2(qc) * (1.0f / kFastScale) : (WIDE_MODE == 3 ? exp_neg2_wide(qc) : qc);
     q_s[i] = WIDE_MODE == 3 ? exp_neg2_wide(qw) : qw;
   }
@@ -521,30 +900,156 @@ __global__ void __launch_bounds__(256, (RT == 1 || RT == 3) ? 2 : 3) attention_k
     alpha_s[i] = p.alpha_s[i];
   }
   __syncthreads();
-  const long long foff = (long long)img * L * H;
-  void* ring = ring_base + warp * AttnVariant<RT>::kRing;
-  if (p.att) {
-    if (fast)
-      score_dispatch<__half, 1, RT>(reinterpret_cast<const __half*>(p.p_att16) + foff, L, R, q_c, alpha_c, sc_c, ring, warp, lane);
-    else
-      score_dispatch<WideT, WIDE_MODE, RT>(reinterpret_cast<const WideT*>(p.p_att) + foff, L, R, q_c, alpha_c, sc_c, ring, warp, lane);
+  if (p.sw) score_senti_direct<WIDE_MODE, RT>(p.p_sw + (long long)img * S * H, S, q_s, alpha_s, sc_s, warp, lane);
+  if (p.att && !fast) {
+    // flagged image: full-width rows through per-warp cp.async rings (the ring memory is free: nothing was streamed)
+    score_dispatch<WideT, WIDE_MODE, RT>(reinterpret_cast<const WideT*>(p.p_att) + foff, L, R, q_c, alpha_c, sc_c,
+                                         ring + warp * kRingBytesReg, warp, lane);
+  } else if (p.att) {
+    using LD = FeatLoad<__half>;
+    constexpr int NV = 16;
+    float al[NV], q[RT][NV];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; j += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(alpha_c + LD::col(lane, i) + j);
+        al[i * 8 + j] = 2.0f * a.x; al[i * 8 + j + 1] = 2.0f * a.y; al[i * 8 + j + 2] = 2.0f * a.z; al[i * 8 + j + 3] = 2.0f * a.w;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          const float4 t = *reinterpret_cast<const float4*>(q_c + r * H + LD::col(lane, i) + j);
+          q[r][i * 8 + j] = t.x; q[r][i * 8 + j + 1] = t.y; q[r][i * 8 + j + 2] = t.z; q[r][i * 8 + j + 3] = t.w;
+        }
+      }
+    for (int g = 0; g * 8 < n_ca; ++g) {  // 8 chunks per group: slot = k, parity = g & 1
+      float acc[RT][8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = g * 8 + k;
+#pragma unroll
+        for (int r = 0; r < RT; ++r) acc[r][k] = 0.f;
+        if (c < n_ca) {  // block-uniform
+          if (producer) pump(c, c + kTmaSlots - 1);
+          __syncwarp();
+          bulk::mbar_wait(&full[k], g & 1);
+          const int l = c * kTmaChunkRows + warp;
+          if (l < L) {
+            float pv[NV];
+            const __half* row = reinterpret_cast<const __half*>(ring + k * kTmaChunkBytes + warp * kTmaRowBytes);
+            LD::load_shared(row, lane, 0, pv);
+            LD::load_shared(row, lane, 1, pv + 8);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+              float a = 0.f;
+#pragma unroll
+              for (int j = 0; j < NV; j += 2) a = score2_eprod(pv[j], pv[j + 1], q[r][j], q[r][j + 1], al[j], al[j + 1], a);
+              acc[r][k] = a;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) bulk::mbar_arrive(&empty[k]);
+        }
+      }
+      const int kk = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      const int lw = (g * 8 + kk) * kTmaChunkRows + warp;
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const float tot = treduce8(acc[r], lane);
+        if ((lane & 3) == 0 && lw < L) sc_c[r * L + lw] = tot;
+      }
+    }
   }
-  if (p.sw)
-    score_dispatch<float, WIDE_MODE, RT>(p.p_sw + (long long)img * S * H, S, R, q_s, alpha_s, sc_s, ring, warp, lane);
   __syncthreads();
-  const bool att_half = fast && p.att16 != nullptr;
-  if (p.att) {  // the first rows of the weighted sum travel to L2 while the softmax runs
-    if (att_half) prefetch_first_rows(reinterpret_cast<const __half*>(p.att16) + foff, L);
-    else prefetch_first_rows(reinterpret_cast<const WideT*>(p.att) + foff, L);
-  }
   if (p.att) softmax_rows(sc_c, L, R, warp, lane, 8, p.cont_w, p.ld_cont_w, row0);
   if (p.sw) softmax_rows(sc_s, S, R, warp, lane, 8, p.senti_w, p.ld_senti_w, row0);
-  __syncthreads();
-  if (p.att) {
-    if (att_half) weighted_sum<__half, RT>(reinterpret_cast<const __half*>(p.att16) + foff, L, R, sc_c, p.cont_dst, row0, p.cont_col);
-    else weighted_sum<WideT, RT>(reinterpret_cast<const WideT*>(p.att) + foff, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  // the sentiment rows of this thread's two columns: requested now, used after the content pass (latency hidden)
+  const int c2 = threadIdx.x * 2;
+  float2 sv[kSentiDirectMax];
+  const bool senti_direct = p.sw != nullptr && S <= kSentiDirectMax;
+  if (senti_direct) {
+#pragma unroll
+    for (int l = 0; l < kSentiDirectMax; ++l)
+      sv[l] = l < S ? __ldg(reinterpret_cast<const float2*>(p.sw + ((long long)img * S + l) * H + c2)) : make_float2(0.f, 0.f);
   }
-  if (p.sw) weighted_sum<float, RT>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+  __syncthreads();
+  if (p.att && !fast) {
+    weighted_sum<WideT, RT>(reinterpret_cast<const WideT*>(p.att) + foff, L, R, sc_c, p.cont_dst, row0, p.cont_col);
+  } else if (p.att) {
+    float2 acc[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r] = make_float2(0.f, 0.f);
+    for (int cc = 0; cc < n_ca; ++cc) {
+      const int c = n_ca + cc, slot = c % kTmaSlots;
+      if (producer) pump(c, c + kTmaSlots - 1);
+      __syncwarp();
+      bulk::mbar_wait(&full[slot], (c / kTmaSlots) & 1);
+      const AttT* chunk = reinterpret_cast<const AttT*>(ring + slot * kTmaChunkBytes) + c2;
+      const int l0 = cc * kTmaChunkRows;
+      float2 a[kTmaChunkRows];
+      if (l0 + kTmaChunkRows <= L) {
+#pragma unroll
+        for (int u = 0; u < kTmaChunkRows; ++u) {
+          const unsigned v = *reinterpret_cast<const unsigned*>(chunk + u * H);
+          a[u] = PREC == ISC_PREC_BF16 ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v))
+                                       : __half22float2(*reinterpret_cast<const __half2*>(&v));
+        }
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float4 w = *reinterpret_cast<const float4*>(sc_c + r * L + l0 + 4 * hh);
+            acc[r].x = fmaf(w.x, a[4 * hh].x, acc[r].x); acc[r].y = fmaf(w.x, a[4 * hh].y, acc[r].y);
+            acc[r].x = fmaf(w.y, a[4 * hh + 1].x, acc[r].x); acc[r].y = fmaf(w.y, a[4 * hh + 1].y, acc[r].y);
+            acc[r].x = fmaf(w.z, a[4 * hh + 2].x, acc[r].x); acc[r].y = fmaf(w.z, a[4 * hh + 2].y, acc[r].y);
+            acc[r].x = fmaf(w.w, a[4 * hh + 3].x, acc[r].x); acc[r].y = fmaf(w.w, a[4 * hh + 3].y, acc[r].y);
+          }
+        }
+      } else {
+        for (int u = 0; l0 + u < L; ++u) {
+          const unsigned v = *reinterpret_cast<const unsigned*>(chunk + u * H);
+          const float2 x = PREC == ISC_PREC_BF16 ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v))
+                                                 : __half22float2(*reinterpret_cast<const __half2*>(&v));
+#pragma unroll
+          for (int r = 0; r < RT; ++r) {
+            const float w = sc_c[r * L + l0 + u];
+            acc[r].x = fmaf(w, x.x, acc[r].x);
+            acc[r].y = fmaf(w, x.y, acc[r].y);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) bulk::mbar_arrive(&empty[slot]);
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) p.cont_dst.store2(row0 + r, p.cont_col + c2, acc[r]);
+  }
+  if (senti_direct) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int l = 0; l < kSentiDirectMax; ++l)
+        if (l < S) {
+          const float w = sc_s[r * S + l];
+          acc.x = fmaf(w, sv[l].x, acc.x);
+          acc.y = fmaf(w, sv[l].y, acc.y);
+        }
+      p.senti_dst.store2(row0 + r, p.senti_col + c2, acc);
+    }
+  } else if (p.sw) {
+    weighted_sum<float, RT>(p.sw + (long long)img * S * H, S, R, sc_s, p.senti_dst, row0, p.senti_col);
+  }
+}
+
+template <int PREC>
+static int launch_attention_tma(const AttnParams& p, int B, cudaStream_t stream) {
+  const int Lp = (p.L + 3) & ~3, Sp = (p.S + 3) & ~3;
+  const size_t smem = kTmaRingBytes + sizeof(float) * (2 * p.R * H + 2 * H + p.R * Lp + p.R * Sp + 2) + 2 * kTmaSlots * sizeof(uint64_t);
+  void (*k)(AttnParams) = p.R == 1 ? attention_tma_kernel<PREC, 1> : attention_tma_kernel<PREC, 3>;
+  ISC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISC_CUDA(launch_pdl(k, dim3(B), dim3(256), smem, stream, p));
+  ISC_LAUNCH_CHECK();
+  return 0;
 }
 
 template <int PREC>
@@ -576,6 +1081,14 @@ int launch_attention(const AttnParams& p, int B, int precision, cudaStream_t str
   const double bytes = (double)B * ((p.att ? p.L * H * feat_b : 0.0) + (p.sw ? 2.0 * p.S * H * 4.0 : 0.0) +
                                     (double)p.R * (3.0 * H * 4.0 + 2.0 * H * 4.0));
   ProfScope ps(ISC_K_ATTENTION, bytes, stream);
+  // TMA-staged kernel (measured slower than the per-warp rings, kept behind ISC_ATTN_TMA=1): the 16-bit copies exist,
+  // 1 or 3 rows per image, 16-byte aligned score rows
+  static const bool tma_on = getenv("ISC_ATTN_TMA") && atoi(getenv("ISC_ATTN_TMA")) != 0;
+  const bool tma_ok = tma_on && fastp && p.att && (p.R == 1 || p.R == 3) && (p.L % 4) == 0 &&
+                      (precision == ISC_PREC_BF16 || p.att16 != nullptr) &&
+                      (reinterpret_cast<uintptr_t>(p.p_att16) % 16) == 0 &&
+                      (reinterpret_cast<uintptr_t>(precision == ISC_PREC_BF16 ? p.att : p.att16) % 16) == 0;
+  if (tma_ok) return precision == ISC_PREC_BF16 ? launch_attention_tma<ISC_PREC_BF16>(p, B, stream) : launch_attention_tma<ISC_PREC_BF16X3>(p, B, stream);
   if (precision == ISC_PREC_BF16) return launch_attention_t<ISC_PREC_BF16>(p, B, smem, stream);
   if (precision == ISC_PREC_BF16X3) return launch_attention_t<ISC_PREC_BF16X3>(p, B, smem, stream);
   return launch_attention_t<ISC_PREC_FP32>(p, B, smem, stream);

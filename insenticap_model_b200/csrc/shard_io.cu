@@ -21,6 +21,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/isc.h"
@@ -48,7 +49,8 @@ struct Shard {
   std::unordered_map<std::string, int64_t> index;
 };
 
-size_t elem_bytes(uint32_t dtype) { return dtype == ISC_SHARD_BF16 ? 2 : 4; }
+size_t elem_bytes(uint32_t dtype) { return dtype == ISC_SHARD_F32 ? 4 : 2; }
+bool known_dtype(uint32_t dtype) { return dtype == ISC_SHARD_F32 || dtype == ISC_SHARD_BF16 || dtype == ISC_SHARD_F16; }
 uint64_t round_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 uint16_t f32_to_bf16_rne(float f) {  // same rounding as __float2bfloat16_rn (NaN kept quiet)
@@ -77,7 +79,7 @@ extern "C" {
 int isc_shard_write(const char* path, int dtype, int feat_dim, int n_regions, int64_t n_images, const char* const* names,
                     const float* fc_feats, const float* att_feats) {
   ISC_REQUIRE(path && names && fc_feats && att_feats, "shard_write: NULL argument");
-  ISC_REQUIRE((dtype == ISC_SHARD_F32 || dtype == ISC_SHARD_BF16) && feat_dim > 0 && n_regions > 0 && n_images > 0,
+  ISC_REQUIRE(known_dtype((uint32_t)dtype) && feat_dim > 0 && n_regions > 0 && n_images > 0,
               "shard_write: bad dtype / dims");
   ShardHeader h;
   memset(&h, 0, sizeof(h));
@@ -112,10 +114,14 @@ int isc_shard_write(const char* path, int dtype, int feat_dim, int n_regions, in
     if (h.dtype == ISC_SHARD_F32) {
       memcpy(rec.data(), fc, (size_t)feat_dim * 4);
       memcpy(rec.data() + (size_t)feat_dim * 4, att, (size_t)n_regions * feat_dim * 4);
-    } else {
+    } else if (h.dtype == ISC_SHARD_BF16) {
       uint16_t* o = reinterpret_cast<uint16_t*>(rec.data());
       for (int j = 0; j < feat_dim; ++j) o[j] = f32_to_bf16_rne(fc[j]);
       for (uint64_t j = 0; j < (uint64_t)n_regions * feat_dim; ++j) o[feat_dim + j] = f32_to_bf16_rne(att[j]);
+    } else {  // IEEE half, round to nearest even (cuda_fp16.h's host conversion)
+      __half* o = reinterpret_cast<__half*>(rec.data());
+      for (int j = 0; j < feat_dim; ++j) o[j] = __float2half_rn(fc[j]);
+      for (uint64_t j = 0; j < (uint64_t)n_regions * feat_dim; ++j) o[feat_dim + j] = __float2half_rn(att[j]);
     }
     ok = fwrite(rec.data(), h.record_bytes, 1, f) == 1;
   }
@@ -155,7 +161,7 @@ int isc_shard_open(const char* path, isc_shard_t* out) {
   memcpy(&s->h, s->map, sizeof(ShardHeader));
   const ShardHeader& h = s->h;
   const bool sane = memcmp(h.magic, "ISCFEAT1", 8) == 0 && h.version == 1 &&
-                    (h.dtype == ISC_SHARD_F32 || h.dtype == ISC_SHARD_BF16) && h.feat_dim > 0 && h.n_regions > 0 && h.feat_dim <= (1u << 24) && h.n_regions <= (1u << 24) &&
+                    known_dtype(h.dtype) && h.feat_dim > 0 && h.n_regions > 0 && h.feat_dim <= (1u << 24) && h.n_regions <= (1u << 24) &&
                     h.record_bytes >= (uint64_t)h.feat_dim * (1 + (uint64_t)h.n_regions) * elem_bytes(h.dtype) &&
                     // every bound is checked without a product or sum that could wrap for a crafted header
                     h.record_bytes > 0 && h.names_bytes <= s->map_bytes - sizeof(ShardHeader) &&

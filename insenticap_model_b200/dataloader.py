@@ -27,7 +27,7 @@ from torch.utils import data
 
 from . import _lib
 
-_DTYPES = {"fp32": 0, "bf16": 1}
+_DTYPES = {"fp32": 0, "bf16": 1, "fp16": 2}
 
 
 class FeatureShard:
@@ -43,7 +43,7 @@ class FeatureShard:
         n, d, l, dt = C.c_int64(), C.c_int(), C.c_int(), C.c_int()
         _lib.check(lib.isc_shard_info(h, C.byref(n), C.byref(d), C.byref(l), C.byref(dt)), "isc_shard_info")
         self.n_images, self.feat_dim, self.n_regions = n.value, d.value, l.value
-        self.dtype = torch.bfloat16 if dt.value == 1 else torch.float32
+        self.dtype = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[dt.value]
         self.direct_device = None  # set by pin(): batches are then DMA'd from the page cache, no staging copy
         g = math.isqrt(self.n_regions)
         self.att_shape = (g, g, self.feat_dim) if g * g == self.n_regions else (self.n_regions, self.feat_dim)
@@ -132,7 +132,7 @@ class FeatureShard:
 
     def __getitem__(self, fn):
         fc, att = self.gather([self.index(fn)], threads=1, pin=False)
-        if self.dtype == torch.bfloat16:
+        if self.dtype != torch.float32:
             fc, att = fc.float(), att.float()
         return fc[0].numpy(), att[0].numpy()
 

@@ -178,6 +178,7 @@ class Detector(nn.Module):
             if training:
                 optim = self._optim()
                 optim.zero_grad()
+                optim.begin_iteration(2 + (data_type == "fact"))  # sampled re-score + seq2seq (+ xe) backward nodes
                 cap_loss.backward()
                 optim.step()  # clip_gradient (+-0.1) and Adam in one kernel
 

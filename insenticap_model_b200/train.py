@@ -84,6 +84,70 @@ class FusedClampAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
         self.steps = 0
         model._packed_key = None
+        # gradient sink (captioner._TeacherForced.backward): name -> slice of the flat gradient, bucket boundaries
+        self._slices, off = {}, 0
+        for name, p in model.named_parameters():
+            self._slices[name] = (off, p.numel(), tuple(p.shape))
+            off += p.numel()
+        self._pending_nodes = 0   # captioner backward nodes still to run in this iteration (begin_iteration)
+        self._async = []          # (work handle) of all-reduces already in flight
+        self._reduced = []        # [(lo, hi)] ranges of flat_g already handed to the collective
+        self._comm_stream = None
+        self._marks = None
+        self.overlap = True
+        self.overlap_note = None
+        if hasattr(model, "forward_rl"):  # a Captioner: its backward adds straight into flat_g
+            model._grad_sink = self
+
+    # ---- gradient sink -------------------------------------------------------------------------------------------
+    def accepts(self, dev, shapes):
+        return self.flat_g.device == dev and self.flat_g.is_cuda
+
+    def grad_slice(self, name):
+        off, n, _ = self._slices[name]
+        return self.flat_g[off:off + n]
+
+    def begin_iteration(self, n_nodes):
+        """Called by the iteration drivers before backward(): ``n_nodes`` captioner forward passes carry gradients. The
+        LAST of their backward nodes to run gets the gradient-ready marks (isc_train_backward_marks)."""
+        self._pending_nodes = int(n_nodes)
+        self._async, self._reduced = [], []
+
+    def _world(self):
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def node_starting(self):
+        self._pending_nodes -= 1
+        if self._pending_nodes != 0 or not self.overlap or self._world() <= 1:
+            return None
+        if self._marks is None:
+            self._marks = (torch.cuda.Event(), torch.cuda.Event())
+            for ev in self._marks:
+                ev.record()  # creates the CUDA events (torch makes them lazily); the library re-records them
+            self._comm_stream = torch.cuda.Stream(self.flat_g.device)
+        return self._marks
+
+    def _bucket_bounds(self):
+        """Flat-buffer ranges that are final at mark 0 / mark 1 of isc_train_backward (named_parameters order: ...,
+        att_lstm.*, att2att, senti2att, attention.cont_att.*, attention.senti_att.*, attention.{h2att,...}, lang_lstm.*,
+        classifier.*): the tail from attention.h2att on, then the att_lstm block."""
+        tail_lo = self._slices["attention.h2att.weight"][0]
+        a_lo = self._slices["att_lstm.weight_ih"][0]
+        last = self._slices["att_lstm.bias_hh"]
+        return (tail_lo, self.flat_g.numel()), (a_lo, last[0] + last[1])
+
+    def node_done(self, marks):
+        """After the node's launches are queued: all-reduce each final bucket on the side stream as soon as its event
+        fires, i.e. under the remaining backward work of this node."""
+        if marks is None:
+            return
+        for ev, (lo, hi) in zip(marks, self._bucket_bounds()):
+            self._comm_stream.wait_event(ev)
+            with torch.cuda.stream(self._comm_stream):
+                self._async.append(dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._reduced.append((lo, hi))
 
     # -- torch.optim.Optimizer surface the reference's scripts use: param_groups[...]['lr'] for the learning-rate decay
     #    (train_xe.py:130-133), state_dict()/load_state_dict() for checkpoint save / resume (train_xe.py:53, :245)
@@ -133,7 +197,31 @@ class FusedClampAdam:
         if not self.flat_p.is_cuda:
             raise RuntimeError("FusedClampAdam.step runs on the GPU only (isc_adam_step); there is no CPU fallback")
         self._gather_grads()
-        world = allreduce_gradients(self.flat_g, self.group)
+        if self._reduced and self._pending_nodes != 0:
+            raise RuntimeError("FusedClampAdam: begin_iteration() announced fewer backward nodes than ran; gradients were "
+                               "added after their bucket's all-reduce had started")
+        if self._reduced:
+            # buckets already in flight (started inside the last backward node): reduce what is left — the head of the
+            # buffer and the slice between the two buckets —, then join the asynchronous ones
+            world = self._world()
+            done = sorted(self._reduced)
+            pos, rest = 0, []
+            for lo, hi in done:
+                if lo > pos:
+                    rest.append((pos, lo))
+                pos = hi
+            if pos < self.flat_g.numel():
+                rest.append((pos, self.flat_g.numel()))
+            for lo, hi in rest:
+                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            for work in self._async:
+                work.wait()
+            n_async = sum(hi - lo for lo, hi in done)
+            self.overlap_note = "all-reduce in %d buckets: %.0f %% of the gradient started inside the backward" % (
+                len(done) + len(rest), 100.0 * n_async / self.flat_g.numel())
+            self._async, self._reduced = [], []
+        else:
+            world = allreduce_gradients(self.flat_g, self.group)
         self.steps += 1
         lib = _lib.load()
         with torch.cuda.device(self.flat_p.device):
@@ -153,6 +241,8 @@ def xe_iteration(model, optim, batch, seq2seq_batch=None, ss_prob=0.0, fused_los
     xe_crit, da_crit = XECriterion(), nn.MSELoss()
     fc, att, caps, lengths, cpts, labels = batch
     optim.zero_grad()
+    if hasattr(optim, "begin_iteration"):
+        optim.begin_iteration(1 + (seq2seq_batch is not None))
     if fused_loss:
         xe_loss = model.xe_loss(fc, att, cpts, caps, labels, lengths, ss_prob)
     else:
@@ -184,6 +274,8 @@ def rl_iteration(model, optim, scorer, batch, max_seq_len=16, seq2seq_batch=None
     fns, fc, att, caps, lengths, cpts, sentis, labels, ground_truth = batch
     rl_crit, xe_crit, da_crit = RewardCriterion(), XECriterion(), nn.MSELoss()
     optim.zero_grad()
+    if hasattr(optim, "begin_iteration"):
+        optim.begin_iteration(1 + (caps is not None) + (seq2seq_batch is not None))
     R = int(samples_per_image)
     rep = (lambda x: x.repeat_interleave(R, dim=0)) if R > 1 else (lambda x: x)
     s_fns = [fn for fn in fns for _ in range(R)]

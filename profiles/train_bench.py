@@ -59,21 +59,50 @@ else:
     step = lambda: TR.xe_iteration(m, optim, batch, s2s)
     rows = B
 
-for _ in range(2):
-    out = step()
-torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
+def timed(n):
+    for _ in range(2):
+        o = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        o = step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), o
+
+
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters):
-    out = step()
-e1.record()
-torch.cuda.synchronize()
-ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev, dtype=torch.float64)
+ms_val, out = timed(iters)  # gradient all-reduce in buckets started inside the backward (the default)
+ms = torch.tensor([ms_val], device=dev, dtype=torch.float64)
+comm = {"allreduce_ms": None, "allreduce_busbw_gbs": None, "ms_per_iteration_no_overlap": None, "overlap": optim.overlap_note}
+if world > 1:
+    optim.overlap = False  # one blocking all-reduce of the flat gradient after the backward (round 1's scheme)
+    comm["ms_per_iteration_no_overlap"], _ = timed(iters)
+    optim.overlap = True
+    buf = torch.zeros_like(optim.flat_g)
+    for _ in range(2):
+        dist.all_reduce(buf)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(5):
+        dist.all_reduce(buf)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    comm["allreduce_ms"] = float(t.item())
+    comm["allreduce_busbw_gbs"] = 2.0 * (world - 1) / world * buf.numel() * 4 / (float(t.item()) * 1e-3) / 1e9
+    comm["grad_bytes"] = buf.numel() * 4
+    del buf
 chk = optim.flat_p.double().sum().reshape(1)
 if world > 1:
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     lo, hi = chk.clone(), chk.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX)
@@ -84,7 +113,7 @@ if rank == 0:
     print(json.dumps({"workload": what, "n_gpus": world, "batch_per_gpu": B, "samples_per_image": spi if what == "rl" else None,
                       "ms_per_iteration": float(ms.item()), "rows_per_s": world * rows / (float(ms.item()) * 1e-3),
                       "losses": {k: float(v) for k, v in out.items()}, "replicas_in_sync": in_sync,
-                      "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}), flush=True)
+                      "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9, **comm}), flush=True)
 # per-kernel-class device time of one more iteration (CUDA events around every launch of the library)
 if rank == 0 and os.environ.get("ISC_TRAIN_PROFILE"):
     import ctypes as C

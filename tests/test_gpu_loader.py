@@ -22,7 +22,7 @@ def corpus(tmp_path_factory):
     fc, att, cpts, sentis, labels = syn.synthetic_inputs(N, V, seed=12)
     names = ["img%03d" % i for i in range(N)]
     d = tmp_path_factory.mktemp("shards")
-    paths = {k: dl.FeatureShard.write(str(d / (k + ".iscf")), names, fc, att, dtype=k) for k in ("fp32", "bf16")}
+    paths = {k: dl.FeatureShard.write(str(d / (k + ".iscf")), names, fc, att, dtype=k) for k in ("fp32", "bf16", "fp16")}
     meta = dict(names=names, fc=fc, att=att, concepts={fn: cpts[i].tolist() for i, fn in enumerate(names)},
                 sentiments={fn: sentis[i].tolist() for i, fn in enumerate(names)},
                 labels=[(fn, int(labels[i])) for i, fn in enumerate(names)], sentis=sentis, lab=labels)
@@ -90,3 +90,34 @@ def test_pinned_shard_collates_straight_into_device_tensors(corpus):
             assert labels.is_cuda and labels.tolist() == [l for _, l in meta["labels"][seen:seen + n]]
             seen += n
         assert seen == N
+
+
+def test_fp16_shard_is_the_fp32_computation_on_the_stored_values(corpus):
+    """A fp16 feature shard halves the host->device bytes in EVERY precision: fp16 values are fp32 values (isc_expand_f16 is
+    exact) and fit the split-bf16 GEMM operands exactly, so decoding the shard's tensors — device tensors, or pinned host
+    tensors through the pipelined host path — is bit-identical to decoding their fp32 widening, and token-exact against the
+    CPU oracle run on those same values."""
+    import numpy as np
+    from oracle import captioner_oracle as O
+    paths, meta = corpus
+    sh = dl.FeatureShard(paths["fp16"])
+    fc16, att16 = sh.gather(range(N))
+    assert fc16.dtype == torch.float16 and fc16.is_pinned() and torch.equal(fc16, meta["fc"].half())
+    sentis, lab = meta["sentis"], meta["lab"]
+    for precision in ("bf16x3", "bf16"):
+        m = _captioner(precision)
+        with torch.no_grad():
+            want = [x.clone() for x in m.beam_search(fc16.float().cuda(), att16.float().cuda(), sentis.cuda(), lab.cuda(), 3, 1, 16)]
+            got = m.beam_search(fc16.cuda(), att16.cuda(), sentis.cuda(), lab.cuda(), 3, 1, 16)
+            assert all(torch.equal(a, b) for a, b in zip(got, want))
+            got_h = m.beam_search(fc16, att16, sentis, lab, 3, 1, 16, host_chunk=8)
+            assert all(torch.equal(a.cuda(), b) for a, b in zip(got_h, want))
+    m = _captioner("bf16x3")
+    p = syn.synthetic_state_dict(V, 2)
+    with torch.no_grad():
+        got = m.beam_search(fc16.cuda(), att16.cuda(), sentis.cuda(), lab.cuda(), 3, 1, 16)
+        f = O.prologue(p, fc16.float(), att16.float(), None, sentis, lab)
+        tk_o, sc_o, ln_o, margin = O.beam_search(p, f, N, 3, 1, 16, return_margins=True)
+    if margin > 1e-5:
+        assert np.array_equal(got[0].cpu().numpy(), tk_o.numpy())
+        np.testing.assert_allclose(got[1].cpu().numpy(), sc_o.numpy(), atol=2e-4)

@@ -85,7 +85,7 @@ def _numpy_parse(path):
     return [s.decode() for s in names], elems[:, :d], elems[:, d:].reshape(n, l, d), data_off, rec
 
 
-@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("dtype", ["fp32", "bf16", "fp16"])
 def test_shard_round_trip_against_numpy_parse(tmp_path, dtype):
     n, d, l = 37, 24, 9
     g = torch.Generator().manual_seed(3)
@@ -104,8 +104,9 @@ def test_shard_round_trip_against_numpy_parse(tmp_path, dtype):
             assert torch.equal(gfc, fc[idx]) and torch.equal(gatt, att[idx])
             assert np.array_equal(gfc.numpy(), pfc[idx])
         else:
-            assert gfc.dtype == torch.bfloat16
-            assert torch.equal(gfc, fc[idx].bfloat16()) and torch.equal(gatt, att[idx].bfloat16())  # round-to-nearest-even
+            tdt = torch.bfloat16 if dtype == "bf16" else torch.float16
+            assert gfc.dtype == tdt
+            assert torch.equal(gfc, fc[idx].to(tdt)) and torch.equal(gatt, att[idx].to(tdt))  # round-to-nearest-even
             assert np.array_equal(gfc.view(torch.int16).numpy().view(np.uint16), pfc[idx])
             assert np.array_equal(gatt.view(torch.int16).numpy().view(np.uint16).reshape(len(idx), l, d), patt[idx])
     only_att = sh.gather([1, 2], want_fc=False, pin=False)
