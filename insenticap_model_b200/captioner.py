@@ -220,6 +220,8 @@ class Captioner(nn.Module):
         # caller may keep results across calls like with the reference, False hands out the graph's own buffers
         self.graph_outputs_fresh = True
         self._graphs = {}
+        self._host_graphs = {}
+        self.use_host_graphs = True  # host-tensor beam_search: replay a captured graph per sub-batch (two staging sets)
         self._copy_stream = None
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
         self.fc_feats = self.cpt_feats = None
@@ -251,6 +253,7 @@ class Captioner(nn.Module):
             # a captured CUDA graph holds the raw address of the workspace it was captured with: growing the buffer
             # frees that block, so every graph captured so far is dropped (recaptured on its next use)
             self._graphs.clear()
+            self._host_graphs.clear()
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
             self._ws[key] = buf
         return buf
@@ -695,33 +698,99 @@ class Captioner(nn.Module):
             return tuple(o.clone() for o in hit[1])
         return hit[1]
 
+    def _host_graph(self, inputs, n, K, constraint, T, dev):
+        """Per (sub-batch shape, dtypes, beam, length) TWO staging sets — device input tensors, device outputs and a CUDA
+        graph of the whole device-side call on them (~190 launches): the pipelined host path replays a graph per sub-batch
+        instead of launching eagerly (no per-launch host cost, and the copy engine only ever waits for a free set)."""
+        self.pack_weights()
+        key = tuple((tuple(x.shape[1:]), x.dtype) if x is not None else None for x in inputs) + (
+            int(n), K, int(bool(constraint)), T, self._packed_key)
+        hit = self._host_graphs.get(key)
+        if hit is None:
+            if len(self._host_graphs) >= 4:
+                self._host_graphs.clear()
+            sets = []
+            for _ in range(2):
+                stage = [torch.empty((n,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev) if x is not None else None
+                         for x in inputs]
+                for t in stage:
+                    if t is not None:
+                        t.zero_()  # valid word ids / finite features for the sizing and capture runs
+                if stage[3] is not None:
+                    stage[3].fill_(0)
+                out = (torch.empty(n, K, T, dtype=torch.long, device=dev), torch.empty(n, K, dtype=torch.float64, device=dev),
+                       torch.empty(n, K, dtype=torch.int32, device=dev))
+                self._beam_search_device(*stage, K, constraint, T, out=out)  # sizes the workspaces outside the capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._beam_search_device(*stage, K, constraint, T, out=out)
+                sets.append((stage, out, g))
+            hit = self._host_graphs[key] = (sets, tuple(self._ws.values()), self._packed)
+        return hit[0]
+
     def _beam_search_host(self, fc_feats, att_feats, senti_words, senti_labels, beam_size, decoding_constraint,
                           max_seq_len, host_chunk):
         dev = self._device()
         B, K, T = fc_feats.shape[0], int(beam_size), int(max_seq_len)
+        n = min(int(host_chunk), B)
+        inputs = (fc_feats, att_feats, senti_words, senti_labels)
         cur = torch.cuda.current_stream(dev)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
-        cs.wait_stream(cur)
-        staged = []
-        for lo in range(0, B, int(host_chunk)):  # enqueue every H2D copy up front: the copy engine runs ahead
-            hi = min(B, lo + int(host_chunk))
-            with torch.cuda.stream(cs):
-                d = [x[lo:hi].to(dev, non_blocking=True) if x is not None else None
-                     for x in (fc_feats, att_feats, senti_words, senti_labels)]
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            staged.append((lo, hi, d, ev))
         tokens = torch.empty(B, K, T, dtype=torch.long, device=dev)
         scores = torch.empty(B, K, dtype=torch.float64, device=dev)
         lengths = torch.empty(B, K, dtype=torch.int32, device=dev)
-        for lo, hi, d, ev in staged:
-            cur.wait_event(ev)
-            for x in d:
-                if x is not None:
-                    x.record_stream(cur)
-            self._beam_search_device(*d, K, decoding_constraint, T, out=(tokens[lo:hi], scores[lo:hi], lengths[lo:hi]))
+        chunks = [(lo, min(B, lo + n)) for lo in range(0, B, n)]
+        sets = self._host_graph(inputs, n, K, decoding_constraint, T, dev) if self.use_host_graphs else None
+        cs.wait_stream(cur)
+        if sets is None:
+            staged = []
+            for lo, hi in chunks:  # enqueue every H2D copy up front: the copy engine runs ahead
+                with torch.cuda.stream(cs):
+                    d = [x[lo:hi].to(dev, non_blocking=True) if x is not None else None for x in inputs]
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                staged.append((lo, hi, d, ev))
+            for lo, hi, d, ev in staged:
+                cur.wait_event(ev)
+                for x in d:
+                    if x is not None:
+                        x.record_stream(cur)
+                self._beam_search_device(*d, K, decoding_constraint, T, out=(tokens[lo:hi], scores[lo:hi], lengths[lo:hi]))
+        else:
+            # two staging sets: the copy of sub-batch i + 2 waits (on the device) until the replay of sub-batch i has read
+            # its set; with the decode of a sub-batch shorter than its copy, the copy engine never idles
+            ready, consumed = {}, {}
+
+            def copy_in(i):
+                lo, hi = chunks[i]
+                stage = sets[i % 2][0]
+                with torch.cuda.stream(cs):
+                    if i % 2 in consumed:
+                        cs.wait_event(consumed[i % 2])
+                    for dst, src in zip(stage, inputs):
+                        if dst is not None:
+                            dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                ready[i] = ev
+
+            for i in range(min(2, len(chunks))):
+                copy_in(i)
+            for i, (lo, hi) in enumerate(chunks):
+                stage, out, g = sets[i % 2]
+                cur.wait_event(ready[i])
+                g.replay()  # a short last sub-batch decodes the set's stale tail rows too; only [lo, hi) is kept
+                tokens[lo:hi].copy_(out[0][:hi - lo])
+                scores[lo:hi].copy_(out[1][:hi - lo])
+                lengths[lo:hi].copy_(out[2][:hi - lo])
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                consumed[i % 2] = ev
+                if i + 2 < len(chunks):
+                    copy_in(i + 2)
         outs = []
         for x in (tokens, scores, lengths):
             h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
