@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(NT) greedy_select_kernel(GreedyParams p) {
 // Pool the candidates of an image's rows with its carried finished beams and keep the K best by fp64 score,
 // stably (captioner.py:404-409); then write the new beam state. Called by every thread of ONE block per image,
 // after the rows' candidates (cand_lp / cand_word / cand_count) are visible.
-__device__ __forceinline__ void beam_pool(const BeamParams& p, int b) {
+// s_lp / s_word / s_cnt: the rows' candidates in SHARED memory (fused merge kernel: [K][KMAX] / [K]); null = read the
+// global scratch the unfused row CTAs published them to.
+__device__ __forceinline__ void beam_pool(const BeamParams& p, int b, const float* s_lp = nullptr, const int* s_word = nullptr,
+                                          const int* s_cnt = nullptr) {
   __shared__ int sel_parent[KMAX], sel_word[KMAX], sel_n;
   const int K = p.K, t = p.t, T = p.T;
   if (threadIdx.x == 0) {
@@ -177,12 +180,12 @@ __device__ __forceinline__ void beam_pool(const BeamParams& p, int b) {
         pool_word[n] = -1;
         ++n;
       } else {
-        const int cnt = __ldcg(p.cand_count + mm);
+        const int cnt = s_cnt ? s_cnt[kk] : __ldcg(p.cand_count + mm);
         for (int r = 0; r < cnt; ++r) {
           // python-float running sum of fp32 log-probs (captioner.py:404-407)
-          pool_score[n] = base + (double)__ldcg(p.cand_lp + mm * KMAX + r);
+          pool_score[n] = base + (double)(s_lp ? s_lp[kk * KMAX + r] : __ldcg(p.cand_lp + mm * KMAX + r));
           pool_parent[n] = kk;
-          pool_word[n] = __ldcg(p.cand_word + mm * KMAX + r);
+          pool_word[n] = s_word ? s_word[kk * KMAX + r] : __ldcg(p.cand_word + mm * KMAX + r);
           ++n;
         }
       }
@@ -419,12 +422,16 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
   constexpr int SEL_REC = sel_rec(SEL_K);
   pdl_trigger();
   pdl_wait();
+  // the rows' candidates stay in shared memory (the pooling thread used to read them back from global scratch)
+  __shared__ float s_lp[KMAX * KMAX];
+  __shared__ int s_word[KMAX * KMAX], s_cnt[KMAX];
   const int b = blockIdx.x, K = p.K, t = p.t;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int kk = warp; kk < K; kk += 4) {
     const int m = b * K + kk;
     const bool alive = p.alive_in[m] != 0;
     const bool finished = alive && t > 0 && (int)p.it[m] == p.eos_id;
+    if (lane == 0) s_cnt[kk] = 0;
     if (alive && !finished) {
       float mx, lse, v[SEL_K];
       int w[SEL_K];
@@ -435,18 +442,17 @@ __global__ void __launch_bounds__(128) beam_merge_kernel(BeamParams p) {
 #pragma unroll
         for (int r = 0; r < SEL_K; ++r) {
           if (r < K && v[r] > -CUDART_INF_F) {
-            p.cand_lp[m * KMAX + r] = (v[r] - mx) - lse;  // log_softmax value, fp32 like the reference
-            p.cand_word[m * KMAX + r] = w[r];
+            s_lp[kk * KMAX + r] = (v[r] - mx) - lse;  // log_softmax value, fp32 like the reference
+            s_word[kk * KMAX + r] = w[r];
             cnt = r + 1;
           }
         }
-        p.cand_count[m] = cnt;
+        s_cnt[kk] = cnt;
       }
     }
   }
-  __threadfence_block();
   __syncthreads();
-  beam_pool(p, b);
+  beam_pool(p, b, s_lp, s_word, s_cnt);
   if (p.h_state) {  // the next step's operand rows of this image's beams, read through the parents chosen above
     __syncthreads();
     const int c = threadIdx.x * 4;
