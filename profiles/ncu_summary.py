@@ -5,8 +5,8 @@ import sys
 
 WANT = [("us", "gpu__time_duration.sum"), ("dram_rd_MB", "dram__bytes_read.sum"), ("dram_wr_MB", "dram__bytes_write.sum"),
         ("dram_%", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-        ("tensor_%", "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
-        ("hmma_ops_%", "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"),
+        ("tc_pipe_%", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed"),  # sees tcgen05.mma (UTCHMMA)
+        ("utchmma_Gop", "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum"),
         ("L2_%", "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
         ("L1_%", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
         ("issue_%", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
@@ -33,6 +33,8 @@ for r in rows[2:]:
                 f /= 1e3
             if u == "Gbyte":
                 f *= 1e3
+            if n == "utchmma_Gop":
+                f /= 1e9
             vals.append("%.1f" % f)
         except ValueError:
             vals.append(v[:10])
