@@ -707,7 +707,7 @@ class Captioner(nn.Module):
             int(n), K, int(bool(constraint)), T, self._packed_key)
         hit = self._host_graphs.get(key)
         if hit is None:
-            if len(self._host_graphs) >= 4:
+            if len(self._host_graphs) >= 8:
                 self._host_graphs.clear()
             sets = []
             for _ in range(2):
@@ -743,7 +743,15 @@ class Captioner(nn.Module):
         scores = torch.empty(B, K, dtype=torch.float64, device=dev)
         lengths = torch.empty(B, K, dtype=torch.int32, device=dev)
         chunks = [(lo, min(B, lo + n)) for lo in range(0, B, n)]
-        sets = self._host_graph(inputs, n, K, decoding_constraint, T, dev) if self.use_host_graphs else None
+        if self.use_host_graphs and len(chunks) >= 3 and n % 2 == 0 and chunks[-1][1] - chunks[-1][0] == n:
+            # the decode of the LAST sub-batch is the one piece of work no copy hides: halve it (one more graph shape)
+            lo, hi = chunks.pop()
+            chunks += [(lo, lo + n // 2), (lo + n // 2, hi)]
+        sets = None
+        if self.use_host_graphs:
+            # largest shape first: sizing a larger one later would reallocate the workspaces under the graphs captured before
+            sizes = sorted({n} | {hi - lo for lo, hi in chunks if hi - lo in (n, n // 2)}, reverse=True)
+            sets = {sz: self._host_graph(inputs, sz, K, decoding_constraint, T, dev) for sz in sizes}
         cs.wait_stream(cur)
         if sets is None:
             staged = []
@@ -762,14 +770,20 @@ class Captioner(nn.Module):
         else:
             # two staging sets: the copy of sub-batch i + 2 waits (on the device) until the replay of sub-batch i has read
             # its set; with the decode of a sub-batch shorter than its copy, the copy engine never idles
-            ready, consumed = {}, {}
+            ready, consumed, which = {}, {}, {}
+            seen = {}
+            for i, (lo, hi) in enumerate(chunks):  # staging set of sub-batch i: (graph shape, alternating 0 / 1 per shape)
+                sz = n // 2 if (hi - lo <= n // 2 and n // 2 in sets) else n
+                which[i] = (sz, seen.get(sz, 0) % 2)
+                seen[sz] = seen.get(sz, 0) + 1
 
             def copy_in(i):
                 lo, hi = chunks[i]
-                stage = sets[i % 2][0]
+                sz, par = which[i]
+                stage = sets[sz][par][0]
                 with torch.cuda.stream(cs):
-                    if i % 2 in consumed:
-                        cs.wait_event(consumed[i % 2])
+                    if which[i] in consumed:
+                        cs.wait_event(consumed[which[i]])
                     for dst, src in zip(stage, inputs):
                         if dst is not None:
                             dst[:hi - lo].copy_(src[lo:hi], non_blocking=True)
@@ -777,10 +791,17 @@ class Captioner(nn.Module):
                     ev.record(cs)
                 ready[i] = ev
 
-            for i in range(min(2, len(chunks))):
-                copy_in(i)
+            issued = 0
+            def top_up(upto):  # copies are issued in order, at most two sub-batches ahead of the replays
+                nonlocal issued
+                while issued < len(chunks) and issued <= upto:
+                    copy_in(issued)
+                    issued += 1
+
+            top_up(1)
             for i, (lo, hi) in enumerate(chunks):
-                stage, out, g = sets[i % 2]
+                sz, par = which[i]
+                stage, out, g = sets[sz][par]
                 cur.wait_event(ready[i])
                 g.replay()  # a short last sub-batch decodes the set's stale tail rows too; only [lo, hi) is kept
                 tokens[lo:hi].copy_(out[0][:hi - lo])
@@ -788,9 +809,8 @@ class Captioner(nn.Module):
                 lengths[lo:hi].copy_(out[2][:hi - lo])
                 ev = torch.cuda.Event()
                 ev.record(cur)
-                consumed[i % 2] = ev
-                if i + 2 < len(chunks):
-                    copy_in(i + 2)
+                consumed[which[i]] = ev
+                top_up(i + 2)
         outs = []
         for x in (tokens, scores, lengths):
             h = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
