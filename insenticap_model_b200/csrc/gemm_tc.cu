@@ -1326,6 +1326,12 @@ static int launch_lstm(const Operand& A, const Operand& W, int M, int K, const f
   int grid = persistent_grid<BN, CG>(M, N);
   if (BN == 256) {
     ep.lstm_wide = lstm_wide_tiles(M, CG);
+    // experiment hook: ISC_LSTM_WIDE1 / ISC_LSTM_WIDE2 force the number of 256-column tiles per row block for the
+    // K <= 1024 (attention LSTM) / K > 1024 (language LSTM) gate GEMM
+    static const int w1 = getenv("ISC_LSTM_WIDE1") ? atoi(getenv("ISC_LSTM_WIDE1")) : -1;
+    static const int w2 = getenv("ISC_LSTM_WIDE2") ? atoi(getenv("ISC_LSTM_WIDE2")) : -1;
+    const int wf = K <= 1024 ? w1 : w2;
+    if (wf >= 0 && wf <= N / 256) ep.lstm_wide = wf;
     const int tiles = ((M + CG * BM - 1) / (CG * BM)) * (ep.lstm_wide + (N / 256 - ep.lstm_wide) * 2);
     const int slots = num_sms() / CG;
     grid = CG * (tiles < slots ? tiles : slots);
