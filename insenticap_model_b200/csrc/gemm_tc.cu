@@ -1360,6 +1360,8 @@ static int pair_mode() {
 // quantise worse on 148 SMs: pick the shape with the smaller waves x tile-cost estimate.
 static bool use_wide_tiles(int M, int N) {
   if (N < 256) return false;
+  static const int force = getenv("ISC_GEMM_WIDE") ? atoi(getenv("ISC_GEMM_WIDE")) : -1;  // experiments: 0 narrow, 1 wide
+  if (force >= 0 && M == 3072) return force != 0;
   const long long sms = num_sms(), tm = (M + BM - 1) / BM;
   const long long narrow = (tm * ((N + 127) / 128) + sms - 1) / sms * 2;
   const long long wide = (tm * ((N + 255) / 256) + sms - 1) / sms * 3;

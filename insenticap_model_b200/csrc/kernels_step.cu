@@ -97,6 +97,11 @@ struct FeatLoad<float> {
     float4 t = *reinterpret_cast<const float4*>(row + col(lane, i));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
+  __device__ static __forceinline__ void load_shared2(const float* row, int lane, int i, float2* v) {  // kWidth / 2 pairs
+    float4 t = *reinterpret_cast<const float4*>(row + col(lane, i));
+    v[0] = make_float2(t.x, t.y);
+    v[1] = make_float2(t.z, t.w);
+  }
   static constexpr int kWidth = 4;
 };
 template <>
@@ -113,6 +118,12 @@ struct FeatLoad<__nv_bfloat16> {
       v[2 * q + 1] = f.y;
     }
   }
+  __device__ static __forceinline__ void load_shared2(const __nv_bfloat16* row, int lane, int i, float2* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(row + col(lane, i));
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __bfloat1622float2(p[q]);
+  }
   static constexpr int kWidth = 8;
 };
 template <>
@@ -128,6 +139,12 @@ struct FeatLoad<__half> {
       v[2 * q] = f.x;
       v[2 * q + 1] = f.y;
     }
+  }
+  __device__ static __forceinline__ void load_shared2(const __half* row, int lane, int i, float2* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(row + col(lane, i));
+    const __half2* p = reinterpret_cast<const __half2*>(&t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __half22float2(p[q]);
   }
   static constexpr int kWidth = 8;
 };
@@ -149,6 +166,38 @@ __device__ __forceinline__ float score2_eprod_wide(float ea0, float ea1, float e
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
   return fmaf(r, fmaf(a0x2, d1, a1x2 * d0), acc);
+}
+
+// Packed fp32 arithmetic (Blackwell FFMA2 / FMUL2: two fp32 operations per instruction). A three-register FFMA issues
+// every SECOND cycle per scheduler on this architecture (register-port bound), so a kernel whose inner loops are fp32
+// multiply-adds — this one: ncu had its fma pipe at 39 % "of peak", i.e. 78 % of what three-register FFMAs can reach —
+// doubles its arithmetic rate by pairing them.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long*>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long v) { return *reinterpret_cast<float2*>(&v); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+// Four values of the softmax-equivalent score at once (score2_eprod's algebra on register pairs): with the natural pairs
+// (v0, v1), (v2, v3) of a converted half2, d01 = 1 + ea01 * eb01 and d23 likewise; values 0 / 2 and 1 / 3 share a
+// reciprocal: D = d01 * d23 = (d0 d2, d1 d3), N = a01 * d23 + a23 * d01 = (a0 d2 + a2 d0, a1 d3 + a3 d1), acc += N / D.
+// Six packed instructions and two MUFU for four values (fourteen scalar ones before).
+__device__ __forceinline__ float2 score4_eprod(float2 ea01, float2 ea23, float2 eb01, float2 eb23, float2 a01, float2 a23,
+                                               float2 acc) {
+  const float2 one = make_float2(1.0f, 1.0f);
+  const float2 d01 = fma2(ea01, eb01, one), d23 = fma2(ea23, eb23, one);
+  const float2 D = mul2(d01, d23);
+  float2 r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(D.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(D.y));
+  const float2 n = fma2(a01, d23, mul2(a23, d01));
+  return fma2(r, n, acc);
 }
 
 // RT > 0: rows per image known at compile time (fully unrolled); RT == 0: runtime R <= 8.
@@ -331,7 +380,20 @@ __device__ __forceinline__ void score_rows_reg(const FeatT* __restrict__ p_feat,
       asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
 #pragma unroll
       for (int r = 0; r < RT; ++r) acc[r][k] = 0.f;
-      if (l < n_items) {  // warp-uniform
+      if (l < n_items && TANH_MODE == 1) {  // warp-uniform; packed fp32 (score4_eprod)
+        float2 pv2[NV / 2];
+#pragma unroll
+        for (int i = 0; i < L::kChunks; ++i) L::load_shared2(ring + (k % RING) * H, lane, i, pv2 + i * (L::kWidth / 2));
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+          float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < NV; j += 4)
+            a2 = score4_eprod(pv2[j / 2], pv2[j / 2 + 1], make_float2(q[r][j], q[r][j + 1]), make_float2(q[r][j + 2], q[r][j + 3]),
+                              make_float2(al[j], al[j + 1]), make_float2(al[j + 2], al[j + 3]), a2);
+          acc[r][k] = a2.x + a2.y;
+        }
+      } else if (l < n_items) {
         float pv[NV];
 #pragma unroll
         for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (k % RING) * H, lane, i, pv + i * L::kWidth);
@@ -400,11 +462,11 @@ __device__ __forceinline__ void wsum_rows_reg(const FeatT* __restrict__ feat, in
   constexpr int NV = L::kChunks * L::kWidth;
   constexpr int RING = kRingBytesReg / (H * (int)sizeof(FeatT));
   FeatT* ring = reinterpret_cast<FeatT*>(ring_raw);
-  float ctx[RT][NV];
+  float2 ctx[RT][NV / 2];  // register pairs: the accumulation runs on packed fp32 FMAs (fma2)
 #pragma unroll
   for (int r = 0; r < RT; ++r)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) ctx[r][j] = 0.f;
+    for (int j = 0; j < NV / 2; ++j) ctx[r][j] = make_float2(0.f, 0.f);
   constexpr int kLines = H * (int)sizeof(FeatT) / 128;
   int it = 0;
   for (int l = warp; l < n_items; l += n_warps, ++it) {
@@ -421,14 +483,15 @@ __device__ __forceinline__ void wsum_rows_reg(const FeatT* __restrict__ feat, in
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group %0;" ::"n"(RING - 1) : "memory");
-    float pv[NV];
+    float2 pv[NV / 2];
 #pragma unroll
-    for (int i = 0; i < L::kChunks; ++i) L::load_shared(ring + (it % RING) * H, lane, i, pv + i * L::kWidth);
+    for (int i = 0; i < L::kChunks; ++i) L::load_shared2(ring + (it % RING) * H, lane, i, pv + i * (L::kWidth / 2));
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
       const float w = w_smem[r * n_items + l];  // broadcast
+      const float2 w2 = make_float2(w, w);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) ctx[r][j] = fmaf(w, pv[j], ctx[r][j]);
+      for (int j = 0; j < NV / 2; ++j) ctx[r][j] = fma2(w2, pv[j], ctx[r][j]);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -439,10 +502,10 @@ __device__ __forceinline__ void wsum_rows_reg(const FeatT* __restrict__ feat, in
 #pragma unroll
     for (int i = 0; i < L::kChunks; ++i)
 #pragma unroll
-      for (int j = 0; j < L::kWidth; j += 4)
-        *reinterpret_cast<float4*>(part + r * H + L::col(lane, i) + j) =
-            make_float4(ctx[r][i * L::kWidth + j], ctx[r][i * L::kWidth + j + 1], ctx[r][i * L::kWidth + j + 2],
-                        ctx[r][i * L::kWidth + j + 3]);
+      for (int j = 0; j < L::kWidth; j += 4) {
+        const float2 lo = ctx[r][(i * L::kWidth + j) / 2], hi = ctx[r][(i * L::kWidth + j) / 2 + 1];
+        *reinterpret_cast<float4*>(part + r * H + L::col(lane, i) + j) = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
 }
 
 // FAST: exp through the raw MUFU op and one reciprocal per row (weights differ from expf / true division by ~3e-7

@@ -1,6 +1,6 @@
 """Input pipeline throughput on the GPU box: native shard gather into pinned memory
 (GB/s by thread count), and images/s of shard -> DevicePrefetcher -> Captioner.beam_search (beam 3, 16 tokens, V=10000)
-for an fp32 shard in the token-exact mode and a bf16 shard in the bf16 mode. Usage: python profiles/loader_bench.py [N] [B]"""
+for an fp32 and a fp16 shard in the token-exact mode and a bf16 shard in the bf16 mode. Usage: python profiles/loader_bench.py [N] [B]"""
 import os
 import sys
 import tempfile
@@ -22,10 +22,10 @@ g = torch.Generator().manual_seed(0)
 fc = torch.rand(N, 2048, generator=g)
 att = torch.rand(N, 196, 2048, generator=g)
 _, _, cpts, sentis, labels = syn.synthetic_inputs(N, V, seed=1)
-paths = {k: dl.FeatureShard.write(os.path.join(d, k + ".iscf"), names, fc, att, dtype=k) for k in ("fp32", "bf16")}
+paths = {k: dl.FeatureShard.write(os.path.join(d, k + ".iscf"), names, fc, att, dtype=k) for k in ("fp32", "fp16", "bf16")}
 del fc, att
 try:
-    for k in ("fp32", "bf16"):
+    for k in ("fp32", "fp16", "bf16"):
         sh = dl.FeatureShard(paths[k])
         idx = torch.randperm(N, generator=g)[:B].tolist()
         gb = B * (1 + 196) * 2048 * (4 if k == "fp32" else 2) / 1e9
@@ -39,7 +39,7 @@ try:
     concepts = {fn: cpts[i].tolist() for i, fn in enumerate(names)}
     sentiments = {fn: sentis[i].tolist() for i, fn in enumerate(names)}
     labs = [(fn, int(labels[i])) for i, fn in enumerate(names)]
-    for k, prec, pin in (("fp32", "bf16x3", False), ("bf16", "bf16", False), ("fp32", "bf16x3", True), ("bf16", "bf16", True)):
+    for k, prec, pin in (("fp32", "bf16x3", False), ("fp16", "bf16x3", False), ("bf16", "bf16", False), ("fp16", "bf16x3", True)):
         m = Captioner(syn.make_vocab(V), syn.SENTIMENT_CATEGORIES, dict(syn.DEFAULT_SETTINGS), precision=prec)
         m.load_state_dict(syn.synthetic_state_dict(V, 0))
         m = m.cuda().eval()
