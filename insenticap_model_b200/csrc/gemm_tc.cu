@@ -365,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
     }
     for (int s = 0; s < C::kStages; ++s) {
-      mbar_init(&full_bar[s], AF ? 1 + CONV_WARPS : 1);  // AF: the producer's arrive (B bytes) + one arrive per converter warp (A tiles)
+      mbar_init(&full_bar[s], AF ? 1 + CG * CONV_WARPS : 1);  // AF: the producer's arrive (B bytes) + one arrive per converter warp (A tiles; of both CTAs of a pair)
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < C::kStgSlots; ++s) {
@@ -442,9 +442,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tma_load_2d(stg + slot * C::kStgBytes, &map_a_hi, &stg_full[slot], ak, am);
             // B planes straight into the stage
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
-            tma_load_2d_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
-            if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
+            if (CG == 2) {
+              // CTA pair: each CTA loads HALF of the tile's B rows; every byte of both halves completes on the leader's barrier
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kPlanes * C::kBTileBytes);
+              tma_load_2d_pair_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
+              if (PASSES == 3) tma_load_2d_pair_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
+            } else {
+              mbar_expect_tx(&full_bar[s], C::kPlanes * C::kBTileBytes);
+              tma_load_2d_hint(stb, &map_b_hi, &full_bar[s], k0, n0, wpol);
+              if (PASSES == 3) tma_load_2d_hint(stb + C::kBTileBytes, &map_b_lo, &full_bar[s], k0, n0, wpol);
+            }
           } else if (CG == 2 && EPI == EPI_LSTM) {
             // CTA pair: each CTA loads its 128 rows of A and HALF of the tile's (gate-interleaved, contiguous) B rows,
             // 64-row boxes; every byte of both CTAs completes on the leader's barrier
@@ -578,8 +585,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
-        if ((threadIdx.x & 31) == 0)
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+        if ((threadIdx.x & 31) == 0) {
+          // a pair's MMAs are issued by the leader and read BOTH CTAs' A tiles: the peer's converters signal the leader's barrier
+          if (CG == 2) mbar_arrive_cta(&full_bar[s], 0);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+        }
       }
     }
   } else if (EPI == EPI_LOGITS || EPI == EPI_LOGITS8) {
@@ -1189,17 +1199,19 @@ static int launch_logits(const Operand& A, const Operand& W, int M, int N, int K
   return launch_kernel<PASSES, BN, ACT_NONE, EPI_LOGITS, CG>(m, ep, grid, stream);
 }
 
-// A given as fp32 (split into operand planes inside the kernel), 128x256 tiles
-template <int PASSES>
+// A given as fp32 (split into operand planes inside the kernel), 128x256 tiles; CG = 2: 256x256 tiles on CTA pairs — each
+// CTA converts its own 128 rows of A and loads half of the B rows, which takes the kernel from L2 -> SM port bound
+// (16 KB of fp32 A + 32 KB of B planes per 0.4 us of MMAs and SM) to MMA bound
+template <int PASSES, int CG>
 static int launch_af32(const float* A, int64_t lda, const Operand& W, const Dest& Cd, int M, int N, int K, const Epilogue& e,
                        cudaStream_t stream) {
   constexpr int BN = 256;
-  using C = Cfg<PASSES, BN, 1, 1>;
+  using C = Cfg<PASSES, BN, CG, 1>;
   Maps m;
   ISC_TRY(make_map_f32(&m.a_hi, A, M, K, lda));
   m.a_lo = m.a_hi;
-  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, BN, C::kBK));
-  if (PASSES == 3) ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, BN, C::kBK));
+  ISC_TRY(make_map(&m.b_hi, W.hi, N, K, W.ldp, C::kBRows, C::kBK));
+  if (PASSES == 3) ISC_TRY(make_map(&m.b_lo, W.lo, N, K, W.ldp, C::kBRows, C::kBK));
   else m.b_lo = m.b_hi;
   EpiParams ep;
   memset(&ep, 0, sizeof(ep));
@@ -1219,15 +1231,15 @@ static int launch_af32(const float* A, int64_t lda, const Operand& W, const Dest
   ep.M = M;
   ep.N = N;
   ep.K = K;
-  const int grid = persistent_grid<BN, 1>(M, N);
+  const int grid = persistent_grid<BN, CG>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
   if (ep.h16.out) {
-    if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, 1, 1>(m, ep, grid, stream);
+    if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG, 1, 1>(m, ep, grid, stream);
     set_error("gemm_tc_af32: fp16 output is only built for the ReLU epilogue");
     return ISC_ERR_ARG;
   }
-  if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, 1, 1>(m, ep, grid, stream);
-  return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, 1, 1>(m, ep, grid, stream);
+  if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG, 1>(m, ep, grid, stream);
+  return launch_kernel<PASSES, BN, ACT_NONE, EPI_STD, CG, 1>(m, ep, grid, stream);
 }
 
 // 3x3 convolution (stride 1, zero padding 1) over 16x16-gridded rows as one GEMM, 128x256 tiles. A: fp32 [M][C]
@@ -1398,11 +1410,16 @@ int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, i
   if (M <= 0 || N <= 0) return 0;
   ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_af32: K=%d must be a positive multiple of 8", K);
   ISC_REQUIRE(A && W.hi && (ep.act == ACT_RELU || ep.act == ACT_NONE), "gemm_tc_af32: operands missing / unsupported activation");
+  // CTA pairs (ISC_AF_PAIR=1): measured SLOWER than single-CTA tiles on the prologue's region-embedding GEMM (M = 18816,
+  // K = 2048: 113 -> ~190 us; the peer converters' remote arrivals and the five 32-column stages cost more than the halved
+  // weight traffic returns), so off by default; the tests pass with it forced on
+  static const int pair_env = getenv("ISC_AF_PAIR") ? atoi(getenv("ISC_AF_PAIR")) : 0;
+  const bool pair = M > tc::BM && pair_env == 1;
   if (passes == 3) {
     ISC_REQUIRE(W.lo, "gemm_tc_af32: bf16 lo plane missing for the 3-pass mode");
-    return tc::launch_af32<3>(A, lda, W, C, M, N, K, ep, stream);
+    return pair ? tc::launch_af32<3, 2>(A, lda, W, C, M, N, K, ep, stream) : tc::launch_af32<3, 1>(A, lda, W, C, M, N, K, ep, stream);
   }
-  return tc::launch_af32<1>(A, lda, W, C, M, N, K, ep, stream);
+  return pair ? tc::launch_af32<1, 2>(A, lda, W, C, M, N, K, ep, stream) : tc::launch_af32<1, 1>(A, lda, W, C, M, N, K, ep, stream);
 }
 
 int gemm_tc_conv3x3(const float* A32, int64_t lda, const Operand& A, const Operand& W, const Dest& C, int M, int N, int C_in,
