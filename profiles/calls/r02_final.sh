@@ -2,6 +2,7 @@
 # round-2 evidence call (1 GPU): tests, bench, launch list, tcgen05 counters, ncu --set full of the hot kernels, training, sweep, cider
 O=gpurun_out/r02/final; mkdir -p $O
 timeout 600 python -m pytest tests -m gpu -q > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log
+timeout 300 python __graft_entry__.py smoke > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 $O/smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/bench.log 2> $O/bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.log 2>&1
 timeout 300 python bench.py --precision bf16 --steps 20 --warmup 5 --no-cpu-baseline --no-train > $O/bench_bf16.log 2>&1

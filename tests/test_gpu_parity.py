@@ -62,18 +62,25 @@ def test_gemm(precision, shape):
         assert bool((err <= tol).all()), (precision, shape, act, err.max().item(), (err / tol).max().item())
 
 
-def test_gemm_and_decode_with_cta_pairs_forced():
-    """ISC_GEMM_PAIR=1 / ISC_LSTM_PAIR=1 / ISC_LOGITS_PAIR=1 route every multi-tile GEMM — plain, fused-LSTM and logits
-    epilogues — through the cta_group::2 kernels (cluster of 2, 256-row tiles), also at the small and ragged row counts
-    where the heuristics would keep single-CTA tiles: the GEMM shapes and the golden beam / greedy decodes must hold
-    there too (run in a subprocess: the switches are read once per process)."""
+@pytest.mark.parametrize("switches", [
+    dict(ISC_GEMM_PAIR="1", ISC_LSTM_PAIR="1", ISC_LOGITS_PAIR="1"),
+    dict(ISC_AF_PAIR="1", ISC_ATTN_TMA="1", ISC_GEMM_WIDE="0", ISC_LSTM_UNIFORM_TILES="1"),
+], ids=["pairs", "alternates"])
+def test_gemm_and_decode_with_switched_variants(switches):
+    """The kernels kept behind environment switches must stay parity-green (run in a subprocess: the switches are read
+    once per process).
+    pairs: ISC_GEMM_PAIR=1 / ISC_LSTM_PAIR=1 / ISC_LOGITS_PAIR=1 route every multi-tile GEMM — plain, fused-LSTM and
+    logits epilogues — through the cta_group::2 kernels (cluster of 2, 256-row tiles), also at the small and ragged row
+    counts where the heuristics would keep single-CTA tiles.
+    alternates: the variants DESIGN.md records as measured-and-dropped — fp32-A GEMM on CTA pairs, the TMA-staged
+    attention kernel, narrow GEMM tiles, the uniform LSTM tile list."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "pytest", "tests/test_gpu_parity.py", "-q", "-x", "-k",
-                        "test_gemm and not pairs or cfg1_matches or ragged"], cwd=root, capture_output=True, text=True,
-                       env=dict(os.environ, ISC_GEMM_PAIR="1", ISC_LSTM_PAIR="1", ISC_LOGITS_PAIR="1"), timeout=900)
+                        "test_gemm and not switched or cfg1_matches or ragged or extreme_preactivations or fast_feature_path"], cwd=root,
+                       capture_output=True, text=True, env=dict(os.environ, **switches), timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
