@@ -98,6 +98,9 @@ struct EpiParams {
   int seg_kb;
   int seg_off[9];
   int zero_border;  // force the output rows on the 16x16 grid's border to zero (they feed the next convolution as padding)
+  // split-K (template SK): the kernel is launched in clusters of split_k CTAs; CTA r of a cluster runs slice r of its tile's
+  // K loop and the cluster sums the partial tiles through distributed shared memory (see the SK epilogue)
+  int split_k;
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -192,6 +195,18 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {  
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes from the shared memory of CTA `cta` of the cluster, at the address `local` has in this CTA
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local, uint32_t cta) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
+      "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(local), "r"(cta)
+      : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -326,7 +341,9 @@ __device__ __forceinline__ void trace_stamp(int slot) {
 
 // H16: the standard epilogue also writes the fp16 copy described by EpiParams::h16 (a compile-time switch: as a run-time
 // test inside the store loop it cost every plain GEMM of the decode step ~4 us)
-template <int PASSES, int BN, int ACT, int EPI, int CG, int AF, int H16 = 0>
+// SK: split-K across the CTAs of a thread-block cluster, for GEMMs with fewer tiles than SMs and a long K loop
+// (EpiParams::split_k = cluster size; EPI_STD, ACT_NONE, CG = 1, BN = 128 only).
+template <int PASSES, int BN, int ACT, int EPI, int CG, int AF, int H16 = 0, int SK = 0>
 __global__ void __launch_bounds__(NUM_THREADS + (AF ? CONV_WARPS * 32 : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -354,8 +371,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   const int tiles_m = (ep.M + CG * BM - 1) / (CG * BM);  // CG = 2: a tile is 256 rows, 128 per CTA of the pair
   const int num_tiles = (EPI == EPI_LSTM && BN == 256) ? tiles_m * (ep.lstm_wide + (tiles_n - ep.lstm_wide) * 2) : tiles_m * tiles_n;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
-  const int walker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;  // the pair walks the tile list together
-  const int walkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // SK: one cluster per tile (grid = tiles * split_k, no walking); this CTA's K slice is its rank in the cluster
+  const int split_k = SK ? ep.split_k : 1;
+  const int ks = SK ? (int)cluster_ctarank() : 0;
+  const int walker = CG == 2 ? (int)(blockIdx.x >> 1) : (SK ? (int)blockIdx.x / split_k : (int)blockIdx.x);  // the pair walks the tile list together
+  const int walkers = CG == 2 ? (int)(gridDim.x >> 1) : (SK ? num_tiles : (int)gridDim.x);
+  const int kb_begin = SK ? (int)((long long)ks * num_kb / split_k) : 0;
+  const int kb_end = SK ? (int)((long long)(ks + 1) * num_kb / split_k) : num_kb;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
@@ -415,7 +437,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           lstm_tile<BN, CG * BM>(tile, tiles_m, tiles_n, ep.lstm_wide, m0, n0, lw);
           m0 += cta_rank * BM;
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           ISC_TRACE(it == 8, 12);
@@ -499,6 +521,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
     }
+    if (SK) {  // the cluster-wide barrier between the partial tiles and their sum (all threads of the cluster take part)
+      __syncwarp();
+      cluster_sync_all();
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
     if (lane == 0 && cta_rank == 0) {  // CG = 2: the leader issues for the pair
@@ -512,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint32_t accumulate = 0;
         uint32_t idesc_t = idesc;
         if (EPI == EPI_LSTM && BN == 256 && tile >= tiles_m * ep.lstm_wide) idesc_t = umma_idesc_bf16(CG * BM, 128);  // narrow tile
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -545,6 +571,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         else umma_commit(&acc_full[as]);
         ISC_TRACE(j < 2, 3 + j);
       }
+    }
+    if (SK) {
+      __syncwarp();
+      cluster_sync_all();
     }
   } else if (AF && warp >= 2 + EPI_WARPS) {
     // ===================== converters: fp32 A tile (staging) -> bf16 hi/lo operand tiles of the stage =====================
@@ -830,7 +860,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const bool madd_vec = ep.addmat && ((reinterpret_cast<uintptr_t>(ep.addmat) & 15) == 0) && ((ep.ld_addmat & 3) == 0);
     const bool bias_vec = ep.bias && ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     int j = 0;
-    for (int tile = walker; tile < num_tiles; tile += walkers, ++j) {
+    if (SK) {
+      // ===================== split-K epilogue (one tile per cluster, one K slice per CTA) =====================
+      // 1. every CTA parks its raw fp32 partial tile in its own shared memory — the operand stages are free: each stage
+      //    was consumed by the MMAs the accumulator barrier has just reported complete, and a CTA runs one K slice only;
+      // 2. cluster barrier; 3. CTA r sums rows [r, r + 1) * BM / split_k of all the partial tiles through distributed
+      // shared memory, in slice order, and finishes them (bias, addends, fp32 / bf16-plane stores).
+      const int tile = walker;
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      float4* part = reinterpret_cast<float4*>(smem);  // [BM][BN / 4] float4, slot ^= row & 31
+      mbar_wait(&acc_full[0], 0);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
+        float v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+        const int r = quarter * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          part[r * (BN / 4) + ((c * 8 + q) ^ (r & 31))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      cluster_sync_all();
+      const int rows_cta = BM / split_k, rows_warp = rows_cta / EPI_WARPS;  // split_k in {2, 4, 8}: 8 / 4 / 2 rows per warp
+      const int n = n0 + lane * 4;
+      const bool full4 = n + 3 < ep.N;
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.bias && n < ep.N) b4 = (full4 && bias_vec) ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : load4_guarded(ep.bias + n, n, ep.N);
+#pragma unroll 1
+      for (int k = 0; k < rows_warp; k += 2) {
+        float4 x[2], add[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = ks * rows_cta + ew * rows_warp + k + u;
+          const long long row = m0 + r;
+          const uint32_t local = smem_u32(part + r * (BN / 4) + (lane ^ (r & 31)));
+          add[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < ep.M && n < ep.N) {
+            if (ep.addmat) {
+              const float* mp = ep.addmat + row * ep.ld_addmat + n;
+              add[u] = (full4 && madd_vec) ? __ldg(reinterpret_cast<const float4*>(mp)) : load4_guarded(mp, n, ep.N);
+            }
+            if (ep.rowadd) {
+              const float* rp = ep.rowadd + (long long)((unsigned)row / (unsigned)ep.rows_per_group) * ep.ld_rowadd + n;
+              const float4 t = (full4 && radd_vec) ? __ldg(reinterpret_cast<const float4*>(rp)) : load4_guarded(rp, n, ep.N);
+              add[u].x += t.x; add[u].y += t.y; add[u].z += t.z; add[u].w += t.w;
+            }
+          }
+          float4 t[8];  // all slices requested up front, summed in slice order: the sum is the same on every run
+#pragma unroll
+          for (int sl = 0; sl < 8; ++sl)
+            if (sl < split_k) t[sl] = ld_dsmem_f4(local, sl);
+          x[u] = t[0];
+#pragma unroll
+          for (int sl = 1; sl < 8; ++sl)
+            if (sl < split_k) { x[u].x += t[sl].x; x[u].y += t[sl].y; x[u].z += t[sl].z; x[u].w += t[sl].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int r = ks * rows_cta + ew * rows_warp + k + u;
+          const long long row = m0 + r;
+          if (row < ep.M && n < ep.N) {
+            float4 y = x[u];
+            y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+            y.x += add[u].x; y.y += add[u].y; y.z += add[u].z; y.w += add[u].w;
+            if (ep.c) {
+              float* dst = ep.c + row * ep.ldc + n;
+              if (full4 && c_vec) {
+                *reinterpret_cast<float4*>(dst) = y;
+              } else {
+                dst[0] = y.x;
+                if (n + 1 < ep.N) dst[1] = y.y;
+                if (n + 2 < ep.N) dst[2] = y.z;
+                if (n + 3 < ep.N) dst[3] = y.w;
+              }
+            }
+            if (ep.hi) {
+              __nv_bfloat16 h[4], l[4];
+              split_bf16(y.x, h[0], l[0]);
+              split_bf16(y.y, h[1], l[1]);
+              split_bf16(y.z, h[2], l[2]);
+              split_bf16(y.w, h[3], l[3]);
+              __nv_bfloat16* dh = ep.hi + row * ep.ldp + n;
+              __nv_bfloat16* dl = ep.lo ? ep.lo + row * ep.ldp + n : nullptr;
+              if (full4 && p_vec) {
+                *reinterpret_cast<uint2*>(dh) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                if (dl) *reinterpret_cast<uint2*>(dl) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+              } else {
+                for (int q = 0; q < 4 && n + q < ep.N; ++q) {
+                  dh[q] = h[q];
+                  if (dl) dl[q] = l[q];
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    for (int tile = walker; !SK && tile < num_tiles; tile += walkers, ++j) {
       const int m0 = (tile / tiles_n) * (CG * BM) + cta_rank * BM, n0 = (tile % tiles_n) * BN;
       const int as = j & 1;
       const int row0 = m0 + quarter * 32 + r_off;  // this lane's rows: row0 + 4*i, i = 0..7
@@ -988,7 +1117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 
   tcgen05_fence_before();
-  if (CG == 2) cluster_sync_all();  // no CTA of the pair leaves while the other may still signal into its smem
+  if (CG == 2 || SK) cluster_sync_all();  // no CTA of the pair leaves while the other may still signal into its smem (SK: read it)
   else __syncthreads();
   ISC_TRACE(threadIdx.x == 0, 15);
   if (warp == 1) {
@@ -1087,13 +1216,13 @@ static int make_map_f32(CUtensorMap* map, const float* base, int64_t rows, int64
   return 0;
 }
 
-template <int PASSES, int BN, int ACT, int EPI, int CG, int AF = 0, int H16 = 0>
+template <int PASSES, int BN, int ACT, int EPI, int CG, int AF = 0, int H16 = 0, int SK = 0>
 static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStream_t stream) {
-  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG, AF, H16>;
+  auto kern = gemm_tc_kernel<PASSES, BN, ACT, EPI, CG, AF, H16, SK>;
   constexpr int smem = Cfg<PASSES, BN, CG, AF>::kSmemBytes;
   constexpr int NUM_THREADS = Cfg<PASSES, BN, CG, AF>::kThreads;
   ISC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (CG == 2) {
+  if (CG == 2 || SK) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -1102,7 +1231,7 @@ static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStrea
     cfg.stream = stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.x = SK ? ep.split_k : 2;
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
@@ -1129,6 +1258,22 @@ static int make_maps(Maps& m, const Operand& A, const Operand& W, int M, int N, 
     m.b_lo = m.b_hi;
   }
   return 0;
+}
+
+// ---- split-K: GEMMs with few tiles and a long K loop (the training path's M = 256 step GEMMs: 8-32 tiles of 16-32
+// k-blocks; its weight-gradient contractions over batch x regions rows: 16-64 tiles of 784 k-blocks) leave most SMs idle
+// while a few CTAs pull their whole operand panels through one SM's L2 port. Such a tile is given to a cluster of 2 / 4 / 8
+// CTAs, one K slice each, which sum their partial tiles through distributed shared memory.
+// Returns the cluster size for an M x N x K GEMM on 128 x 128 tiles with 64-wide k-blocks (1 = do not split).
+// ISC_SPLITK=0 switches it off.
+static int splitk_slices(int M, int N, int K) {
+  static const bool on = !(getenv("ISC_SPLITK") && atoi(getenv("ISC_SPLITK")) == 0);
+  if (!on) return 1;
+  const int tiles = ((M + BM - 1) / BM) * ((N + 127) / 128), num_kb = (K + 63) / 64;
+  if (tiles * 2 > num_sms() || num_kb < 12) return 1;
+  int s = 8;  // at least four k-blocks per slice: below that, fill and the exchange cost more than the slices save
+  while (s > 1 && (s * tiles > num_sms() || s * 4 > num_kb)) s >>= 1;
+  return s;
 }
 
 // persistent grid: one CTA (CG = 2: one CTA pair) per SM (pair) walks the tile list
@@ -1164,6 +1309,13 @@ static int launch(const Operand& A, const Operand& W, const Dest& Cd, int M, int
   ep.K = K;
   const int grid = persistent_grid<BN, CG>(M, N);
   ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * N * K * PASSES, stream);
+  if (PASSES == 3 && BN == 128 && CG == 1 && e.act == ACT_NONE && !ep.h16.out) {
+    const int slices = splitk_slices(M, N, K);
+    if (slices > 1) {
+      ep.split_k = slices;
+      return launch_kernel<PASSES, 128, ACT_NONE, EPI_STD, 1, 0, 0, (PASSES == 3 && BN == 128 && CG == 1) ? 1 : 0>(m, ep, grid * slices, stream);
+    }
+  }
   if (ep.h16.out) {  // fp16 copy of the result (the prologue's projected features): only the two activations it is used with
     if (e.act == ACT_RELU) return launch_kernel<PASSES, BN, ACT_RELU, EPI_STD, CG, 0, 1>(m, ep, grid, stream);
     if (e.act == ACT_EXPNEG2_RELU) return launch_kernel<PASSES, BN, ACT_EXPNEG2_RELU, EPI_STD, CG, 0, 1>(m, ep, grid, stream);
@@ -1398,6 +1550,7 @@ int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int
   const bool pair = M > tc::BM && (tc::pair_mode() == 1 || (tc::pair_mode() < 0 && tc::pair_pays(M, N, wide)));
   if (passes == 3) {
     ISC_REQUIRE(A.lo && W.lo, "gemm_tc: bf16 lo planes missing for the 3-pass mode");
+    if (ep.act == ACT_NONE && !C.h16.out && tc::splitk_slices(M, N, K) > 1) return tc::launch<3, 128, 1>(A, W, C, M, N, K, ep, stream);
     if (pair) return wide ? tc::launch<3, 256, 2>(A, W, C, M, N, K, ep, stream) : tc::launch<3, 128, 2>(A, W, C, M, N, K, ep, stream);
     return wide ? tc::launch<3, 256, 1>(A, W, C, M, N, K, ep, stream) : tc::launch<3, 128, 1>(A, W, C, M, N, K, ep, stream);
   }
