@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out/r02/w; mkdir -p $O
+timeout 600 python -m pytest tests/test_gpu_train.py tests/test_gpu_detector.py -m gpu -q -x > $O/pytest_w.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_w.log
+for d in 0 1 0 1; do echo "deep=$d"; ISC_ATTN_BWD_DEEP=$d timeout 300 python profiles/train_bench.py rl 512 3 5 2>/dev/null | grep '^{' | head -1 | cut -c1-140; done
+for d in 0 1; do echo "deep=$d"; ISC_ATTN_BWD_DEEP=$d timeout 300 python profiles/train_bench.py xe 256 5 2>/dev/null | grep '^{' | head -1 | cut -c1-140; done
+echo default; timeout 300 python profiles/train_bench.py rl 512 3 5 2>/dev/null | grep '^{' | head -1 | cut -c1-140
