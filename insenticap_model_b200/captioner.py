@@ -328,8 +328,11 @@ class Captioner(nn.Module):
         if not self.training or p <= 0.0:
             return None
         dev = self._device()
-        masks = {k: (torch.rand(sh, device=dev) >= p).to(torch.uint8) for k, sh in shapes.items()}
-        masks["out"] = (torch.rand(n_steps, B, 512, device=dev) >= p).to(torch.uint8)
+        # one Bernoulli(1 - p) kernel per mask, written as uint8 (rand -> compare -> cast was three passes over the
+        # [B, regions, 512] mask)
+        keep = lambda sh: torch.empty(sh, dtype=torch.uint8, device=dev).bernoulli_(1.0 - p)
+        masks = {k: keep(sh) for k, sh in shapes.items()}
+        masks["out"] = keep((n_steps, B, 512))
         masks["scale"] = 1.0 / (1.0 - p)
         return masks
 

@@ -401,7 +401,9 @@ __global__ void __launch_bounds__(256) attention_bwd_final_kernel(AttnBwdFinal p
   }
   for (int i = threadIdx.x; i < H; i += 256) alpha_s[i] = p.alpha[i];
   __syncthreads();
-  for (int l = warp; l < p.n_items; l += 8) {
+  // gridDim.y CTAs share an image's items (each re-reads the 2 * T * H query / d ctx rows, which are L2 hits): one CTA per
+  // image left the 148 SMs with 1.7 CTAs each
+  for (int l = blockIdx.y * 8 + warp; l < p.n_items; l += 8 * gridDim.y) {
     float af[16], ap[16], e[16], al[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -413,10 +415,20 @@ __global__ void __launch_bounds__(256) attention_bwd_final_kernel(AttnBwdFinal p
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) af[i] = ap[i] = 0.f;
-    for (int t = 0; t < p.T; ++t) {
-      const long long row = (long long)t * p.M + b;
-      const float w = p.w_all[row * p.n_items + l];
-      const float de = p.de_all[row * p.n_items + l];
+    // lane t fetches step t's softmax weight and its gradient once (they sit T * n_items apart: read inside the step loop,
+    // every trip waited for two L2 round trips), the step loop takes them by shuffle
+    for (int t0 = 0; t0 < p.T; t0 += 32) {
+    float w_l = 0.f, de_l = 0.f;
+    if (t0 + lane < p.T) {
+      const long long row = (long long)(t0 + lane) * p.M + b;
+      w_l = p.w_all[row * p.n_items + l];
+      de_l = p.de_all[row * p.n_items + l];
+    }
+    const int tn = p.T - t0 < 32 ? p.T - t0 : 32;
+    for (int tt_ = 0; tt_ < tn; ++tt_) {
+      const int t = t0 + tt_;
+      const float w = __shfl_sync(0xffffffffu, w_l, tt_);
+      const float de = __shfl_sync(0xffffffffu, de_l, tt_);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = i * 128 + lane * 4;
@@ -432,6 +444,7 @@ __global__ void __launch_bounds__(256) attention_bwd_final_kernel(AttnBwdFinal p
           ap[4 * i + j] = fmaf(de * al[4 * i + j], 1.f - tt[j] * tt[j], ap[4 * i + j]);
         }
       }
+    }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -707,7 +720,8 @@ int launch_attention_bwd_final(int T, int M, int B, int n_items, const float* ea
   ISC_REQUIRE(smem <= 200 * 1024, "attention_bwd_final: %d steps do not fit shared memory", T);
   ISC_CUDA(cudaFuncSetAttribute(attention_bwd_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope ps(ISC_K_TRAIN, (double)B * n_items * H * 4.0 * 3, s);
-  attention_bwd_final_kernel<<<B, 256, smem, s>>>(p);
+  const int split = n_items >= 64 ? 3 : 1;  // region features (196 items): 3 CTAs per image, 3 resident per SM
+  attention_bwd_final_kernel<<<dim3(B, split), 256, smem, s>>>(p);
   ISC_LAUNCH_CHECK();
   return 0;
 }
