@@ -66,15 +66,21 @@ def timed(n):
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
     e0.record()
+    h0 = time.perf_counter()
     for _ in range(n):
         o = step()
+    host_issue_ms[0] = (time.perf_counter() - h0) * 1e3 / n  # host time to ISSUE an iteration (no sync inside the loop)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / n], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item()), o
+
+
+host_issue_ms = [None]
 
 
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -115,7 +121,7 @@ else:
     in_sync = True
 if rank == 0:
     print(json.dumps({"workload": what, "n_gpus": world, "batch_per_gpu": B, "samples_per_image": spi if what == "rl" else None,
-                      "ms_per_iteration": float(ms.item()), "rows_per_s": world * rows / (float(ms.item()) * 1e-3),
+                      "ms_per_iteration": float(ms.item()), "host_issue_ms_per_iteration": host_issue_ms[0], "rows_per_s": world * rows / (float(ms.item()) * 1e-3),
                       "losses": {k: float(v) for k, v in out.items()}, "replicas_in_sync": in_sync,
                       "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9, **comm}), flush=True)
 # per-kernel-class device time of one more iteration (CUDA events around every launch of the library)
