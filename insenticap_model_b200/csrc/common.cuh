@@ -209,6 +209,22 @@ struct LstmEpilogue {
 int gemm_tc_lstm(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* rowadd,
                  int64_t ld_rowadd, int rows_per_group, const LstmEpilogue& lstm, cudaStream_t stream);
 
+// Fused gate of Attention.forward (models/captioner.py:108-117) on the tensor-core GEMM:
+//   g3 = tanh([c | s] W3^T + b3 + addmat),  w = sigmoid(alpha . g3 + alpha_b),  out = w c + (1 - w) s.
+// A row's 512 gate columns are four 128-column tiles: the four CTAs of a thread-block cluster compute them, exchange
+// their partial alpha . g3 sums through distributed shared memory and each mixes its 128 output columns — g3 never
+// reaches HBM and the separate gate_mix launch disappears. `out` takes the mixed context (fp32 and / or bf16 planes).
+struct GateEpilogue {
+  const float* alpha = nullptr;    // [H]
+  const float* alpha_b = nullptr;  // [1]
+  const float* cs = nullptr;       // [M, ld_cs] fp32: content context at column 0, sentiment context at column H
+  long long ld_cs = 0;
+  float* gate_w = nullptr;         // optional [M] (stride ld_gate_w): the gate weight w
+  long long ld_gate_w = 0;
+};
+int gemm_tc_gate(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* addmat,
+                 int64_t ld_addmat, const GateEpilogue& gate, const Dest& out, cudaStream_t stream);
+
 // tensor-core GEMM whose A operand is fp32 in HBM: TMA brings fp32 tiles into a staging ring and four converter warps
 // split them into the bf16 hi/lo operand tiles in shared memory (no plane-split pass over HBM). 128x256 tiles.
 int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, int M, int N, int K, int passes,

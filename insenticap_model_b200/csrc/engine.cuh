@@ -447,17 +447,41 @@ int run_step(const Ctx& c, const DecodeWs& w, int M, int R, const StepIO& io) {
     ISC_TRY(launch_attention(ap, B, c.precision, c.s));
   }
   if (rl) {
-    Epilogue ep;
-    ep.bias = pk.b3;
-    ep.addmat = w.hproj + 2 * H;
-    ep.ld_addmat = 3 * H;
-    ep.act = ACT_TANH;
-    Dest dst;
-    dst.f32 = w.g3;
-    dst.ld = H;
-    ISC_TRY(gemm(c.precision, operand(w.cs, 2 * H, w.pcs, 2 * H), pk.W3.op(), dst, M, H, 2 * H, ep, c.s));
-    ISC_TRY(launch_gate_mix(w.g3, w.cs, pk.alpha_g, pk.alpha_g_b, x2, io.gate_w, io.ld_gate_w, M, c.s));
+    // ISC_GATE_FUSED=1: gate GEMM with the gate weight and the context mix in its epilogue (a cluster of 4 CTAs per row
+    // block exchanging their alpha . g3 partial sums through distributed shared memory; not when the tape needs g3 or the
+    // GEMM runs on CUDA cores). Measured on the B = 1024 beam-3 call: the gate_mix launch (7 us) and the g3 round trip
+    // disappear, the cluster barrier, the exchange and the mix inside the epilogue add 4-6 us to the GEMM, and cluster
+    // launches start later: 7.47-7.49 ms unfused, 7.50-7.58 ms fused per call — off by default, results identical.
+    static const bool gate_fused_on = getenv("ISC_GATE_FUSED") && atoi(getenv("ISC_GATE_FUSED")) != 0;
+    if (gate_fused_on && c.precision != ISC_PREC_FP32 && !w.tape) {
+      GateEpilogue ge;
+      ge.alpha = pk.alpha_g;
+      ge.alpha_b = pk.alpha_g_b;
+      ge.cs = w.cs;
+      ge.ld_cs = 2 * H;
+      ge.gate_w = io.gate_w;
+      ge.ld_gate_w = io.ld_gate_w;
+      Dest dst;
+      dst.f32 = x2.f32;
+      dst.ld = x2.ld;
+      dst.hi = x2.hi;
+      dst.lo = x2.lo;
+      dst.ldp = x2.ldp;
+      ISC_TRY(gemm_tc_gate(operand(w.cs, 2 * H, w.pcs, 2 * H), pk.W3.op(), M, 2 * H, passes, pk.b3, w.hproj + 2 * H, 3 * H, ge, dst, c.s));
+    } else {
+      Epilogue ep;
+      ep.bias = pk.b3;
+      ep.addmat = w.hproj + 2 * H;
+      ep.ld_addmat = 3 * H;
+      ep.act = ACT_TANH;
+      Dest dst;
+      dst.f32 = w.g3;
+      dst.ld = H;
+      ISC_TRY(gemm(c.precision, operand(w.cs, 2 * H, w.pcs, 2 * H), pk.W3.op(), dst, M, H, 2 * H, ep, c.s));
+      ISC_TRY(launch_gate_mix(w.g3, w.cs, pk.alpha_g, pk.alpha_g_b, x2, io.gate_w, io.ld_gate_w, M, c.s));
+    }
   }
+
   // language LSTM
   if (fuse_lstm) {
     LstmEpilogue le;

@@ -70,7 +70,7 @@ struct Cfg {
   static constexpr int kThreads = NUM_THREADS + (AF ? CONV_WARPS * 32 : 0);
 };
 
-enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2, EPI_LOGITS8 = 3 };  // EPI_LOGITS8: 8 candidates per slice
+enum { EPI_STD = 0, EPI_LOGITS = 1, EPI_LSTM = 2, EPI_LOGITS8 = 3, EPI_GATE = 4 };  // EPI_LOGITS8: 8 candidates per slice
 
 struct EpiParams {
   const float* bias;
@@ -91,6 +91,8 @@ struct EpiParams {
   LogitsSelect sel;
   // EPI_LSTM: the LSTM cell applied to the four gate pre-activations of each hidden unit
   LstmEpilogue lstm;
+  // EPI_GATE: gate weight and mixed context of Attention.forward from the four column tiles of a row block (cluster of 4)
+  GateEpilogue gate;
   int lstm_wide;  // EPI_LSTM with BN = 256: 256-column tiles per 128-row block, the rest of the row in 128-column tiles
   // 3x3 convolution as ONE GEMM over a zero-bordered 16x16 grid per image (rows = image * 256 + y * 16 + x): the K loop
   // runs over 9 segments of seg_kb k-blocks; segment s reads the A rows shifted by seg_off[s] = dy * 16 + dx (TMA
@@ -204,6 +206,17 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local, uint32_t cta) {
       "mapa.shared::cluster.u32 ra, %4, %5;\n\t"
       "ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [ra];\n\t}"
       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "r"(local), "r"(cta)
+      : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local, uint32_t cta) {
+  float v;
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %1, %2;\n\t"
+      "ld.shared::cluster.f32 %0, [ra];\n\t}"
+      : "=f"(v)
       : "r"(local), "r"(cta)
       : "memory");
   return v;
@@ -521,7 +534,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
     }
-    if (SK) {  // the cluster-wide barrier between the partial tiles and their sum (all threads of the cluster take part)
+    if (SK || EPI == EPI_GATE) {  // the cluster-wide barrier of the SK / gate epilogues: all threads of the cluster take part
       __syncwarp();
       cluster_sync_all();
     }
@@ -572,7 +585,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         ISC_TRACE(j < 2, 3 + j);
       }
     }
-    if (SK) {
+    if (SK || EPI == EPI_GATE) {
       __syncwarp();
       cluster_sync_all();
     }
@@ -726,7 +739,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       __syncwarp();  // bias slice is rewritten for the next tile
     }
+  } else if (EPI == EPI_GATE) {
+    // ===================== epilogue: gate weight + mixed context (cluster of 4 = the four column tiles of a row block) =====
+    const GateEpilogue& G = ep.gate;
+    const int ew = warp - 2;
+    const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int half = ew >> 2;      // which half of the tile's columns this warp drains
+    float4* sc = reinterpret_cast<float4*>(epi_smem) + ew * 32 * 8;  // 32 rows x 8 float4, slot ^= row & 7
+    float* mine = reinterpret_cast<float*>(sc);  // after the chunks: [0, 32) this warp's row sums (read by the cluster), [32, 64) w
+    const int r_off = lane >> 3, c4 = lane & 7;
+    const int tile = walker;  // one tile per CTA: grid = tiles, cluster rank = column tile
+    const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    const int row0 = m0 + quarter * 32 + r_off;  // this lane's rows: row0 + 4*i, i = 0..7
+    int nvalid = (ep.M - row0 + 3) >> 2;
+    nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
+    float psum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) psum[i] = 0.f;
+    mbar_wait(&acc_full[0], 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 64; ++cc) {
+      const int c = half * (BN / 64) + cc;
+      float v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        sc[lane * 8 + (q ^ (lane & 7))] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      __syncwarp();
+      const int n = n0 + c * 32 + c4 * 4;  // N = 512: every column is valid
+      const float4 b4 = ep.bias ? __ldg(reinterpret_cast<const float4*>(ep.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(G.alpha + n));
+      float4 add4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        add4[i] = (i < nvalid && ep.addmat) ? __ldg(reinterpret_cast<const float4*>(ep.addmat + (long long)(row0 + 4 * i) * ep.ld_addmat + n))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + r_off;
+        float4 x = sc[r * 8 + (c4 ^ (r & 7))];
+        x.x = act_ct<ACT_TANH>(x.x + b4.x + add4[i].x);
+        x.y = act_ct<ACT_TANH>(x.y + b4.y + add4[i].y);
+        x.z = act_ct<ACT_TANH>(x.z + b4.z + add4[i].z);
+        x.w = act_ct<ACT_TANH>(x.w + b4.w + add4[i].w);
+        psum[i] += a4.x * x.x + a4.y * x.y + a4.z * x.z + a4.w * x.w;
+      }
+      __syncwarp();  // staging tile is reused by the next chunk
+    }
+    tcgen05_fence_before();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // the eight lanes that share a row
+      psum[i] += __shfl_xor_sync(0xffffffffu, psum[i], 1);
+      psum[i] += __shfl_xor_sync(0xffffffffu, psum[i], 2);
+      psum[i] += __shfl_xor_sync(0xffffffffu, psum[i], 4);
+    }
+    if (c4 == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mine[r_off + 4 * i] = psum[i];
+    }
+    __syncwarp();
+    cluster_sync_all();
+    // gate weight of row quarter * 32 + lane: the eight partial sums (4 column tiles x 2 halves) in a fixed order, so
+    // that the four CTAs (and both half-warps) of a row block arrive at the same bits
+    float e = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) e += ld_dsmem_f32(smem_u32(epi_smem + (h * 4 + (ew & 3)) * 1024 + lane), d);  // warp (half h, this quarter)
+    const float wl = sigmoid_accurate(e + __ldg(G.alpha_b));
+    mine[32 + lane] = wl;
+    if (G.gate_w && n0 == 0 && half == 0 && m0 + quarter * 32 + lane < ep.M)
+      G.gate_w[(long long)(m0 + quarter * 32 + lane) * G.ld_gate_w] = wl;
+    __syncwarp();
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 64; ++cc) {
+      const int n = n0 + (half * (BN / 64) + cc) * 32 + c4 * 4;
+      float4 cv[8], sv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nvalid) {
+          const float* p = G.cs + (long long)(row0 + 4 * i) * G.ld_cs + n;
+          cv[i] = __ldg(reinterpret_cast<const float4*>(p));
+          sv[i] = __ldg(reinterpret_cast<const float4*>(p + H));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i < nvalid) {
+          const long long row = row0 + 4 * i;
+          const float w = mine[32 + r_off + 4 * i];
+          float4 o;
+          o.x = w * cv[i].x + (1.f - w) * sv[i].x;
+          o.y = w * cv[i].y + (1.f - w) * sv[i].y;
+          o.z = w * cv[i].z + (1.f - w) * sv[i].z;
+          o.w = w * cv[i].w + (1.f - w) * sv[i].w;
+          if (ep.c) *reinterpret_cast<float4*>(ep.c + row * ep.ldc + n) = o;
+          if (ep.hi) {
+            __nv_bfloat16 h[4], l[4];
+            split_bf16(o.x, h[0], l[0]);
+            split_bf16(o.y, h[1], l[1]);
+            split_bf16(o.z, h[2], l[2]);
+            split_bf16(o.w, h[3], l[3]);
+            *reinterpret_cast<uint2*>(ep.hi + row * ep.ldp + n) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+            if (ep.lo) *reinterpret_cast<uint2*>(ep.lo + row * ep.ldp + n) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+          }
+        }
+      }
+    }
   } else if (EPI == EPI_LSTM) {
+
     // ===================== epilogue: LSTM cell on the gate pre-activations (tile columns = [i f g o] x 16 units per group) =====
     // (Measured and dropped in round 2: routing c_prev, the addend rows and the results through a per-warp shared-memory
     // tile so that the warp's global accesses are coalesced — 4x fewer L1 wavefronts, but the shuffles, warp barriers and
@@ -1117,7 +1239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 
   tcgen05_fence_before();
-  if (CG == 2 || SK) cluster_sync_all();  // no CTA of the pair leaves while the other may still signal into its smem (SK: read it)
+  if (CG == 2 || SK || EPI == EPI_GATE) cluster_sync_all();  // no CTA of the pair leaves while the other may still signal into its smem (SK: read it)
   else __syncthreads();
   ISC_TRACE(threadIdx.x == 0, 15);
   if (warp == 1) {
@@ -1222,7 +1344,7 @@ static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStrea
   constexpr int smem = Cfg<PASSES, BN, CG, AF>::kSmemBytes;
   constexpr int NUM_THREADS = Cfg<PASSES, BN, CG, AF>::kThreads;
   ISC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (CG == 2 || SK) {
+  if (CG == 2 || SK || EPI == EPI_GATE) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -1231,7 +1353,7 @@ static int launch_kernel(const Maps& m, const EpiParams& ep, int grid, cudaStrea
     cfg.stream = stream;
     cudaLaunchAttribute attr;
     attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = SK ? ep.split_k : 2;
+    attr.val.clusterDim.x = SK ? ep.split_k : (EPI == EPI_GATE ? 4 : 2);
     attr.val.clusterDim.y = 1;
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
@@ -1556,6 +1678,44 @@ int gemm_tc(const Operand& A, const Operand& W, const Dest& C, int M, int N, int
   }
   if (pair) return wide ? tc::launch<1, 256, 2>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 2>(A, W, C, M, N, K, ep, stream);
   return wide ? tc::launch<1, 256, 1>(A, W, C, M, N, K, ep, stream) : tc::launch<1, 128, 1>(A, W, C, M, N, K, ep, stream);
+}
+
+int gemm_tc_gate(const Operand& A, const Operand& W, int M, int K, int passes, const float* bias, const float* addmat,
+                 int64_t ld_addmat, const GateEpilogue& gate, const Dest& out, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  ISC_REQUIRE(K > 0 && K % 8 == 0, "gemm_tc_gate: K=%d must be a positive multiple of 8", K);
+  ISC_REQUIRE(A.hi && W.hi && (passes != 3 || (A.lo && W.lo)), "gemm_tc_gate: operand planes missing");
+  ISC_REQUIRE(gate.alpha && gate.alpha_b && gate.cs, "gemm_tc_gate: gate parameters missing");
+  auto aligned = [](const void* p, int64_t ld, int elem) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld * elem) % 16 == 0; };
+  ISC_REQUIRE(aligned(gate.cs, gate.ld_cs, 4) && aligned(gate.alpha, 4, 4) && (!bias || aligned(bias, 4, 4)) &&
+                  (!addmat || aligned(addmat, ld_addmat, 4)) && (!out.f32 || aligned(out.f32, out.ld, 4)) &&
+                  (!out.hi || ((reinterpret_cast<uintptr_t>(out.hi) & 7) == 0 && (out.ldp & 3) == 0)) &&
+                  (!out.lo || (reinterpret_cast<uintptr_t>(out.lo) & 7) == 0),
+              "gemm_tc_gate: operands must be 16-byte aligned with 16-byte multiple row pitches");
+  tc::Maps m;
+  tc::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.bias = bias;
+  ep.addmat = addmat;
+  ep.ld_addmat = ld_addmat;
+  ep.rows_per_group = 1;
+  ep.c = out.f32;
+  ep.ldc = out.ld;
+  ep.hi = out.hi;
+  ep.lo = out.lo;
+  ep.ldp = out.ldp;
+  ep.M = M;
+  ep.N = H;
+  ep.K = K;
+  ep.gate = gate;
+  const int grid = ((M + tc::BM - 1) / tc::BM) * (H / 128);  // one 128 x 128 tile per CTA, clusters of 4 along a row block
+  ProfScope ps(ISC_K_GEMM_TC, 2.0 * M * H * K * passes, stream);
+  if (passes == 3) {
+    ISC_TRY((tc::make_maps<3, 128, 1>(m, A, W, M, H, K)));
+    return tc::launch_kernel<3, 128, ACT_TANH, tc::EPI_GATE, 1>(m, ep, grid, stream);
+  }
+  ISC_TRY((tc::make_maps<1, 128, 1>(m, A, W, M, H, K)));
+  return tc::launch_kernel<1, 128, ACT_TANH, tc::EPI_GATE, 1>(m, ep, grid, stream);
 }
 
 int gemm_tc_af32(const float* A, int64_t lda, const Operand& W, const Dest& C, int M, int N, int K, int passes,

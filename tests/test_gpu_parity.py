@@ -72,7 +72,7 @@ def test_gemm(precision, shape):
 
 @pytest.mark.parametrize("switches", [
     dict(ISC_GEMM_PAIR="1", ISC_LSTM_PAIR="1", ISC_LOGITS_PAIR="1"),
-    dict(ISC_AF_PAIR="1", ISC_ATTN_TMA="1", ISC_GEMM_WIDE="0", ISC_LSTM_UNIFORM_TILES="1", ISC_SPLITK="0"),
+    dict(ISC_AF_PAIR="1", ISC_ATTN_TMA="1", ISC_GEMM_WIDE="0", ISC_LSTM_UNIFORM_TILES="1", ISC_SPLITK="0", ISC_GATE_FUSED="1"),
 ], ids=["pairs", "alternates"])
 def test_gemm_and_decode_with_switched_variants(switches):
     """The kernels kept behind environment switches must stay parity-green (run in a subprocess: the switches are read
@@ -81,7 +81,7 @@ def test_gemm_and_decode_with_switched_variants(switches):
     logits epilogues — through the cta_group::2 kernels (cluster of 2, 256-row tiles), also at the small and ragged row
     counts where the heuristics would keep single-CTA tiles.
     alternates: the variants DESIGN.md records as measured-and-dropped — fp32-A GEMM on CTA pairs, the TMA-staged
-    attention kernel, narrow GEMM tiles, the uniform LSTM tile list."""
+    attention kernel, narrow GEMM tiles, the uniform LSTM tile list, unsplit K loops, the gate GEMM with the context mix in its epilogue (cluster of 4)."""
     import os
     import subprocess
     import sys
