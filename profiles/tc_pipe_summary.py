@@ -15,7 +15,7 @@ for r in rows[rows.index(hdr) + 1:]:
         continue
     key = (int(r[ix["ID"]]), r[ix["Kernel Name"]].split("(")[0].replace("void isc::tc::", ""), r[ix["Grid Size"]].replace(" ", ""))
     recs.setdefault(key, {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
-print("%-4s %-44s %-12s %8s %12s %9s %8s %8s" % ("id", "kernel <PASSES,BN,ACT,EPI,CG,AF,H16>", "grid", "us", "utchmma ops", "TFLOP/s", "tc_pipe%", "inst_tc"))
+print("%-4s %-44s %-12s %8s %12s %9s %8s %8s" % ("id", "kernel <PASSES,BN,ACT,EPI,CG,AF,H16,SK>", "grid", "us", "utchmma ops", "TFLOP/s", "tc_pipe%", "inst_tc"))
 for (i, k, g), m in recs.items():
     us = m.get("gpu__time_duration.sum", 0) / 1e3
     ops = m.get("sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum", 0)
