@@ -8,7 +8,8 @@ import time
 
 import torch
 
-from insenticap_model_b200 import dataloader as dl
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from insenticap_model_b200 import dataloader as dl  # noqa: E402
 from insenticap_model_b200 import synthetic as syn
 from insenticap_model_b200.captioner import Captioner
 
