@@ -329,8 +329,16 @@ int isc_shard_copy_to_device(isc_shard_t shard, const int64_t* indices, int64_t 
   const size_t fc_bytes = (size_t)h.feat_dim * elem_bytes(h.dtype);
   const size_t att_bytes = fc_bytes * h.n_regions;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static const bool use_kernel = !(getenv("ISC_SHARD_MEMCPY") && atoi(getenv("ISC_SHARD_MEMCPY")) != 0);
-  if (n > 0 && use_kernel && s->dev_view && fc_bytes % 16 == 0 && h.data_offset % 16 == 0 && h.record_bytes % 16 == 0 &&
+  // ISC_SHARD_COPY=kernel: the zero-copy gather kernel above instead of one cudaMemcpyAsync per record. Measured
+  // (profiles/shard_copy_bench.py, 512 fp16 records = 0.41 GB): the per-record DMA is steady (11.6 ms every time) but
+  // throttles the ISSUING thread for the whole DMA time; the kernel returns at once and has the same median rate
+  // (12.6 ms) but outliers of tens to hundreds of ms on this pool — so the DMA loop stays the default and the loader
+  // issues it from a thread of its own (dataloader.DevicePrefetcher).
+  static const int mode = [] {
+    const char* e = getenv("ISC_SHARD_COPY");
+    return (e && strcmp(e, "kernel") == 0) ? 2 : 1;
+  }();
+  if (n > 0 && mode == 2 && s->dev_view && fc_bytes % 16 == 0 && h.data_offset % 16 == 0 && h.record_bytes % 16 == 0 &&
       att_bytes <= 0xffffffffull) {
     // the indices travel through a stream-ordered allocation (the caller's array is pageable: its copy is staged before
     // cudaMemcpyAsync returns), the records are read in place by the gather kernel

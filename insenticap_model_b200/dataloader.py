@@ -149,14 +149,31 @@ class _Lazy:
         self.shard, self.idx, self.which = shard, idx, which
 
 
+class _Deferred:
+    """Features of a page-locked shard whose copies have not been issued yet: (shard, record indices, 'fc' | 'att').
+    ``DevicePrefetcher`` asks the collate for these (thread-local switch) so that the thread that runs the dataset / collate
+    Python is not the one that sits inside the per-record cudaMemcpyAsync loop for the whole DMA time."""
+    __slots__ = ("shard", "idx", "which")
+
+    def __init__(self, shard, idx, which):
+        self.shard, self.idx, self.which = shard, idx, which
+
+    def resolve(self):
+        fc, att = self.shard.copy_to_device(self.idx, want_fc=self.which == "fc", want_att=self.which == "att")
+        return fc if self.which == "fc" else att
+
+
+_tls = threading.local()
+
+
 def _stack_features(feats):
     """The reference's ``torch.FloatTensor(np.array(feats))``; lazy references become one batched, threaded gather."""
     if feats and isinstance(feats[0], _Lazy):
         sh, which = feats[0].shard, feats[0].which
         # the direct path issues CUDA copies: only in the process that owns the CUDA context (not in a forked worker)
         if sh.direct_device is not None and torch.utils.data.get_worker_info() is None:
-            fc, att = sh.copy_to_device([f.idx for f in feats], want_fc=which == "fc", want_att=which == "att")
-            return fc if which == "fc" else att
+            d = _Deferred(sh, [f.idx for f in feats], which)
+            return d if getattr(_tls, "defer_copies", False) else d.resolve()
         fc, att = sh.gather([f.idx for f in feats], want_fc=which == "fc", want_att=which == "att")
         return fc if which == "fc" else att
     return torch.from_numpy(np.array(feats, dtype=np.float32))
@@ -388,6 +405,8 @@ def get_senti_sents_dataloader(senti_sentences, pad_index, max_seq_len, batch_si
 
 
 def _to_device(x, dev):
+    if isinstance(x, _Deferred):
+        return x.resolve()  # copies queued on the current stream of the shard's device
     if torch.is_tensor(x):
         return x.to(dev, non_blocking=True)
     if isinstance(x, tuple) and not (x and isinstance(x[0], str)):
@@ -396,9 +415,11 @@ def _to_device(x, dev):
 
 
 class DevicePrefetcher:
-    """Iterate ``loader`` with ``depth`` batches in flight: a worker thread runs the loader (dataset reads + collate, i.e.
-    the shard gather into pinned memory) and issues the H2D copies on a private copy stream; the consumer's stream waits
-    on each batch's event, so the copies of batch i+1 overlap whatever the consumer does with batch i."""
+    """Iterate ``loader`` with ``depth`` batches in flight. Two worker threads: one runs the loader (dataset reads + collate,
+    i.e. the shard gather into pinned memory — or, for a page-locked shard, just the record indices), the other issues the
+    H2D copies on a private copy stream (a page-locked shard's per-record copies keep their issuing thread busy for the
+    whole DMA time: with one thread for both, the Python of batch i+1 waited for the copies of batch i). The consumer's
+    stream waits on each batch's event, so the copies of batch i+1 overlap whatever the consumer does with batch i."""
 
     def __init__(self, loader, device, depth=2):
         self.loader, self.device, self.depth = loader, torch.device(device), int(depth)
@@ -407,35 +428,52 @@ class DevicePrefetcher:
         return len(self.loader)
 
     def __iter__(self):
-        q = queue.Queue(maxsize=self.depth)
+        host_q = queue.Queue(maxsize=self.depth)  # collated host batches (features: pinned tensors or _Deferred)
+        q = queue.Queue(maxsize=self.depth)       # (device batch, host batch, copy event)
         stream = torch.cuda.Stream(self.device)
         stop = threading.Event()
 
-        def work():
+        def put(qq, item):
+            while not stop.is_set():
+                try:
+                    qq.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def collate_work():
             try:
-                it = iter(self.loader)
-                while True:
-                    with torch.cuda.stream(stream):  # a pinned shard's collate queues its copies on this stream too
-                        batch = next(it, None)
-                        if batch is None:
-                            break
+                _tls.defer_copies = True  # page-locked shards: leave the copies to copy_work
+                for batch in self.loader:
+                    if not put(host_q, batch):
+                        return
+                put(host_q, None)
+            except BaseException as e:  # surface loader errors in the consumer
+                put(host_q, e)
+
+        def copy_work():
+            try:
+                while not stop.is_set():
+                    try:
+                        batch = host_q.get(timeout=0.1)
+                    except queue.Empty:
+                        continue
+                    if batch is None or isinstance(batch, BaseException):
+                        put(q, batch)
+                        return
+                    with torch.cuda.stream(stream):
                         dev_batch = _to_device(batch, self.device)
                         ev = torch.cuda.Event()
                         ev.record(stream)
-                    while not stop.is_set():
-                        try:
-                            q.put((dev_batch, batch, ev), timeout=0.1)  # the host batch stays alive until its copy is done
-                            break
-                        except queue.Full:
-                            continue
-                    if stop.is_set():
+                    if not put(q, (dev_batch, batch, ev)):  # the host batch stays alive until its copy is done
                         return
-                q.put(None)
-            except BaseException as e:  # surface loader errors in the consumer
-                q.put(e)
+            except BaseException as e:
+                put(q, e)
 
-        th = threading.Thread(target=work, daemon=True)
-        th.start()
+        threads = [threading.Thread(target=collate_work, daemon=True), threading.Thread(target=copy_work, daemon=True)]
+        for th in threads:
+            th.start()
         try:
             while True:
                 item = q.get()
@@ -453,7 +491,8 @@ class DevicePrefetcher:
                 yield dev_batch
         finally:
             stop.set()
-            th.join(timeout=5)
+            for th in threads:
+                th.join(timeout=5)
 
 
 def _tensors(x):

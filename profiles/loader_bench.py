@@ -13,8 +13,8 @@ from insenticap_model_b200 import dataloader as dl  # noqa: E402
 from insenticap_model_b200 import synthetic as syn
 from insenticap_model_b200.captioner import Captioner
 
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
-B = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 V = 10000
 root = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
 d = tempfile.mkdtemp(dir=root)

@@ -1,5 +1,6 @@
 """Bandwidth and jitter of isc_shard_copy_to_device alone (page-locked fp16 shard, 512 shuffled records per call):
-the zero-copy gather kernel against one cudaMemcpyAsync per record (ISC_SHARD_MEMCPY=1). Usage: python profiles/shard_copy_bench.py [N] [B]"""
+one cudaMemcpyAsync per record (default) against the zero-copy gather kernel (ISC_SHARD_COPY=kernel).
+Usage: python profiles/shard_copy_bench.py [N] [B]"""
 import os
 import sys
 import tempfile
