@@ -1,6 +1,4 @@
 #!/bin/bash
 O=gpurun_out/r02/ab; mkdir -p $O
-timeout 600 python -m pytest tests/test_gpu_loader.py -m gpu -q -x 2>&1 | tail -2
-timeout 600 python profiles/loader_pipeline.py 4096 512 3 pin 2>&1 | grep -v Warning | grep "epoch [0-9]"
-timeout 600 python profiles/loader_pipeline.py 8192 512 3 pin 2>&1 | grep -v Warning | grep "epoch [0-9]"
-timeout 600 python profiles/loader_pipeline.py 4096 512 3 2>&1 | grep -v Warning | grep "epoch [0-9]"
+timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest.log
+timeout 900 python profiles/loader_bench.py 4096 512 > $O/loader_bench.log 2>&1; grep "shard(\|threads=16" $O/loader_bench.log

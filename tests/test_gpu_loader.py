@@ -121,3 +121,33 @@ def test_fp16_shard_is_the_fp32_computation_on_the_stored_values(corpus):
     if margin > 1e-5:
         assert np.array_equal(got[0].cpu().numpy(), tk_o.numpy())
         np.testing.assert_allclose(got[1].cpu().numpy(), sc_o.numpy(), atol=2e-4)
+
+
+def test_prefetcher_stops_early_and_surfaces_loader_errors(corpus):
+    """The two worker threads (collate, copy) end when the consumer leaves the loop early, and an exception raised inside
+    the loader (here: by the collate) reaches the consumer instead of hanging it."""
+    import threading
+    paths, meta = corpus
+    sh = dl.FeatureShard(paths["fp16"])
+    loader = dl.get_rl_senti_dataloader(sh, sh, meta["concepts"], meta["sentiments"], meta["labels"], 0, 5, 10, batch_size=4,
+                                        shuffle=False)
+    before = threading.active_count()
+    for i, batch in enumerate(dl.DevicePrefetcher(loader, "cuda:0", depth=2)):
+        assert batch[2].is_cuda and batch[2].dtype == torch.float16
+        if i == 1:
+            break
+    assert threading.active_count() <= before  # both workers joined
+
+    class Broken(torch.utils.data.Dataset):
+        def __len__(self):
+            return 8
+
+        def __getitem__(self, i):
+            if i == 5:
+                raise ValueError("broken item")
+            return torch.zeros(3)
+
+    bad = torch.utils.data.DataLoader(Broken(), batch_size=2)
+    with pytest.raises(ValueError, match="broken item"):
+        for _ in dl.DevicePrefetcher(bad, "cuda:0", depth=2):
+            pass
