@@ -205,6 +205,12 @@ int zero_pm(const PM& p, size_t rows, cudaStream_t s) {
   if (p.lo) ISC_CUDA(cudaMemsetAsync(p.lo, 0, rows * p.ld * sizeof(bf16), s));
   return 0;
 }
+// Transposed operand planes are contracted over pad8(valid_cols) columns: only the padding columns need zeros, so a plane
+// whose column count is a multiple of 8 (every one of them at the BASELINE sizes: T * B = 4096, B = 256, B * regions = 50176)
+// is not cleared before it is overwritten — that was ~0.3 GB of memset per backward call.
+int zero_pm_pad(const PM& p, size_t rows, long long valid_cols, cudaStream_t s) {
+  return valid_cols % 8 == 0 ? 0 : zero_pm(p, rows, s);
+}
 // fp32 [rows][cols] -> transposed planes [cols][ldT] at column col0
 int to_T(const float* src, long long ld, long long rows, int cols, const PM& dst, long long col0, cudaStream_t s) {
   return launch_split_transpose(src, ld, rows, cols, dst.hi, dst.lo, dst.ld, col0, s);
@@ -408,7 +414,7 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
   ISC_TRY(to_T(pk.W2.f32, H, 3 * H, H, w.W2T, 0, s));
   ISC_TRY(to_T(pk.W3.f32, 2 * H, H, 2 * H, w.W3T, 0, s));
   ISC_TRY(to_T(pk.W4.f32, 3 * H, G4, 3 * H, w.W4T, 0, s));
-  ISC_TRY(zero_pm(w.W5T, H, s));
+  ISC_TRY(zero_pm_pad(w.W5T, H, V, s));
   ISC_TRY(to_T(pk.W5.f32, H, V, H, w.W5T, 0, s));
   ISC_TRY(to_T(pk.Wpre.f32, 2 * H, G4, 2 * H, w.WpreT, 0, s));
   ISC_TRY(to_T(pk.Wl2w.f32, H, H, H, w.Wl2wT, 0, s));
@@ -430,14 +436,14 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     if (w.Vp != V) ISC_CUDA(zf(w.dlogits, (size_t)TM * w.Vp));  // pad columns must read as zero
     ISC_TRY(zero_pm(w.pdhproj, M, s));
 
-    ISC_TRY(zero_pm(w.dlogT, V, s));
-    ISC_TRY(zero_pm(w.dg1T, G4, s));
-    ISC_TRY(zero_pm(w.dg2T, G4, s));
-    ISC_TRY(zero_pm(w.dhprojT, 3 * H, s));
-    ISC_TRY(zero_pm(w.X1T, 3 * H, s));
-    ISC_TRY(zero_pm(w.X2T, 3 * H, s));
-    ISC_TRY(zero_pm(w.csT, 2 * H, s));
-    ISC_TRY(zero_pm(w.hLT, H, s));
+    ISC_TRY(zero_pm_pad(w.dlogT, V, TM, s));
+    ISC_TRY(zero_pm_pad(w.dg1T, G4, TM, s));
+    ISC_TRY(zero_pm_pad(w.dg2T, G4, TM, s));
+    ISC_TRY(zero_pm_pad(w.dhprojT, 3 * H, TM, s));
+    ISC_TRY(zero_pm_pad(w.X1T, 3 * H, TM, s));
+    ISC_TRY(zero_pm_pad(w.X2T, 3 * H, TM, s));
+    ISC_TRY(zero_pm_pad(w.csT, 2 * H, TM, s));
+    ISC_TRY(zero_pm_pad(w.hLT, H, TM, s));
 
     // ---- classifier backward for ALL steps at once (none of it depends on the recurrence): d logits from the
     // log-softmax backward, their planes (operand of d h_lang = d logits . W5) and transposed planes (operand of dW5)
@@ -570,11 +576,11 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
 
     // ---- hoisted step-invariant terms: pre_gates = [fc | sl] Wpre^T (+ biases, already covered by colsum(dg1))
     ISC_TRY(split_planes(w.dpre_gates, G4, w.pB4.hi, w.pB4.lo, G4, M, G4, s));
-    ISC_TRY(zero_pm(w.B4T, G4, s));
+    ISC_TRY(zero_pm_pad(w.B4T, G4, M, s));
     ISC_TRY(to_T(w.dpre_gates, G4, M, G4, w.B4T, 0, s));
     ISC_TRY(pgemm(precision, op_of(w.pB4), op_of(w.WpreT), w.dfcsl, 2 * H, M, 2 * H, G4, false, s));  // d [fc | sl]
-    ISC_TRY(zero_pm(w.fcT, H, s));
-    ISC_TRY(zero_pm(w.slT, H, s));
+    ISC_TRY(zero_pm_pad(w.fcT, H, M, s));
+    ISC_TRY(zero_pm_pad(w.slT, H, M, s));
     ISC_TRY(to_T(f.fc, H, M, H, w.fcT, 0, s));
     ISC_TRY(to_T(f.sl, H, M, H, w.slT, 0, s));
     ISC_TRY(pgemm(precision, op_of(w.B4T), op_of(w.fcT), g->att_lstm_w_ih + H, 3 * H, G4, H, Bk, true, s));
@@ -583,7 +589,7 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     const float* dsl_extra = nullptr;
     if (tm.sw) {  // label2word(sl), the label term of the sentiment-attention query
       ISC_TRY(launch_colsum_add(w.dpre_word, H, M, H, g->sa_label2word_b, nullptr, s));
-      ISC_TRY(zero_pm(w.tBT, H, s));
+      ISC_TRY(zero_pm_pad(w.tBT, H, M, s));
       ISC_TRY(to_T(w.dpre_word, H, M, H, w.tBT, 0, s));
       ISC_TRY(pgemm(precision, op_of(w.tBT), op_of(w.slT), g->sa_label2word_w, H, H, H, Bk, true, s));
       ISC_TRY(split_planes(w.dpre_word, H, w.ptB.hi, w.ptB.lo, H, M, H, s));
@@ -598,9 +604,9 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       ISC_TRY(launch_relu_mask_bwd(w.dfcsl, 2 * H, nullptr, 0, f.fc, H, 0, dropout ? dropout->fc : nullptr, H, dscale, M, H, w.tB1,
                                    H, RowDest(), s));
       ISC_TRY(launch_colsum_add(w.tB1, H, M, H, g->fc_embed_b, nullptr, s));
-      ISC_TRY(zero_pm(w.tBT, H, s));
+      ISC_TRY(zero_pm_pad(w.tBT, H, M, s));
       ISC_TRY(to_T(w.tB1, H, M, H, w.tBT, 0, s));
-      ISC_TRY(zero_pm(w.rawfcT, D, s));
+      ISC_TRY(zero_pm_pad(w.rawfcT, D, M, s));
       ISC_TRY(to_T(fc_feats, D, M, (int)D, w.rawfcT, 0, s));
       ISC_TRY(pgemm(precision, op_of(w.tBT), op_of(w.rawfcT), g->fc_embed_w, D, H, (int)D, Bk, true, s));
       // region features: p_att = ReLU(att2att(att)), att = dropout(ReLU(att_embed(raw)))
@@ -608,8 +614,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       ISC_TRY(launch_relu_mask_bwd(w.dp_att, H, nullptr, 0, static_cast<const float*>(f.p_att), H, 1, nullptr, 0, 1.f, BL, H, w.dz,
                                    H, rd_of(nullptr, 0, w.pdz), s));
       ISC_TRY(launch_colsum_add(w.dz, H, BL, H, g->att2att_b, nullptr, s));
-      ISC_TRY(zero_pm(w.dzT, H, s));
-      ISC_TRY(zero_pm(w.attT, H, s));
+      ISC_TRY(zero_pm_pad(w.dzT, H, BL, s));
+      ISC_TRY(zero_pm_pad(w.attT, H, BL, s));
       ISC_TRY(to_T(w.dz, H, BL, H, w.dzT, 0, s));
       ISC_TRY(to_T(static_cast<const float*>(f.att), H, BL, H, w.attT, 0, s));
       ISC_TRY(pgemm(precision, op_of(w.dzT), op_of(w.attT), g->att2att_w, H, H, H, (int)pad8(BL), true, s));
@@ -617,9 +623,9 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       ISC_TRY(launch_relu_mask_bwd(w.datt, H, w.datt2, H, static_cast<const float*>(f.att), H, 0, dropout ? dropout->att : nullptr, H,
                                    dscale, BL, H, w.dz, H, RowDest(), s));
       ISC_TRY(launch_colsum_add(w.dz, H, BL, H, g->att_embed_b, nullptr, s));
-      ISC_TRY(zero_pm(w.dzT, H, s));
+      ISC_TRY(zero_pm_pad(w.dzT, H, BL, s));
       ISC_TRY(to_T(w.dz, H, BL, H, w.dzT, 0, s));
-      ISC_TRY(zero_pm(w.rawT, D, s));
+      ISC_TRY(zero_pm_pad(w.rawT, D, BL, s));
       ISC_TRY(to_T(att_feats, D, BL, (int)D, w.rawT, 0, s));
       ISC_TRY(pgemm(precision, op_of(w.dzT), op_of(w.rawT), g->att_embed_w, D, H, (int)D, (int)pad8(BL), true, s));
     }
@@ -628,8 +634,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       const long long BS = (long long)M * S;
       ISC_TRY(launch_relu_mask_bwd(w.dp_sw, H, nullptr, 0, f.p_sw, H, 1, nullptr, 0, 1.f, BS, H, w.dz, H, rd_of(nullptr, 0, w.pdz), s));
       ISC_TRY(launch_colsum_add(w.dz, H, BS, H, g->senti2att_b, nullptr, s));
-      ISC_TRY(zero_pm(w.dzT, H, s));
-      ISC_TRY(zero_pm(w.attT, H, s));
+      ISC_TRY(zero_pm_pad(w.dzT, H, BS, s));
+      ISC_TRY(zero_pm_pad(w.attT, H, BS, s));
       ISC_TRY(to_T(w.dz, H, BS, H, w.dzT, 0, s));
       ISC_TRY(to_T(f.sw, H, BS, H, w.attT, 0, s));
       ISC_TRY(pgemm(precision, op_of(w.dzT), op_of(w.attT), g->senti2att_w, H, H, H, (int)pad8(BS), true, s));
@@ -655,8 +661,8 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
     }
     ISC_TRY(launch_relu_mask_bwd(a, H, nullptr, 0, w.f.cpt_feats, H, 0, nullptr, 0, 1.f, M, H, w.tB2, H, rd_of(nullptr, 0, w.ptB), s));
     ISC_TRY(launch_colsum_add(w.tB2, H, M, H, g->cpt2fc_b, nullptr, s));
-    ISC_TRY(zero_pm(w.tBT, H, s));
-    ISC_TRY(zero_pm(w.cptT, H, s));
+    ISC_TRY(zero_pm_pad(w.tBT, H, M, s));
+    ISC_TRY(zero_pm_pad(w.cptT, H, M, s));
     ISC_TRY(to_T(w.tB2, H, M, H, w.tBT, 0, s));
     ISC_TRY(to_T(w.cpt_mean, H, M, H, w.cptT, 0, s));
     ISC_TRY(pgemm(precision, op_of(w.tBT), op_of(w.cptT), g->cpt2fc_w, H, H, H, Bk, true, s));
