@@ -108,6 +108,11 @@ class _TeacherForced(torch.autograd.Function):
             targets, coef = call["fused"]
             loss = -(logprobs.gather(2, targets.unsqueeze(2)).squeeze(2) * coef).sum()
             return loss, fc_emb, cpt
+        if call.get("gather") is not None:
+            # REINFORCE form: only the log-probs of the given tokens leave the node, [B,T]; their gradient comes back as
+            # [B,T] too and the backward builds d logits from (tokens, -d out) — no dense [B,T,V] gradient (1.6 GB at
+            # 2560 rows) is created, zero-filled and scattered into by autograd
+            return logprobs.gather(2, call["gather"].unsqueeze(2)).squeeze(2), fc_emb, cpt
         return logprobs, fc_emb, cpt
 
     @staticmethod
@@ -143,6 +148,10 @@ class _TeacherForced(torch.autograd.Function):
             coef = (coef * dlogp).contiguous() if dlogp is not None else None  # dlogp is d loss_out here (a scalar)
             if coef is None:
                 targets = None
+            dlogp = None
+        elif call.get("gather") is not None:
+            targets = call["gather"] if dlogp is not None else None
+            coef = (-dlogp).contiguous() if dlogp is not None else None  # loss form: sum coef * (-logp[target])
             dlogp = None
         else:
             dlogp = dlogp.contiguous() if dlogp is not None else None
@@ -351,9 +360,10 @@ class Captioner(nn.Module):
         sd = dict(self.named_parameters())
         return [sd[name] for _, name in _lib.WEIGHT_FIELDS]
 
-    def _teacher_forced_train(self, mode, fc, att, cpt, sw, labels, inputs, ss_prob, fused=None):
+    def _teacher_forced_train(self, mode, fc, att, cpt, sw, labels, inputs, ss_prob, fused=None, gather=None):
         """Differentiable teacher forcing (autograd.Function over the C ABI). ``fused`` = (targets int64 [B,T],
-        coef fp32 [B,T]) makes the first result the scalar sum coef * (-logprobs[targets]) instead of the log-probs."""
+        coef fp32 [B,T]) makes the first result the scalar sum coef * (-logprobs[targets]) instead of the log-probs;
+        ``gather`` = tokens int64 [B,T] makes it logprobs[b, t, tokens[b, t]] ([B,T], sparse gradient)."""
         if self._prec != _lib.PREC_BF16X3:
             raise NotImplementedError("the backward pass runs in precision='bf16x3' only")
         dev = self._device()
@@ -375,7 +385,8 @@ class Captioner(nn.Module):
         if sw is not None:
             shapes["sw"] = (B, S, 512)
         call = dict(fc=fc, att=att, cpt=cpt, sw=sw, labels=labels, inputs=inputs.long().contiguous(), n_regions=L, n_senti=S,
-                    dropout=self._dropout_masks(shapes, n_steps, B), ss=ss, ss_keep=ss_keep, fused=fused)
+                    dropout=self._dropout_masks(shapes, n_steps, B), ss=ss, ss_keep=ss_keep, fused=fused,
+                    gather=gather.long().clone() if gather is not None else None)
         out, fc_emb, cpt_feats = _TeacherForced.apply(self, mode, call, *self._params_in_field_order())
         self.cont_weights = self.senti_weights = self.cont_senti_weights = []
         return out, fc_emb, (cpt_feats if cpt is not None else None), call
@@ -657,11 +668,12 @@ class Captioner(nn.Module):
                 out, self.fc_feats, self.cpt_feats, _ = self._teacher_forced_train(
                     _lib.MODE_RL, fc_feats.reshape(B, -1).float().contiguous(),
                     att_feats.reshape(B, -1, att_feats.shape[-1]).float().contiguous(), cpt_words.long().contiguous(),
-                    senti_words.reshape(B, -1).long().contiguous(), senti_labels.reshape(B).long().contiguous(), inputs, 0.0)
+                    senti_words.reshape(B, -1).long().contiguous(), senti_labels.reshape(B).long().contiguous(), inputs, 0.0,
+                    gather=seq)
             finally:
                 self.dropout_override = saved
             executed = seq_masks.sum(0, keepdim=True).gt(0).to(out.dtype)  # steps after the whole-batch stop never ran
-            lps = out.gather(2, seq.unsqueeze(2)).squeeze(2) * executed
+            lps = out * executed
         return seq, lps, masks_t
 
     def beam_search(self, fc_feats, att_feats, senti_words=None, senti_labels=None, beam_size=3,
