@@ -265,6 +265,21 @@ int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision,
                       const isc_sched_sampling_t* sched_sampling,
                       float* logprobs, float* fc_embedded, float* cpt_feats,
                       void* workspace, size_t workspace_bytes, isc_stream_t stream);
+/* isc_train_forward with the decoder FREE-RUNNING instead of teacher-forced: the sampled pass of Captioner.forward_rl
+ * (models/captioner.py:317-349, sample_max = 0) recorded on the tape, i.e. what models/decoder.py:86-88 runs under autograd.
+ * Step 0 is fed <SOS>; every step draws its token by Gumbel-max on the step's logits (sample_mode 1: noise [n_steps,B,V]
+ * given; 2: counter-based generator keyed by seed), writes seq / seq_logprobs / seq_masks [B,n_steps] with the bookkeeping
+ * of isc_decode_greedy (mask column = unfinished, token *= unfinished, log-prob unmasked, columns after the step at which
+ * every row has finished stay zero) and feeds the token to the next step. logprobs [B,n_steps,V] and the workspace then
+ * hold the tape of exactly those tokens: isc_train_backward is called with inputs = [<SOS>, seq[:, :-1]], targets = seq.
+ * One pass instead of a sampling decode followed by a teacher-forced re-scoring of its tokens. */
+int isc_train_forward_sample(const isc_dims_t* dims, const void* packed, int precision, int mode,
+                             const float* fc_feats, const float* att_feats, const int64_t* cpt_words, int n_cpt,
+                             const int64_t* senti_words, const int64_t* senti_labels, int B, int n_steps,
+                             const isc_dropout_t* dropout, int sample_mode, const float* noise, uint64_t seed,
+                             int64_t* seq, float* seq_logprobs, float* seq_masks,
+                             float* logprobs, float* fc_embedded, float* cpt_feats,
+                             void* workspace, size_t workspace_bytes, isc_stream_t stream);
 int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision, int mode,
                        const float* fc_feats, const float* att_feats, const int64_t* cpt_words, int n_cpt,
                        const int64_t* senti_words, const int64_t* senti_labels, int B,

@@ -102,6 +102,8 @@ SIGNATURES = {
     "isc_train_workspace_bytes": (_sz, [_PD, C.c_int, C.c_int, C.c_int]),
     "isc_train_forward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,
                                     _PDR, C.POINTER(SchedSampling), _vp, _vp, _vp, _vp, _sz, _vp]),
+    "isc_train_forward_sample": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                           _PDR, C.c_int, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "isc_expand_f16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "isc_train_backward_marks": (C.c_int, [_vp, _vp]),
     "isc_train_backward": (C.c_int, [_PD, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _i64, C.c_int,

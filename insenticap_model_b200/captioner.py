@@ -79,7 +79,11 @@ class _TeacherForced(torch.autograd.Function):
         lib = _lib.load()
         dev = model._device()
         packed = model.pack_weights()
-        B, n_steps = call["inputs"].shape[0], call["inputs"].shape[1] - 1
+        smp = call.get("sample")  # free-running sampled pass recorded on the tape (isc_train_forward_sample)
+        if smp is not None:
+            B, n_steps = call["fc"].shape[0], int(smp["n_steps"])
+        else:
+            B, n_steps = call["inputs"].shape[0], call["inputs"].shape[1] - 1
         d = model._dims(call["n_regions"], call["n_senti"])
         nbytes = lib.isc_train_workspace_bytes(C.byref(d), model._prec, B, n_steps)
         if nbytes == 0:
@@ -90,6 +94,27 @@ class _TeacherForced(torch.autograd.Function):
         fc_emb = torch.zeros(B, 512, **f32)
         cpt = torch.zeros(B, 512, **f32)
         drop = model._dropout_struct(call["dropout"])
+        if smp is not None:
+            seq = torch.empty(B, n_steps, dtype=torch.long, device=dev)
+            seq_lp = torch.empty(B, n_steps, **f32)
+            seq_masks = torch.empty(B, n_steps, **f32)
+            noise = smp.get("noise")
+            with torch.cuda.device(dev):
+                _lib.check(lib.isc_train_forward_sample(
+                    C.byref(d), _lib.ptr(packed), model._prec, mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
+                    _lib.ptr(call["cpt"]), call["cpt"].shape[1] if call["cpt"] is not None else 0, _lib.ptr(call["sw"]),
+                    _lib.ptr(call["labels"]), B, n_steps, C.byref(drop) if call["dropout"] else None,
+                    1 if noise is not None else 2, _lib.ptr(noise), int(smp.get("seed") or 0), _lib.ptr(seq), _lib.ptr(seq_lp),
+                    _lib.ptr(seq_masks), _lib.ptr(logprobs), _lib.ptr(fc_emb), _lib.ptr(cpt) if call["cpt"] is not None else None,
+                    _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "isc_train_forward_sample")
+            sos = torch.full((B, 1), model.sos_id, dtype=torch.long, device=dev)
+            call["inputs"] = torch.cat([sos, seq], dim=1)  # what the tape was fed: [<SOS>, seq[:, :-1]] (+ one unused column)
+            call["gather"] = seq
+            ctx.model, ctx.mode, ctx.call, ctx.ws, ctx.dims, ctx.packed = model, mode, call, ws, d, packed
+            ctx.save_for_backward(logprobs)
+            ctx.param_shapes = [p.shape for p in params]
+            ctx.mark_non_differentiable(fc_emb, seq, seq_masks)
+            return logprobs.gather(2, seq.unsqueeze(2)).squeeze(2), fc_emb, cpt, seq, seq_masks
         with torch.cuda.device(dev):
             _lib.check(lib.isc_train_forward(
                 C.byref(d), _lib.ptr(packed), model._prec, mode, _lib.ptr(call["fc"]), _lib.ptr(call["att"]),
@@ -116,7 +141,7 @@ class _TeacherForced(torch.autograd.Function):
         return logprobs, fc_emb, cpt
 
     @staticmethod
-    def backward(ctx, dlogp, _dfc, dcpt):
+    def backward(ctx, dlogp, _dfc, dcpt, *_unused):
         lib = _lib.load()
         model, call, d = ctx.model, ctx.call, ctx.dims
         dev = model._device()
@@ -224,6 +249,7 @@ class Captioner(nn.Module):
         self._ws = {}
         self.ss_override = None  # tests: {"uniform": [T,B], "noise": [T,B,V]} for scheduled sampling
         self.dropout_override = None  # tests: dict of uint8 keep masks {fc, att, sw, sl, out, scale}
+        self.fuse_sampled_tape = True  # forward_rl under autograd: sample on the training tape (one pass) instead of decode + re-score
         self.use_cuda_graph = False  # beam_search: capture the device-side call once and replay it
         # graph replay writes into the SAME output tensors every time; True returns copies (0.4 MB at B = 1024) so that a
         # caller may keep results across calls like with the reference, False hands out the graph's own buffers
@@ -616,6 +642,27 @@ class Captioner(nn.Module):
             B0, L0 = fc_feats.shape[0], att_feats.reshape(fc_feats.shape[0], -1, att_feats.shape[-1]).shape[1]
             masks = self._dropout_masks({"fc": (B0, 512), "sl": (B0, 512), "att": (B0, L0, 512),
                                          "sw": (B0, senti_words.reshape(B0, -1).shape[1] + 1, 512)}, int(max_seq_len), B0)
+        if with_grad and not self.collect_attention_weights and self.fuse_sampled_tape:
+            # REINFORCE's sampled pass (models/decoder.py:86-88 runs it under autograd) in ONE pass: the decoder runs free on
+            # the training tape (isc_train_forward_sample), so the tokens, their log-probs and the activations the backward
+            # needs come out together — no sampling decode followed by a teacher-forced re-scoring of its tokens
+            B0 = fc_feats.shape[0]
+            T = int(max_seq_len)
+            if noise is not None:
+                noise = noise.to(dev).float().contiguous()
+                assert noise.shape == (T, B0, self.vocab_size)
+            elif seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            att3 = att_feats.reshape(B0, -1, att_feats.shape[-1]).float().contiguous()
+            sw2 = senti_words.reshape(B0, -1).long().contiguous()
+            call = dict(fc=fc_feats.reshape(B0, -1).float().contiguous(), att=att3, cpt=cpt_words.long().contiguous(), sw=sw2,
+                        labels=senti_labels.reshape(B0).long().contiguous(), n_regions=att3.shape[1], n_senti=sw2.shape[1] + 1,
+                        dropout=masks, ss=None, fused=None, sample=dict(n_steps=T, noise=noise, seed=seed))
+            lps, self.fc_feats, self.cpt_feats, seq, seq_masks = _TeacherForced.apply(self, _lib.MODE_RL, call,
+                                                                                      *self._params_in_field_order())
+            self.cont_weights = self.senti_weights = self.cont_senti_weights = []
+            executed = seq_masks.sum(0, keepdim=True).gt(0).to(lps.dtype)  # steps after the whole-batch stop never ran
+            return seq, lps * executed, seq_masks
         t, B = self.prologue(fc_feats, att_feats, cpt_words, senti_words, senti_labels, dropout=masks)
         self.fc_feats, self.cpt_feats = t["fc"], t.get("cpt_feats")
         d = t["_dims"]

@@ -46,7 +46,10 @@ struct TrainWs {
   void* pro_ws;
   size_t pro_bytes;
   float* cpt_mean;  // inside pro_ws
-  long long* it;  // [T][M] tokens actually fed (ground truth, or scheduled-sampling draws)
+  long long* it;  // [T + 1][M] tokens actually fed (ground truth, scheduled-sampling draws, or the sampled tokens of
+                  // isc_train_forward_sample, whose last step writes row T)
+  int* unfinished;   // [M]     isc_train_forward_sample: rows still decoding
+  int* alive_count;  // [T_MAX] isc_train_forward_sample: unfinished rows after each step
   // tape
   float *state_h, *state_c;  // [T+1][2][M][H]
   PM pX1, pX2, pcs, phL;     // [T*M][.]
@@ -119,7 +122,9 @@ TrainWs carve_train(const isc_dims_t& d, int precision, int B, int T, void* base
   w.pro_ws = b.take<uint8_t>(w.pro_bytes);
   w.cpt_mean = base ? carve_prologue(d, precision, B, w.pro_ws).tmp : nullptr;
   const size_t tm = (size_t)T * m;
-  w.it = b.take<long long>(tm);
+  w.it = b.take<long long>(tm + m);
+  w.unfinished = b.take<int>(m);
+  w.alive_count = b.take<int>(T_MAX);
   w.state_h = b.take<float>((size_t)(T + 1) * 2 * m * H);
   w.state_c = b.take<float>((size_t)(T + 1) * 2 * m * H);
   pm(w.pX1, tm, 3 * H);
@@ -297,16 +302,29 @@ size_t isc_train_workspace_bytes(const isc_dims_t* dims, int precision, int B, i
   return carve_train(*dims, precision, B, n_steps, nullptr).total;
 }
 
-int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision, int mode, const float* fc_feats,
-                      const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
-                      const int64_t* senti_labels, int B, const int64_t* inputs, int64_t ld_inputs, int n_steps,
-                      const isc_dropout_t* dropout, const isc_sched_sampling_t* ss, float* logprobs, float* fc_embedded,
-                      float* cpt_feats, void* workspace, size_t workspace_bytes, isc_stream_t stream) {
+}  // extern "C"
+
+namespace {
+// isc_train_forward_sample: free-running sampling (Captioner.forward_rl :317-349) recorded on the tape
+struct SampleOut {
+  int sample_mode;            // 1 external noise, 2 counter-based Gumbel
+  const float* noise;         // [n_steps, B, V] (mode 1)
+  unsigned long long seed;
+  long long* seq;             // [B, n_steps]
+  float* seq_logprobs;        // [B, n_steps]
+  float* seq_masks;           // [B, n_steps]
+};
+
+int train_forward_impl(const isc_dims_t* dims, const void* packed, int precision, int mode, const float* fc_feats,
+                       const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
+                       const int64_t* senti_labels, int B, const int64_t* inputs, int64_t ld_inputs, int n_steps,
+                       const isc_dropout_t* dropout, const isc_sched_sampling_t* ss, const SampleOut* so, float* logprobs,
+                       float* fc_embedded, float* cpt_feats, void* workspace, size_t workspace_bytes, isc_stream_t stream) {
   ISC_TRY(check_device());
   ISC_TRY(check_dims(dims));
   ISC_REQUIRE(precision == ISC_PREC_BF16X3, "training runs in ISC_PREC_BF16X3 only");
   ISC_REQUIRE(mode == ISC_MODE_XE || mode == ISC_MODE_SEQ2SEQ || mode == ISC_MODE_RL, "unknown mode %d", mode);
-  ISC_REQUIRE(B > 0 && n_steps > 0 && n_steps <= T_MAX && inputs && logprobs && ld_inputs >= n_steps && senti_labels,
+  ISC_REQUIRE(B > 0 && n_steps > 0 && n_steps <= T_MAX && logprobs && senti_labels && (so || (inputs && ld_inputs >= n_steps)),
               "bad train_forward arguments");
   TrainWs w = carve_train(*dims, precision, B, n_steps, workspace);
   if (!workspace || workspace_bytes < w.total) {
@@ -330,9 +348,18 @@ int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision,
   ISC_CUDA(cudaMemsetAsync(w.state_h, 0, st, c.s));
   ISC_CUDA(cudaMemsetAsync(w.state_c, 0, st, c.s));
   const long long V = dims->vocab, L = dims->n_regions, S = dims->n_senti;
+  if (so) {
+    ISC_CUDA(cudaMemsetAsync(so->seq, 0, (size_t)B * n_steps * sizeof(long long), c.s));
+    ISC_CUDA(cudaMemsetAsync(so->seq_logprobs, 0, (size_t)B * n_steps * sizeof(float), c.s));
+    ISC_CUDA(cudaMemsetAsync(so->seq_masks, 0, (size_t)B * n_steps * sizeof(float), c.s));
+    ISC_CUDA(cudaMemsetAsync(w.alive_count, 0, T_MAX * sizeof(int), c.s));
+    ISC_TRY(launch_greedy_init(w.it, w.unfinished, B, dims->sos_id, c.s));  // step 0 feeds <SOS>
+  }
   for (int t = 0; t < n_steps; ++t) {
     long long* it_t = w.it + (size_t)t * B;
-    if (ss && ss->prob > 0.f && ss->uniform && t >= 1) {
+    if (so) {
+      // fed token = what the previous step's selection wrote (it *= unfinished included)
+    } else if (ss && ss->prob > 0.f && ss->uniform && t >= 1) {
       ISC_TRY(launch_ss_select(logprobs + (long long)(t - 1) * V, (long long)n_steps * V,
                                reinterpret_cast<const long long*>(inputs) + t, ld_inputs, ss->uniform + (size_t)t * B, ss->prob,
                                ss->noise ? ss->noise + (size_t)t * B * V : nullptr, ss->seed, t, B, (int)V, it_t, c.s));
@@ -367,9 +394,63 @@ int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision,
       io.drop_scale = dropout->scale;
     }
     ISC_TRY(run_step(c, v, B, 1, io));
+    if (so) {  // the draw, its log-prob, the mask column and the next input, exactly as isc_decode_greedy forms them
+      GreedyParams g;
+      g.logits = io.logits;
+      g.ld = io.ld_logits;
+      g.B = B;
+      g.V = (int)V;
+      g.T = n_steps;
+      g.t = t;
+      g.sample_mode = so->sample_mode;
+      g.noise = so->noise ? so->noise + (long long)t * B * V : nullptr;
+      g.seed = so->seed;
+      g.eos_id = dims->eos_id;
+      g.it = w.it + (size_t)(t + 1) * B;
+      g.unfinished = w.unfinished;
+      g.alive_count = w.alive_count;
+      g.seq = so->seq;
+      g.seq_logprobs = so->seq_logprobs;
+      g.seq_masks = so->seq_masks;
+      ISC_TRY(launch_greedy_select(g, c.s));
+    }
     ISC_TRY(launch_log_softmax(io.logits, io.ld_logits, B, (int)V, c.s));
   }
   return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int isc_train_forward(const isc_dims_t* dims, const void* packed, int precision, int mode, const float* fc_feats,
+                      const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
+                      const int64_t* senti_labels, int B, const int64_t* inputs, int64_t ld_inputs, int n_steps,
+                      const isc_dropout_t* dropout, const isc_sched_sampling_t* ss, float* logprobs, float* fc_embedded,
+                      float* cpt_feats, void* workspace, size_t workspace_bytes, isc_stream_t stream) {
+  return train_forward_impl(dims, packed, precision, mode, fc_feats, att_feats, cpt_words, n_cpt, senti_words, senti_labels, B,
+                            inputs, ld_inputs, n_steps, dropout, ss, nullptr, logprobs, fc_embedded, cpt_feats, workspace,
+                            workspace_bytes, stream);
+}
+
+int isc_train_forward_sample(const isc_dims_t* dims, const void* packed, int precision, int mode, const float* fc_feats,
+                             const float* att_feats, const int64_t* cpt_words, int n_cpt, const int64_t* senti_words,
+                             const int64_t* senti_labels, int B, int n_steps, const isc_dropout_t* dropout, int sample_mode,
+                             const float* noise, uint64_t seed, int64_t* seq, float* seq_logprobs, float* seq_masks,
+                             float* logprobs, float* fc_embedded, float* cpt_feats, void* workspace, size_t workspace_bytes,
+                             isc_stream_t stream) {
+  ISC_REQUIRE(seq && seq_logprobs && seq_masks, "train_forward_sample: NULL output");
+  ISC_REQUIRE(sample_mode == 1 || sample_mode == 2, "train_forward_sample: sample_mode must be 1 (noise) or 2 (seed)");
+  ISC_REQUIRE(sample_mode != 1 || noise, "train_forward_sample: sample_mode 1 needs noise");
+  SampleOut so;
+  so.sample_mode = sample_mode;
+  so.noise = noise;
+  so.seed = seed;
+  so.seq = reinterpret_cast<long long*>(seq);
+  so.seq_logprobs = seq_logprobs;
+  so.seq_masks = seq_masks;
+  return train_forward_impl(dims, packed, precision, mode, fc_feats, att_feats, cpt_words, n_cpt, senti_words, senti_labels, B,
+                            nullptr, 0, n_steps, dropout, nullptr, &so, logprobs, fc_embedded, cpt_feats, workspace,
+                            workspace_bytes, stream);
 }
 
 int isc_train_backward_marks(void* event0, void* event1) {

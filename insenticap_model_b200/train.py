@@ -279,7 +279,13 @@ def rl_iteration(model, optim, scorer, batch, max_seq_len=16, seq2seq_batch=None
     R = int(samples_per_image)
     rep = (lambda x: x.repeat_interleave(R, dim=0)) if R > 1 else (lambda x: x)
     s_fns = [fn for fn in fns for _ in range(R)]
-    sample, sample_lp, seq_masks = model(rep(fc), rep(att), rep(cpts), rep(sentis), rep(labels), max_seq_len, 0, mode="rl")
+    # nobody reads the per-step attention weights here (Detector.forward does the same): without them the sampled pass runs
+    # once, on the training tape
+    collect, model.collect_attention_weights = model.collect_attention_weights, False
+    try:
+        sample, sample_lp, seq_masks = model(rep(fc), rep(att), rep(cpts), rep(sentis), rep(labels), max_seq_len, 0, mode="rl")
+    finally:
+        model.collect_attention_weights = collect
     da_loss = da_crit(model.cpt_feats, model.fc_feats.detach())
     was_training = model.training
     model.eval()

@@ -143,6 +143,7 @@ def test_rl_reinforce_backward_matches_oracle_autograd(dropout):
     T = 6
     masks = _masks("rl", T) if dropout else None
     m.train(dropout)
+    m.collect_attention_weights = False  # as Detector.forward / rl_iteration run it: the one-pass sampled tape
     m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()} if masks else None
     m.zero_grad()
     g = torch.Generator().manual_seed(9)
@@ -320,3 +321,34 @@ def test_fused_nll_equals_criterion_on_logprobs():
     for k in grads[0][1]:
         a, b = grads[0][1][k], grads[1][1][k]
         assert float((a - b).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-9, k
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_one_pass_sampled_tape_equals_decode_plus_rescoring(dropout):
+    """forward_rl under autograd runs the sampled pass once, on the training tape (isc_train_forward_sample); the older
+    two-pass form (isc_decode_greedy sampling, then a teacher-forced re-scoring of its tokens) must give the same tokens,
+    masks, log-probs and gradients for the same Gumbel noise and dropout masks."""
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    T = 6
+    masks = _masks("rl", T) if dropout else None
+    g = torch.Generator().manual_seed(21)
+    noise = -torch.log(-torch.log(torch.rand(T, B, V, generator=g).clamp_min(1e-9)))
+    rewards = torch.randn(B, T, generator=g).cuda()
+    res = []
+    for fused in (True, False):
+        m, _ = _model()
+        m.fuse_sampled_tape = fused
+        m.collect_attention_weights = False  # (with it on, both runs would take the two-pass form, which keeps the weights)
+        m.train(dropout)
+        m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()} if masks else None
+        m.zero_grad()
+        seq, lps, smask = m(fc.cuda(), att.cuda(), cpts.cuda(), sentis.cuda(), labels.cuda(), T, 0, mode="rl", noise=noise)
+        loss = -(lps * smask * rewards).sum() / smask.sum() + torch.nn.functional.mse_loss(m.cpt_feats, m.fc_feats.detach())
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((seq.cpu(), smask.cpu(), lps.detach().cpu(), float(loss), {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}))
+    (s1, k1, l1, f1, g1), (s2, k2, l2, f2, g2) = res
+    assert torch.equal(s1, s2) and torch.equal(k1, k2)
+    assert torch.allclose(l1, l2, rtol=1e-5, atol=1e-5) and abs(f1 - f2) <= 1e-5 * max(1.0, abs(f2))
+    for k in g1:
+        assert torch.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-6), k
