@@ -52,6 +52,13 @@ typedef struct isc_dims {
   int32_t n_senti;    /* 11 = 10 sentiment words + the prepended PAD (captioner.py:307-309) */
   int32_t n_labels;   /* 3 sentiment categories */
   int32_t pad_id, sos_id, eos_id, unk_id; /* captioner.py:125-128 */
+  /* Tiled batches (0 or 1: none). R > 1: every R consecutive batch rows are the same image — the SCST sampled pass with R
+   * samples per image — and att_feats holds B / R images, [B/R, n_regions, feat_dim]: ReLU(att_embed(.)) is computed once
+   * per image and expanded to the B rows under each row's own dropout mask (exactly what the reference computes on the
+   * tiled tensor), and its weight gradient contracts over B/R images after the tiles' gradients have been summed. Every
+   * other per-row input (fc_feats, words, labels) stays tiled. Honoured by isc_prologue, isc_train_forward(_sample) and
+   * isc_train_backward in ISC_PREC_FP32 / ISC_PREC_BF16X3. */
+  int32_t att_tile;
 } isc_dims_t;
 
 /* fp32 parameters, one pointer per tensor of Captioner.state_dict() (captioner.py:121-161). */

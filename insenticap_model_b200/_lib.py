@@ -19,7 +19,7 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("vocab", "hidden", "feat_dim", "n_regions", "n_senti", "n_labels",
-                 "pad_id", "sos_id", "eos_id", "unk_id")]
+                 "pad_id", "sos_id", "eos_id", "unk_id", "att_tile")]
 
 
 WEIGHT_FIELDS = [

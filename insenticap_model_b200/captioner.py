@@ -84,7 +84,7 @@ class _TeacherForced(torch.autograd.Function):
             B, n_steps = call["fc"].shape[0], int(smp["n_steps"])
         else:
             B, n_steps = call["inputs"].shape[0], call["inputs"].shape[1] - 1
-        d = model._dims(call["n_regions"], call["n_senti"])
+        d = model._dims(call["n_regions"], call["n_senti"], call.get("att_tile", 1))
         nbytes = lib.isc_train_workspace_bytes(C.byref(d), model._prec, B, n_steps)
         if nbytes == 0:
             _lib.check(-1, "isc_train_workspace_bytes")
@@ -276,10 +276,10 @@ class Captioner(nn.Module):
                                "kernels, move the module to a B200 (`.cuda()`); there is no CPU fallback" % dev)
         return dev
 
-    def _dims(self, n_regions=None, n_senti=None):
+    def _dims(self, n_regions=None, n_senti=None, att_tile=1):
         return _lib.Dims(self.vocab_size, 512, self.settings["att_feat_dim"],
                          n_regions or self.n_regions, n_senti or (self.num_senti_words + 1), self.n_labels,
-                         self.pad_id, self.sos_id, self.eos_id, self.unk_id)
+                         self.pad_id, self.sos_id, self.eos_id, self.unk_id, int(att_tile))
 
     def _workspace(self, kind, nbytes, dev):
         key = (kind, dev.index)
@@ -628,8 +628,13 @@ class Captioner(nn.Module):
         return self._teacher_forced(t, B, senti_captions)
 
     def forward_rl(self, fc_feats, att_feats, cpt_words, senti_words, senti_labels, max_seq_len, sample_max,
-                   noise=None, seed=None):
+                   noise=None, seed=None, att_tile=1):
         """Batched greedy (sample_max=1) or sampled (sample_max=0) decode (captioner.py:290-349).
+
+        ``att_tile`` = R > 1 (additive): the batch is TILED — every R consecutive rows of fc_feats / words / labels are the
+        same image (SCST with R samples per image) — and ``att_feats`` holds the B / R images once, [B/R, 14, 14, D]. The
+        result is what the reference computes on ``att_feats.repeat_interleave(R, 0)``; under autograd the region embedding
+        and its weight gradient are then computed once per image instead of once per row (isc_dims_t::att_tile).
 
         Sampling is Gumbel-max: argmax(logprobs + g). ``noise`` [T,B,V] supplies g explicitly (parity
         tests); otherwise g comes from a counter-based generator keyed by ``seed`` (drawn from torch's
@@ -637,9 +642,12 @@ class Captioner(nn.Module):
         dev = self._device()
         lib = _lib.load()
         with_grad = self._needs_grad() and torch.is_grad_enabled() and not sample_max
+        R = int(att_tile)
+        if R > 1 and not (with_grad and not self.collect_attention_weights and self.fuse_sampled_tape):
+            att_feats, R = att_feats.repeat_interleave(R, dim=0), 1  # every other path takes the tiled tensor itself
         masks = None
         if with_grad or (self.training and float(self.settings["dropout_p"]) > 0.0) or self.dropout_override is not None:
-            B0, L0 = fc_feats.shape[0], att_feats.reshape(fc_feats.shape[0], -1, att_feats.shape[-1]).shape[1]
+            B0, L0 = fc_feats.shape[0], att_feats.reshape(att_feats.shape[0], -1, att_feats.shape[-1]).shape[1]
             masks = self._dropout_masks({"fc": (B0, 512), "sl": (B0, 512), "att": (B0, L0, 512),
                                          "sw": (B0, senti_words.reshape(B0, -1).shape[1] + 1, 512)}, int(max_seq_len), B0)
         if with_grad and not self.collect_attention_weights and self.fuse_sampled_tape:
@@ -653,11 +661,12 @@ class Captioner(nn.Module):
                 assert noise.shape == (T, B0, self.vocab_size)
             elif seed is None:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-            att3 = att_feats.reshape(B0, -1, att_feats.shape[-1]).float().contiguous()
+            assert B0 % R == 0 and att_feats.shape[0] * R == B0, "att_tile: att_feats must hold B / att_tile images"
+            att3 = att_feats.reshape(B0 // R, -1, att_feats.shape[-1]).float().contiguous()
             sw2 = senti_words.reshape(B0, -1).long().contiguous()
             call = dict(fc=fc_feats.reshape(B0, -1).float().contiguous(), att=att3, cpt=cpt_words.long().contiguous(), sw=sw2,
                         labels=senti_labels.reshape(B0).long().contiguous(), n_regions=att3.shape[1], n_senti=sw2.shape[1] + 1,
-                        dropout=masks, ss=None, fused=None, sample=dict(n_steps=T, noise=noise, seed=seed))
+                        dropout=masks, ss=None, fused=None, sample=dict(n_steps=T, noise=noise, seed=seed), att_tile=R)
             lps, self.fc_feats, self.cpt_feats, seq, seq_masks = _TeacherForced.apply(self, _lib.MODE_RL, call,
                                                                                       *self._params_in_field_order())
             self.cont_weights = self.senti_weights = self.cont_senti_weights = []

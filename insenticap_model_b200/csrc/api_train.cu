@@ -703,12 +703,23 @@ int isc_train_backward(const isc_dims_t* dims, const void* packed, int precision
       ISC_TRY(pgemm(precision, op_of(w.pdz), op_of(w.Wa2aT), w.datt2, H, (int)BL, H, H, false, s));
       ISC_TRY(launch_relu_mask_bwd(w.datt, H, w.datt2, H, static_cast<const float*>(f.att), H, 0, dropout ? dropout->att : nullptr, H,
                                    dscale, BL, H, w.dz, H, RowDest(), s));
-      ISC_TRY(launch_colsum_add(w.dz, H, BL, H, g->att_embed_b, nullptr, s));
-      ISC_TRY(zero_pm_pad(w.dzT, H, BL, s));
-      ISC_TRY(to_T(w.dz, H, BL, H, w.dzT, 0, s));
-      ISC_TRY(zero_pm_pad(w.rawT, D, BL, s));
-      ISC_TRY(to_T(att_feats, D, BL, (int)D, w.rawT, 0, s));
-      ISC_TRY(pgemm(precision, op_of(w.dzT), op_of(w.rawT), g->att_embed_w, D, H, (int)D, (int)pad8(BL), true, s));
+      // tiled batch (dims->att_tile = R rows per image, att_feats holds M / R images): d att_embed_w = (sum of the R tiles'
+      // gradients)^T . raw — the tiles share raw, so they are summed before the contraction (and the raw transposes and the
+      // GEMM run over M / R images)
+      const int Rt = dims->att_tile > 1 ? dims->att_tile : 1;
+      ISC_REQUIRE(M % Rt == 0, "att_tile=%d does not divide B=%d", Rt, M);
+      const float* dzs = w.dz;
+      const long long BLi = BL / Rt;
+      if (Rt > 1) {
+        ISC_TRY(launch_sum_tiles(w.dz, Rt, L * H, M / Rt, w.datt2, s));  // datt2 was consumed by the pass above
+        dzs = w.datt2;
+      }
+      ISC_TRY(launch_colsum_add(dzs, H, BLi, H, g->att_embed_b, nullptr, s));
+      ISC_TRY(zero_pm_pad(w.dzT, H, BLi, s));
+      ISC_TRY(to_T(dzs, H, BLi, H, w.dzT, 0, s));
+      ISC_TRY(zero_pm_pad(w.rawT, D, BLi, s));
+      ISC_TRY(to_T(att_feats, D, BLi, (int)D, w.rawT, 0, s));
+      ISC_TRY(pgemm(precision, op_of(w.dzT), op_of(w.rawT), g->att_embed_w, D, H, (int)D, (int)pad8(BLi), true, s));
     }
     if (tm.sw) {
       // sentiment words: p_sw = ReLU(senti2att(sw)), sw = dropout(ReLU(word_embed([PAD | senti_words])))

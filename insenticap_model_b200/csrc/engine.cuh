@@ -33,6 +33,7 @@ int check_dims(const isc_dims_t* d) {
   ISC_REQUIRE(d->vocab >= 8 && d->vocab <= 65534, "vocab=%d out of range [8, 65534]", d->vocab);
   ISC_REQUIRE(d->feat_dim > 0 && d->feat_dim % 8 == 0, "feat_dim=%d must be a positive multiple of 8", d->feat_dim);
   ISC_REQUIRE(d->n_regions > 0 && d->n_senti > 0 && d->n_labels > 0, "n_regions/n_senti/n_labels must be positive");
+  ISC_REQUIRE(d->att_tile >= 0 && d->att_tile <= 64, "att_tile=%d out of range [0, 64]", d->att_tile);
   return 0;
 }
 int check_precision(int p) {
@@ -543,6 +544,7 @@ struct ProWs {
   bf16 *raw_hi, *raw_lo;  // [chunk*L, D] raw region features as planes
   bf16 *att_hi, *att_lo;  // [chunk*L, H]
   bf16 *fc_hi, *fc_lo;    // [B, D]
+  float* att_pre;         // [chunk*L, H] tiled batches: ReLU(att_embed) of a chunk's images, before expansion + dropout
   float* tmp;             // [B*S, H] scratch rows (cpt mean / sw)
   bf16 *tmp_hi, *tmp_lo;
   float* fcsl;
@@ -567,6 +569,7 @@ ProWs carve_prologue(const isc_dims_t& d, int precision, int B, void* base) {
     w.fc_hi = b.take<bf16>((size_t)B * d.feat_dim);
     if (x3) w.fc_lo = b.take<bf16>((size_t)B * d.feat_dim);
   }
+  if (d.att_tile > 1) w.att_pre = b.take<float>(rows * H);
   const size_t trow = (size_t)B * (d.n_senti > 1 ? d.n_senti : 1);
   w.tmp = b.take<float>(trow * H);
   if (tc) {
@@ -665,10 +668,15 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
     // planes fit the 126 MB L2). Running the fp32 -> bf16 plane split of chunk i+1 on a second stream beside the GEMMs
     // of chunk i was measured and gains nothing: both are bound by the same L2/HBM traffic.
     static const bool fused_split = getenv("ISC_PROLOGUE_SPLIT_KERNEL") == nullptr;  // set to use the separate split pass
-    for (int b0 = 0; b0 < B; b0 += w.chunk) {
-      const int nb = (B - b0 < w.chunk) ? (B - b0) : w.chunk;
-      const long long rows = (long long)nb * L;
-      const float* raw = att_feats + (long long)b0 * L * D;
+    const int R = dims->att_tile > 1 ? dims->att_tile : 1;  // tiled batch: R rows per image, att_feats holds B / R images
+    ISC_REQUIRE(R == 1 || (B % R == 0 && precision != ISC_PREC_BF16 && !raw_bf16 && w.att_pre && w.chunk >= R),
+                "att_tile=%d needs B %% att_tile == 0 (B=%d) and fp32 features", R, B);
+    const int chunk = R == 1 ? w.chunk : (w.chunk / R) * R;  // a chunk holds whole images' tiles
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+      const int nb = (B - b0 < chunk) ? (B - b0) : chunk;
+      const long long rows = (long long)nb * L;           // rows of the (tiled) feature tensors in this chunk
+      const long long rows_in = rows / R;                 // rows of the raw features behind them
+      const float* raw = att_feats + (long long)(b0 / R) * L * D;
       Planes praw;
       praw.hi = w.raw_hi;
       praw.lo = w.raw_lo;
@@ -692,9 +700,14 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
           patt.lo = w.att_lo;
         }
       }
+      float* att_out = dst.f32;
+      if (R > 1) {  // the GEMM writes the images' embedding once, the expansion below forms the tiled rows and their planes
+        dst.f32 = w.att_pre;
+        dst.hi = dst.lo = nullptr;
+      }
       const bool want16 = tc && out->p_att16 != nullptr;
       if (want16) {
-        ISC_REQUIRE(out->feat_flags && !drop, "out->p_att16 needs out->feat_flags (and no dropout)");
+        ISC_REQUIRE(out->feat_flags && !drop && R == 1, "out->p_att16 needs out->feat_flags (and no dropout, no tiling)");
         if (b0 == 0) ISC_CUDA(cudaMemsetAsync(out->feat_flags, 0, (size_t)B * sizeof(int), c.s));
         if (out->att16 && precision == ISC_PREC_BF16X3) {  // fp16(att) beside the fp32 tensor
           dst.h16.out = static_cast<__half*>(out->att16) + (long long)b0 * L * H;
@@ -710,12 +723,16 @@ int run_prologue(const isc_dims_t* dims, const void* packed, int precision, cons
         ISC_TRY(gemm_tc(operand(nullptr, 0, pin, D), pk.Watt.op(), dst, (int)rows, H, D, 1, ep, c.s));
       } else if (tc && fused_split) {
         // the fp32 region features go straight into the GEMM: its converter warps split them in shared memory
-        ISC_TRY(gemm_tc_af32(raw, D, pk.Watt.op(), dst, (int)rows, H, D, precision == ISC_PREC_BF16X3 ? 3 : 1, ep, c.s));
+        ISC_TRY(gemm_tc_af32(raw, D, pk.Watt.op(), dst, (int)rows_in, H, D, precision == ISC_PREC_BF16X3 ? 3 : 1, ep, c.s));
       } else {
-        if (tc) ISC_TRY(split_planes(raw, D, w.raw_hi, w.raw_lo, D, rows, D, c.s));
-        ISC_TRY(gemm(precision, operand(raw, D, praw, D), pk.Watt.op(), dst, (int)rows, H, D, ep, c.s));
+        if (tc) ISC_TRY(split_planes(raw, D, w.raw_hi, w.raw_lo, D, rows_in, D, c.s));
+        ISC_TRY(gemm(precision, operand(raw, D, praw, D), pk.Watt.op(), dst, (int)rows_in, H, D, ep, c.s));
       }
-      if (drop && drop->att) {
+      if (R > 1) {
+        ISC_TRY(launch_expand_mask(w.att_pre, R, (long long)L * H, nb, (drop && drop->att) ? drop->att + (long long)b0 * L * H : nullptr,
+                                   dscale, att_out, H, rowdest(nullptr, 0, patt, H), c.s));
+        dst.f32 = att_out;
+      } else if (drop && drop->att) {
         ISC_REQUIRE(dst.f32 != nullptr, "dropout needs fp32 features (ISC_PREC_FP32 / ISC_PREC_BF16X3)");
         ISC_TRY(launch_apply_mask(dst.f32, H, drop->att + (long long)b0 * L * H, dscale, rows, H, rowdest(nullptr, 0, patt, H),
                                   c.s));

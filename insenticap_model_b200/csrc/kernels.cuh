@@ -188,6 +188,9 @@ int launch_relu_mask_bwd(const float* a, long long ld_a, const float* b, long lo
                          float* out, long long ld_out, RowDest planes, cudaStream_t s);
 int launch_apply_mask(float* x, long long ld, const unsigned char* mask, float scale, long long rows, int cols, RowDest planes,
                       cudaStream_t s);
+int launch_expand_mask(const float* src, int R, long long per, long long n_dst_images, const unsigned char* mask, float scale,
+                       float* dst, int cols, RowDest planes, cudaStream_t s);
+int launch_sum_tiles(const float* src, int R, long long per, long long n_images, float* dst, cudaStream_t s);
 int launch_colsum_add(const float* src, long long ld, long long rows, int cols, float* dst, float* dst2, cudaStream_t s);
 int launch_sum_steps(const float* src, int T, long long stride_t, long long n, float* dst, cudaStream_t s);
 int launch_add2d(float* dst, long long ld_dst, const float* src, long long ld_src, long long rows, int cols, cudaStream_t s);

@@ -537,6 +537,38 @@ __global__ void apply_mask_kernel(float* __restrict__ x, long long ld, const uns
   }
 }
 
+// Tiled batches (isc_dims_t::att_tile = R: R consecutive rows share one image): dst row block b = src row block b / R,
+// times the row's own dropout mask (or unmasked when mask is null); dst is fp32 + planes. `per` = elements per image.
+__global__ void expand_mask_kernel(const float* __restrict__ src, int R, long long per, long long n_dst_images,
+                                   const unsigned char* __restrict__ mask, float scale, float* __restrict__ dst, int cols,
+                                   RowDest planes) {
+  const long long per4 = per >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_dst_images * per4; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per4, e = (i - b * per4) * 4;
+    float4 v = *reinterpret_cast<const float4*>(src + (b / R) * per + e);
+    if (mask) {
+      const uchar4 k = *reinterpret_cast<const uchar4*>(mask + b * per + e);
+      v.x *= k.x ? scale : 0.f; v.y *= k.y ? scale : 0.f; v.z *= k.z ? scale : 0.f; v.w *= k.w ? scale : 0.f;
+    }
+    *reinterpret_cast<float4*>(dst + b * per + e) = v;
+    const long long flat = b * per + e;
+    planes.store4(flat / cols, (int)(flat % cols), v);
+  }
+}
+// dst image i = sum of the R consecutive src images i * R .. i * R + R - 1 (in that order)
+__global__ void sum_tiles_kernel(const float* __restrict__ src, int R, long long per, long long n_images, float* __restrict__ dst) {
+  const long long per4 = per >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_images * per4; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / per4, e = (i - b * per4) * 4;
+    float4 a = *reinterpret_cast<const float4*>(src + (b * R) * per + e);
+    for (int r = 1; r < R; ++r) {
+      const float4 t = *reinterpret_cast<const float4*>(src + (b * R + r) * per + e);
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    *reinterpret_cast<float4*>(dst + b * per + e) = a;
+  }
+}
+
 // dst[c] += sum_r src[r, c]; a block sums 32 columns x up to 512 rows (8 row-lanes) and adds its partial atomically
 __global__ void __launch_bounds__(256) colsum_add_kernel(const float* __restrict__ src, long long ld, long long rows, int cols,
                                                          float* __restrict__ dst, float* __restrict__ dst2) {
@@ -752,6 +784,21 @@ int launch_apply_mask(float* x, long long ld, const unsigned char* mask, float s
   if (rows <= 0) return 0;
   ProfScope ps(ISC_K_TRAIN, (double)rows * cols * 9.0, s);
   apply_mask_kernel<<<grid_for(rows * (cols / 4)), 256, 0, s>>>(x, ld, mask, scale, rows, cols, planes);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_expand_mask(const float* src, int R, long long per, long long n_dst_images, const unsigned char* mask, float scale,
+                       float* dst, int cols, RowDest planes, cudaStream_t s) {
+  if (n_dst_images <= 0) return 0;
+  ProfScope ps(ISC_K_TRAIN, (double)n_dst_images * per * 9.0, s);
+  expand_mask_kernel<<<grid_for(n_dst_images * (per / 4)), 256, 0, s>>>(src, R, per, n_dst_images, mask, scale, dst, cols, planes);
+  ISC_LAUNCH_CHECK();
+  return 0;
+}
+int launch_sum_tiles(const float* src, int R, long long per, long long n_images, float* dst, cudaStream_t s) {
+  if (n_images <= 0) return 0;
+  ProfScope ps(ISC_K_TRAIN, (double)n_images * per * 4.0 * (R + 1), s);
+  sum_tiles_kernel<<<grid_for(n_images * (per / 4)), 256, 0, s>>>(src, R, per, n_images, dst);
   ISC_LAUNCH_CHECK();
   return 0;
 }

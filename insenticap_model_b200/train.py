@@ -283,7 +283,9 @@ def rl_iteration(model, optim, scorer, batch, max_seq_len=16, seq2seq_batch=None
     # once, on the training tape
     collect, model.collect_attention_weights = model.collect_attention_weights, False
     try:
-        sample, sample_lp, seq_masks = model(rep(fc), rep(att), rep(cpts), rep(sentis), rep(labels), max_seq_len, 0, mode="rl")
+        # the tiles share their image's region features: att goes in once per image (att_tile), every other input tiled
+        sample, sample_lp, seq_masks = model(rep(fc), att, rep(cpts), rep(sentis), rep(labels), max_seq_len, 0, mode="rl",
+                                             att_tile=R)
     finally:
         model.collect_attention_weights = collect
     da_loss = da_crit(model.cpt_feats, model.fc_feats.detach())

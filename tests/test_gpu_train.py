@@ -352,3 +352,38 @@ def test_one_pass_sampled_tape_equals_decode_plus_rescoring(dropout):
     assert torch.allclose(l1, l2, rtol=1e-5, atol=1e-5) and abs(f1 - f2) <= 1e-5 * max(1.0, abs(f2))
     for k in g1:
         assert torch.allclose(g1[k], g2[k], rtol=1e-4, atol=1e-6), k
+
+
+@pytest.mark.parametrize("dropout", [False, True])
+def test_tiled_sampled_pass_shares_region_features(dropout):
+    """forward_rl(att_tile=R): R consecutive rows are the same image and att_feats holds the images once. Tokens, masks,
+    log-probs and every gradient must equal the run on the explicitly tiled tensor (att_feats.repeat_interleave(R)) with the
+    same per-row dropout masks and Gumbel noise — the region embedding is computed once per image, its weight gradient
+    contracts over the images after the tiles' gradients were summed (isc_dims_t::att_tile)."""
+    fc, att, cpts, sentis, labels, caps, lengths = _inputs()
+    R, T = 2, 5
+    n_img = B // R
+    rep = lambda x: x[:n_img].repeat_interleave(R, dim=0)
+    masks = _masks("rl", T) if dropout else None
+    g = torch.Generator().manual_seed(33)
+    noise = -torch.log(-torch.log(torch.rand(T, B, V, generator=g).clamp_min(1e-9)))
+    rewards = torch.randn(B, T, generator=g).cuda()
+    res = []
+    for tiled_arg in (True, False):
+        m, _ = _model()
+        m.collect_attention_weights = False
+        m.train(dropout)
+        m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()} if masks else None
+        m.zero_grad()
+        a = att[:n_img].cuda() if tiled_arg else rep(att).cuda()
+        seq, lps, smask = m(rep(fc).cuda(), a, rep(cpts).cuda(), rep(sentis).cuda(), rep(labels).cuda(), T, 0, mode="rl",
+                            noise=noise, att_tile=R if tiled_arg else 1)
+        loss = -(lps * smask * rewards).sum() / smask.sum() + torch.nn.functional.mse_loss(m.cpt_feats, m.fc_feats.detach())
+        loss.backward()
+        torch.cuda.synchronize()
+        res.append((seq.cpu(), smask.cpu(), lps.detach().cpu(), float(loss), {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}))
+    (s1, k1, l1, f1, g1), (s2, k2, l2, f2, g2) = res
+    assert torch.equal(s1, s2) and torch.equal(k1, k2)
+    assert torch.allclose(l1, l2, rtol=1e-5, atol=1e-5) and abs(f1 - f2) <= 1e-5 * max(1.0, abs(f2))
+    for k in g1:
+        assert torch.allclose(g1[k], g2[k], rtol=2e-4, atol=2e-6), (k, (g1[k] - g2[k]).abs().max().item())
