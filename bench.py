@@ -280,6 +280,41 @@ def train_block(dev, world, rank, rows=256, iters=3):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         out["replicas_in_sync"] = bool((hi - lo).abs().item() == 0.0)
+    # BASELINE configs[3]: one SCST iteration — 512 images per GPU x (5 sampled + 1 greedy decode), CIDEr-D reward on the
+    # device, REINFORCE + XE + seq2seq + DA losses, backward, the same all-reduce, clamp + Adam
+    try:
+        from insenticap_model_b200 import reward as R
+        n_img, spi = 512, 5
+        gi = torch.Generator(device=dev).manual_seed(200 + rank)
+        fc2 = torch.rand(n_img, 2048, device=dev, generator=gi)
+        att2 = torch.rand(n_img, 14, 14, 2048, device=dev, generator=gi)
+        cp2 = torch.randint(4, V, (n_img, 5), device=dev, generator=gi)
+        se2 = torch.randint(4, V, (n_img, 10), device=dev, generator=gi)
+        la2 = (torch.arange(n_img, device=dev) % 3).long()
+        ca2 = torch.randint(4, V, (n_img, T + 1), device=dev, generator=gi)
+        ca2[:, 0] = 1
+        refs = syn.synthetic_references(n_img, V, 5, seed=3 + rank)
+        fns = ["img%d" % i for i in range(n_img)]
+        gts = {fn: refs[i] for i, fn in enumerate(fns)}
+        scorer = R.get_ciderd_scorer({"train": gts}, 1, 2, device=dev)
+        scorer.register_ground_truth(fns, gts, 1, 2)
+        rl_batch = (fns, fc2, att2, ca2, [T] * n_img, cp2, se2, la2, gts)
+        rl_s2s = (ca2, [T] * n_img, cp2, se2, la2)
+        step = lambda: TR.rl_iteration(m, optim, scorer, rl_batch, max_seq_len=T, seq2seq_batch=rl_s2s, samples_per_image=spi)
+        for _ in range(2):
+            step()
+        sync()
+        e0.record()
+        for _ in range(iters):
+            step()
+        e1.record()
+        sync()
+        rl_ms = vmax(e0.elapsed_time(e1) / iters)
+        out["scst"] = {"workload": "SCST iteration: %d images/GPU x (%d sampled + 1 greedy decode), device CIDEr-D reward, "
+                                   "REINFORCE + XE + seq2seq + DA, backward, all-reduce, clamp + Adam" % (n_img, spi),
+                       "iteration_ms": rl_ms, "decoded_rows_per_s": world * n_img * (spi + 1) / (rl_ms * 1e-3)}
+    except Exception as e:  # auxiliary: keep the XE figures
+        out["scst"] = {"error": repr(e)[:300]}
     del m, optim
     torch.cuda.empty_cache()
     return out
