@@ -369,9 +369,9 @@ def test_tiled_sampled_pass_shares_region_features(dropout):
     noise = -torch.log(-torch.log(torch.rand(T, B, V, generator=g).clamp_min(1e-9)))
     rewards = torch.randn(B, T, generator=g).cuda()
     res = []
-    for tiled_arg in (True, False):
+    for tiled_arg in (True, False, "two-pass"):  # the last: att_tile on the two-pass form, which expands att_feats itself
         m, _ = _model()
-        m.collect_attention_weights = False
+        m.collect_attention_weights = tiled_arg == "two-pass"
         m.train(dropout)
         m.dropout_override = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in masks.items()} if masks else None
         m.zero_grad()
@@ -382,8 +382,9 @@ def test_tiled_sampled_pass_shares_region_features(dropout):
         loss.backward()
         torch.cuda.synchronize()
         res.append((seq.cpu(), smask.cpu(), lps.detach().cpu(), float(loss), {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}))
-    (s1, k1, l1, f1, g1), (s2, k2, l2, f2, g2) = res
-    assert torch.equal(s1, s2) and torch.equal(k1, k2)
-    assert torch.allclose(l1, l2, rtol=1e-5, atol=1e-5) and abs(f1 - f2) <= 1e-5 * max(1.0, abs(f2))
-    for k in g1:
-        assert torch.allclose(g1[k], g2[k], rtol=2e-4, atol=2e-6), (k, (g1[k] - g2[k]).abs().max().item())
+    s2, k2, l2, f2, g2 = res[1]
+    for s1, k1, l1, f1, g1 in (res[0], res[2]):
+        assert torch.equal(s1, s2) and torch.equal(k1, k2)
+        assert torch.allclose(l1, l2, rtol=1e-5, atol=1e-5) and abs(f1 - f2) <= 1e-5 * max(1.0, abs(f2))
+        for k in g1:
+            assert torch.allclose(g1[k], g2[k], rtol=2e-4, atol=2e-6), (k, (g1[k] - g2[k]).abs().max().item())
