@@ -167,3 +167,31 @@ def test_loader_factories_cover_every_item(shard):
     assert caps.shape == (9, min(16, max(len(c) for _, c in sents))) and lengths[0] == caps.shape[1]
     eager = dl.CaptionDataset(p, p, it["captions"], it["concepts"], lazy=False)[0]  # reference-style item: numpy features
     assert isinstance(eager[1], np.ndarray) and eager[2].shape == (2, 2, 8)
+
+
+def test_page_locked_shard_collate_defers_its_copies_for_the_prefetcher(shard, monkeypatch):
+    """A page-locked shard's collate issues its device copies itself — except inside DevicePrefetcher's collate thread
+    (thread-local switch), where it leaves `_Deferred(shard, record indices, which)` placeholders for the copy thread:
+    the record order, the rest of the batch and the placeholder's target are what the direct path would have copied."""
+    it = syn.loader_items()
+    fn = dl.create_collate_fn("rl_senti", pad_index=0, num_concepts=5, num_sentiments=10)
+    items = _items(it, "rl_senti", shard)
+    want = fn(_items(it, "rl_senti", shard))  # staged path: pinned / pageable host tensors
+    calls = []
+    monkeypatch.setattr(shard, "direct_device", torch.device("cpu"), raising=False)  # stands in for pin(): no GPU here
+    monkeypatch.setattr(shard, "copy_to_device",
+                        lambda idx, want_fc=True, want_att=True: calls.append((list(idx), want_fc, want_att)) or
+                        shard.gather(idx, want_fc=want_fc, want_att=want_att, pin=False), raising=False)
+    dl._tls.defer_copies = True
+    try:
+        got = fn(items)
+    finally:
+        dl._tls.defer_copies = False
+    assert isinstance(got[1], dl._Deferred) and isinstance(got[2], dl._Deferred) and not calls  # nothing copied yet
+    assert (got[1].which, got[2].which) == ("fc", "att") and got[1].idx == got[2].idx == [shard.index(f) for f in got[0]]
+    assert got[0] == want[0] and all(torch.equal(a, b) for a, b in zip(got[3:], want[3:]))
+    fc, att = got[1].resolve(), got[2].resolve()
+    assert calls == [(got[1].idx, True, False), (got[1].idx, False, True)]
+    assert torch.equal(fc, want[1]) and torch.equal(att, want[2])
+    direct = fn(items)  # outside the prefetcher: copied at once
+    assert torch.is_tensor(direct[1]) and torch.equal(direct[2], want[2]) and len(calls) == 4
